@@ -1,0 +1,169 @@
+/* ladiff_b200 — C-ABI of the B200-native LaDiffCodec sampling path.
+ *
+ * The reference (haiciyang/LaDiffCodec) is pure PyTorch and has no FFI: its "operator API" is
+ * nn.Module.__call__ on the objects srcs/sample.py builds.  Each entry point below
+ * replaces one of those calls; the reference interface it stands in for is cited beside it
+ * (paths relative to the reference root).  INTEGRATION.md shows the ctypes stubs a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative LADIFF_ERR_* otherwise; ladiff_last_error()
+ *    gives the message (thread-local).  No exceptions cross the boundary.
+ *  - all tensor pointers are DEVICE pointers owned by the caller unless the parameter says "host";
+ *    fp32, contiguous, NCL exactly as the reference passes them ([B,C,L]); indices are int64.
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Calls only enqueue
+ *    work; they do not synchronise unless stated.
+ *  - `ws` is caller-owned scratch of at least ladiff_workspace_bytes() bytes, 1024-byte aligned.
+ *    The library allocates device memory only in ladiff_load_weight / ladiff_finalize.
+ *  - one handle == one `DiffAudioRep` (srcs/model.py:32).  Handles are independent; a handle must
+ *    not be used from two threads at once.
+ */
+#ifndef LADIFF_B200_H_
+#define LADIFF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LADIFF_OK 0
+#define LADIFF_ERR_ARG -1        /* bad argument / shape */
+#define LADIFF_ERR_STATE -2      /* call order (e.g. not finalized) */
+#define LADIFF_ERR_KEY -3        /* missing / unexpected / mis-shaped checkpoint key (strict load) */
+#define LADIFF_ERR_CUDA -4       /* CUDA runtime / driver error */
+#define LADIFF_ERR_UNSUPPORTED -5 /* constructor flag outside the sampling path */
+#define LADIFF_ERR_WORKSPACE -6  /* workspace too small or misaligned */
+
+#define LADIFF_MAX_RATIOS 8
+
+/* Mirrors the keyword arguments of DiffAudioRep.__init__ (srcs/model.py:34) that shape the
+ * sampling path.  Flags the path does not support (use_film, self_condition, qtz_condition,
+ * unet_scale_x, run_vae, model_type != 'unet') are rejected in the Python host. */
+typedef struct LadiffConfig {
+  int32_t rep_dims;            /* 128 */
+  int32_t diff_dims;           /* 256 */
+  int32_t n_filters;           /* 32 */
+  int32_t lstm_layers;         /* 2 (0 = no LSTM) */
+  int32_t n_enc_ratios;        /* len(enc_ratios) */
+  int32_t enc_ratios[LADIFF_MAX_RATIOS];
+  int32_t quantization;        /* 1: has RVQ (the conditioning codec) */
+  int32_t n_q;                 /* quantizers built (model.py:65) */
+  int32_t n_q_used;            /* quantizers used by forward() at `bandwidth` (vq.py:86-98) */
+  int32_t run_diff;            /* 1: has Unet1D + GaussianDiffusion1D */
+  int32_t cond_channels;       /* 128 */
+  int32_t n_upsampling_ratios; /* len(upsampling_ratios); 0 = None */
+  int32_t upsampling_ratios[LADIFF_MAX_RATIOS];
+  int32_t unet_scale_cond;     /* per-sample max-abs scaling of the upsampled cond (unet.py:417) */
+  int32_t sample_rate;         /* 16000 */
+  int32_t reserved[8];
+} LadiffConfig;
+
+typedef struct LadiffHandle LadiffHandle;
+
+const char* ladiff_last_error(void);
+/* ABI version of this header; bump on any signature change. */
+int32_t ladiff_abi_version(void);
+
+/* DiffAudioRep(**kwargs)                                              srcs/model.py:34-106 */
+int32_t ladiff_create(const LadiffConfig* cfg, LadiffHandle** out);
+int32_t ladiff_destroy(LadiffHandle* h);
+
+/* load_model(model, path, strict=True) → model.load_state_dict        srcs/utils.py:98-108
+ * One call per state-dict entry, name exactly as stored (after stripping 'module.').  `data`
+ * may be a host or a device pointer (fp32, contiguous); the library copies it.  Keys that are
+ * not part of the layout for this config fail with LADIFF_ERR_KEY (strict). */
+int32_t ladiff_load_weight(LadiffHandle* h, const char* name, const float* data,
+                           const int64_t* shape, int32_t ndim);
+/* End of strict load: verifies every expected key arrived with the expected shape, then folds
+ * (weight-norm g*v/||v||, weight standardisation, time-MLP → FiLM table, bf16 K-major repack).
+ * Synchronises the device. */
+int32_t ladiff_finalize(LadiffHandle* h);
+/* Number of keys the strict layout expects (745 for the README LaDiff model, 148 for the codec). */
+int32_t ladiff_expected_keys(const LadiffHandle* h);
+int32_t ladiff_expected_key_at(const LadiffHandle* h, int32_t i, const char** name,
+                               int64_t* shape4, int32_t* ndim);
+
+/* Scratch needed by any call below for batch B and waveform length T (samples). */
+int64_t ladiff_workspace_bytes(const LadiffHandle* h, int32_t B, int32_t T);
+
+/* model_for_cond.get_cond(wav)                                         srcs/model.py:223-231
+ *   = SEANetEncoder (seanet.py:153) → ResidualVectorQuantizer.forward (vq.py:69-84).
+ * wav [B,1,T] → cond [B,rep_dims,T/hop]; codes [n_q_used,B,T/hop] int64 (optional, may be NULL);
+ * enc_out [B,rep_dims,T/hop] pre-quantisation encoder output (optional). */
+int32_t ladiff_get_cond(LadiffHandle* h, const float* wav, int32_t B, int32_t T, float* cond,
+                        int64_t* codes, float* enc_out, void* ws, int64_t ws_bytes, void* stream);
+
+/* model.encoder(x)                                                     srcs/modules/seanet.py:153 */
+int32_t ladiff_encode(LadiffHandle* h, const float* wav, int32_t B, int32_t T, float* z,
+                      void* ws, int64_t ws_bytes, void* stream);
+
+/* quantizer.decode(codes)  (codes-in wire format)  srcs/quantization/vq.py:109-113, core_vq.py:356-362
+ * codes [n_q,B,F] int64 → quantized [B,rep_dims,F]. */
+int32_t ladiff_rvq_decode(LadiffHandle* h, const int64_t* codes, int32_t n_q, int32_t B, int32_t F,
+                          float* quantized, void* stream);
+/* quantizer.encode(z) / forward(z): z [B,D,F] → codes [n_q,B,F], quantized [B,D,F] (either may be NULL) */
+int32_t ladiff_rvq_encode(LadiffHandle* h, const float* z, int32_t n_q, int32_t B, int32_t F,
+                          int64_t* codes, float* quantized, void* stream);
+
+/* model.diff_model.upsampling_layers[i](x)                             srcs/modules/unet.py:372-377,
+ *   SConvTranspose1d(causal=False)                                     srcs/modules/conv.py:252-274
+ * x [B,C,Lin] → y [B,C,Lin*ratio_i]. */
+int32_t ladiff_upsample_layer(LadiffHandle* h, int32_t i, const float* x, int32_t B, int32_t Lin,
+                              float* y, void* stream);
+
+/* model.diff_model(x, time, x_cond)  = Unet1D.forward                  srcs/modules/unet.py:422-469
+ * x [B,rep_dims,L], time [B] int64, cond [B,cond_channels,F] (un-upsampled; process_cond is applied
+ * inside exactly like the reference) → eps [B,rep_dims,L]. */
+int32_t ladiff_unet_forward(LadiffHandle* h, const float* x, const int64_t* time, const float* cond,
+                            int32_t B, int32_t L, int32_t F, float* eps, void* ws, int64_t ws_bytes,
+                            void* stream);
+
+/* model.diffusion.halfway_sampling(img, t, condition) / p_sample loop  srcs/losses/ddpm_loss.py:244-251,370-385
+ * Runs DDPM steps i = t_start-1 … t_start-n_steps on x [B,rep_dims,L] in place, conditioned on
+ * cond [B,cond_channels,F].  noise: pre-drawn [n_noise,B,rep_dims,L] consumed in loop order (one
+ * per step with i > 0), or NULL → Philox draws from `seed` (documented to differ from torch's stream).
+ * process_cond is hoisted out of the loop (it depends only on cond). */
+int32_t ladiff_ddpm_steps(LadiffHandle* h, float* x, const float* cond, const float* noise,
+                          int64_t n_noise, uint64_t seed, int32_t t_start, int32_t n_steps,
+                          int32_t B, int32_t L, int32_t F, void* ws, int64_t ws_bytes, void* stream);
+
+/* model.decoder(z)  = SEANetDecoder.forward                            srcs/modules/seanet.py:246-248
+ * z [B,rep_dims,L] → wav [B,1,L*hop]. */
+int32_t ladiff_decode(LadiffHandle* h, const float* z, int32_t B, int32_t L, float* wav,
+                      void* ws, int64_t ws_bytes, void* stream);
+
+/* The per-file body of synthesis()                                     srcs/sample.py:94-134
+ * get_cond(cond model) → upsampling_layers → img /= max|img| → halfway_sampling(t = n_steps) →
+ * decoder → /= std → /= max, with every whole-tensor normalisation applied per clip (the reference
+ * runs B = 1).  wav_in [B,1,T] → wav_out [B,1,T].  latent_out [B,rep_dims,L] optional. */
+int32_t ladiff_synthesize(LadiffHandle* model, LadiffHandle* cond_model, const float* wav_in,
+                          int32_t B, int32_t T, int32_t n_steps, const float* noise, int64_t n_noise,
+                          uint64_t seed, float* wav_out, float* latent_out, void* ws, int64_t ws_bytes,
+                          void* stream);
+
+/* Scratch needed by ladiff_synthesize for this pair of models. */
+int64_t ladiff_synthesize_workspace_bytes(const LadiffHandle* model, const LadiffHandle* cond_model,
+                                          int32_t B, int32_t T);
+
+/* Per-clip script-level normalisations                                  srcs/sample.py:129,133-134
+ * mode 0: x /= max|x| + 1e-8 ; mode 1: x /= std_unbiased(x) + 1e-8 then x /= max|x| + 1e-8 ;
+ * mode 2: x /= max|x| + 1e-20 (Unet1D.scaling, srcs/modules/unet.py:401-403).  x [B,n] in place. */
+int32_t ladiff_normalize_clips(float* x, int32_t B, int64_t n, int32_t mode, void* stream);
+
+/* ---- operator-level entry points (tests, profiling) ------------------------------------------ */
+/* Channels-last bf16 Conv1d on the tcgen05 path: x [B,L,Cin] bf16, w [Cout,Cin,k] fp32 (PyTorch
+ * layout), zero padding (k-1)/2, stride 1 → y [B,L,Cout] (bf16, or fp32 if y_f32).  impl 0 = tcgen05,
+ * 1 = SIMT check kernel (same packed operands).  Allocates and frees its own scratch; synchronises. */
+int32_t ladiff_op_conv1d_cl(const void* x_bf16, const float* w, const float* bias, int32_t B, int32_t L,
+                            int32_t Cin, int32_t Cout, int32_t k, void* y, int32_t y_f32, int32_t impl,
+                            float* gn_stats /* [B,Cout/32,2] or NULL */);
+/* Selects the conv implementation used inside the UNet: 0 = tcgen05 (default), 1 = SIMT check kernel. */
+int32_t ladiff_set_conv_impl(LadiffHandle* h, int32_t impl);
+/* Kernel launches issued by this handle since the last call (for bench.py's gpu_launches). */
+int64_t ladiff_take_launch_count(LadiffHandle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LADIFF_B200_H_ */

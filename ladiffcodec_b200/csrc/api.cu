@@ -1,0 +1,1202 @@
+// C-ABI of ladiff_b200 (include/ladiff_b200.h): handle, strict loader, load-time folds, stage plans.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "codec_ops.cuh"
+#include "common.cuh"
+#include "fold.cuh"
+#include "unet_ops.cuh"
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+void ladiff_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* ladiff_last_error(void) { return g_err; }
+extern "C" int32_t ladiff_abi_version(void) { return 1; }
+
+#define TRY(expr)              \
+  do {                         \
+    int _rc = (expr);          \
+    if (_rc != 0) return _rc;  \
+  } while (0)
+
+namespace {
+
+const int kTimesteps = 1000;
+const int kBins = 1024;
+const int kMults[5] = {1, 2, 2, 4, 4};
+
+struct KeySpec {
+  std::string name;
+  std::vector<int64_t> shape;
+  bool alias;   // diffusion.model.* duplicates diff_model.* (presence/shape checked, data not copied)
+  int64_t numel() const { int64_t n = 1; for (auto s : shape) n *= s; return n; }
+};
+
+// ---- folded codec parameters
+struct ConvW { const float* w = nullptr; const float* bias = nullptr; int Cout = 0, Cin = 0, K = 0, stride = 1; };
+struct ConvTrW { const float* w2 = nullptr; const float* bias = nullptr; int Cin = 0, Cout = 0, s = 1; };
+struct ResBlockW { ConvW c1, c2, sc; };
+struct LstmW { int H = 0, layers = 0; const float* wih[4]; const float* whh[4]; const float* bias[4]; };
+struct EncoderW { ConvW first, last; std::vector<ResBlockW> rb; std::vector<ConvW> down; LstmW lstm; };
+struct DecoderW { ConvW first, last; std::vector<ConvTrW> up; std::vector<ResBlockW> rb; LstmW lstm; };
+
+// ---- folded UNet parameters
+enum ConvKind { CK_PLAIN = 0, CK_DOWN = 1, CK_UP = 2 };
+struct PackedConv {
+  bf16* w = nullptr; const float* bias = nullptr;
+  int CoutV = 0, Cin = 0, K = 1, Ktot = 0, kind = CK_PLAIN;
+  CUtensorMap tmW;
+};
+struct ResnetW {
+  PackedConv c1, c2, res; bool has_res = false;
+  const float *g1 = nullptr, *b1 = nullptr, *g2 = nullptr, *b2 = nullptr;
+  long long film_off = 0; int Cin = 0, Cout = 0;
+};
+struct AttnW { PackedConv qkv, out; const float* norm_g = nullptr; const float* out_g = nullptr; int C = 0; };
+struct UNetW {
+  int dims[6];
+  PackedConv init, finalc, down[5], up[5];
+  ResnetW d[5][2], u[5][2], mid1, mid2, fin;
+  AttnW da[5], ua[5], mida;
+  float* film = nullptr; long long film_stride = 0;
+  DdpmTables tb;
+  std::vector<ConvTrW> cond_up;
+};
+
+struct Bump {
+  uintptr_t base; size_t off = 0;
+  explicit Bump(void* p) : base((uintptr_t)p) {}
+  template <class T> T* get(size_t n) {
+    off = align_up(off, 1024);
+    T* p = reinterpret_cast<T*>(base + off);
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+struct UnetBufs {
+  bf16 *xin, *FC, *CA[5], *CB[5], *X[6], *tY, *tH, *tO, *tR, *tA, *qkv, *ao;
+  float* eps; float* ctx; float2* stats; int* t_dev; float* inv_scale; float* condup; float* condtmp;
+  int stats_slots;
+};
+
+typedef std::function<int(cudaStream_t)> Op;
+struct Plan {
+  void* ws = nullptr; int B = 0, L = 0;
+  UnetBufs bufs;
+  std::vector<Op> ops;
+  long long launches_per_run = 0;
+};
+
+}  // namespace
+
+struct LadiffHandle {
+  LadiffConfig cfg;
+  std::vector<KeySpec> keys;
+  std::map<std::string, int> key_index;
+  std::vector<float*> dev;
+  std::vector<char> loaded;
+  std::vector<void*> owned;
+  bool finalized = false;
+  int conv_impl = 0;
+  long long launches = 0;
+  int enc_hop = 1;
+  EncoderW enc; DecoderW dec;
+  float* embed = nullptr; float* embed_sq = nullptr;
+  UNetW un;
+  std::vector<Plan*> plans;
+};
+
+namespace {
+
+typedef LadiffHandle H;
+
+// ------------------------------------------------------------------------------------------------ key layout
+// Mirrors ladiffcodec_b200/layout.py (state_dict order of DiffAudioRep, reference srcs/model.py:34-106).
+void add_key(H* h, const std::string& n, std::vector<int64_t> s, bool alias = false) {
+  h->key_index[n] = (int)h->keys.size();
+  h->keys.push_back(KeySpec{n, std::move(s), alias});
+}
+void keys_wn_conv(H* h, const std::string& p, int cout, int cin, int k) {
+  add_key(h, p + ".conv.conv.bias", {cout});
+  add_key(h, p + ".conv.conv.weight_g", {cout, 1, 1});
+  add_key(h, p + ".conv.conv.weight_v", {cout, cin, k});
+}
+void keys_wn_convtr(H* h, const std::string& p, int cin, int cout, int k) {
+  add_key(h, p + ".convtr.convtr.bias", {cout});
+  add_key(h, p + ".convtr.convtr.weight_g", {cin, 1, 1});
+  add_key(h, p + ".convtr.convtr.weight_v", {cin, cout, k});
+}
+void keys_resblock(H* h, const std::string& p, int dim) {
+  keys_wn_conv(h, p + ".block.1", dim / 2, dim, 3);
+  keys_wn_conv(h, p + ".block.3", dim, dim / 2, 1);
+  keys_wn_conv(h, p + ".shortcut", dim, dim, 1);
+}
+void keys_lstm(H* h, const std::string& p, int dim, int layers) {
+  for (int l = 0; l < layers; ++l) {
+    const std::string s = std::to_string(l);
+    add_key(h, p + ".lstm.weight_ih_l" + s, {4 * dim, dim});
+    add_key(h, p + ".lstm.weight_hh_l" + s, {4 * dim, dim});
+    add_key(h, p + ".lstm.bias_ih_l" + s, {4 * dim});
+    add_key(h, p + ".lstm.bias_hh_l" + s, {4 * dim});
+  }
+}
+std::string M(const std::string& prefix, int i) { return prefix + ".model." + std::to_string(i); }
+
+void keys_unet_resnet(H* h, const std::string& p, int cin, int cout, int td, bool alias) {
+  auto A = [&](const std::string& n, std::vector<int64_t> s) { add_key(h, n, std::move(s), alias); };
+  A(p + ".mlp.1.weight", {2 * cout, td});
+  A(p + ".mlp.1.bias", {2 * cout});
+  for (int b = 1; b <= 2; ++b) {
+    const std::string q = p + ".block" + std::to_string(b);
+    A(q + ".proj.weight", {cout, b == 1 ? cin : cout, 3});
+    A(q + ".proj.bias", {cout});
+    A(q + ".norm.weight", {cout});
+    A(q + ".norm.bias", {cout});
+  }
+  if (cin != cout) {
+    A(p + ".res_conv.weight", {cout, cin, 1});
+    A(p + ".res_conv.bias", {cout});
+  }
+}
+void keys_unet_linattn(H* h, const std::string& p, int dim, bool alias) {
+  auto A = [&](const std::string& n, std::vector<int64_t> s) { add_key(h, n, std::move(s), alias); };
+  A(p + ".fn.fn.to_qkv.weight", {384, dim, 1});
+  A(p + ".fn.fn.to_out.0.weight", {dim, 128, 1});
+  A(p + ".fn.fn.to_out.0.bias", {dim});
+  A(p + ".fn.fn.to_out.1.g", {1, dim, 1});
+  A(p + ".fn.norm.g", {1, dim, 1});
+}
+void keys_unet(H* h, const std::string& pre, bool alias) {
+  const LadiffConfig& c = h->cfg;
+  auto A = [&](const std::string& n, std::vector<int64_t> s) { add_key(h, n, std::move(s), alias); };
+  const int dim = c.diff_dims, inp = c.rep_dims, td = dim * 4, in_ch = inp + c.cond_channels;
+  int dims[6]; dims[0] = dim;
+  for (int i = 0; i < 5; ++i) dims[i + 1] = dim * kMults[i];
+  A(pre + ".init_conv.weight", {dim, in_ch, 7});
+  A(pre + ".init_conv.bias", {dim});
+  A(pre + ".time_mlp.1.weight", {td, dim});
+  A(pre + ".time_mlp.1.bias", {td});
+  A(pre + ".time_mlp.3.weight", {td, td});
+  A(pre + ".time_mlp.3.bias", {td});
+  for (int i = 0; i < 5; ++i) {
+    const std::string p = pre + ".downs." + std::to_string(i);
+    keys_unet_resnet(h, p + ".0", dims[i], dims[i], td, alias);
+    keys_unet_resnet(h, p + ".1", dims[i], dims[i], td, alias);
+    keys_unet_linattn(h, p + ".2", dims[i], alias);
+    A(p + ".3.weight", {dims[i + 1], dims[i], i < 4 ? 4 : 3});
+    A(p + ".3.bias", {dims[i + 1]});
+  }
+  for (int j = 0; j < 5; ++j) {
+    const int i = 4 - j, di = dims[i], dout = dims[i + 1];
+    const std::string p = pre + ".ups." + std::to_string(j);
+    keys_unet_resnet(h, p + ".0", dout + di, dout, td, alias);
+    keys_unet_resnet(h, p + ".1", dout + di, dout, td, alias);
+    keys_unet_linattn(h, p + ".2", dout, alias);
+    const std::string q = p + (j < 4 ? ".3.1" : ".3");
+    A(q + ".weight", {di, dout, 3});
+    A(q + ".bias", {di});
+  }
+  const int mid = dims[5];
+  keys_unet_resnet(h, pre + ".mid_block1", mid, mid, td, alias);
+  A(pre + ".mid_attn.fn.fn.to_qkv.weight", {384, mid, 1});
+  A(pre + ".mid_attn.fn.fn.to_out.weight", {mid, 128, 1});
+  A(pre + ".mid_attn.fn.fn.to_out.bias", {mid});
+  A(pre + ".mid_attn.fn.norm.g", {1, mid, 1});
+  keys_unet_resnet(h, pre + ".mid_block2", mid, mid, td, alias);
+  keys_unet_resnet(h, pre + ".final_res_block", dim * 2, dim, td, alias);
+  A(pre + ".final_conv.weight", {inp, dim, 1});
+  A(pre + ".final_conv.bias", {inp});
+  for (int j = 0; j < c.n_upsampling_ratios; ++j) {
+    const std::string p = pre + ".upsampling_layers." + std::to_string(j) + ".convtr.convtr";
+    A(p + ".weight", {c.cond_channels, c.cond_channels, 2 * c.upsampling_ratios[j]});
+    A(p + ".bias", {c.cond_channels});
+  }
+}
+
+const char* kSchedNames[13] = {"betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod",
+                               "sqrt_one_minus_alphas_cumprod", "log_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod",
+                               "sqrt_recipm1_alphas_cumprod", "posterior_variance", "posterior_log_variance_clipped",
+                               "posterior_mean_coef1", "posterior_mean_coef2", "p2_loss_weight"};
+
+void build_keys(H* h) {
+  const LadiffConfig& c = h->cfg;
+  const int nf = c.n_filters, dim = c.rep_dims, nr = c.n_enc_ratios;
+  {  // encoder, seanet.py:108-151 (ratios reversed)
+    int i = 0, mult = 1;
+    keys_wn_conv(h, M("encoder", i++), nf, 1, 7);
+    for (int r = nr - 1; r >= 0; --r) {
+      keys_resblock(h, M("encoder", i++), mult * nf);
+      i++;
+      keys_wn_conv(h, M("encoder", i++), mult * nf * 2, mult * nf, 2 * c.enc_ratios[r]);
+      mult *= 2;
+    }
+    if (c.lstm_layers) keys_lstm(h, M("encoder", i++), mult * nf, c.lstm_layers);
+    i++;
+    keys_wn_conv(h, M("encoder", i), dim, mult * nf, 7);
+  }
+  {  // decoder, seanet.py:201-236
+    int i = 0, mult = 1 << nr;
+    keys_wn_conv(h, M("decoder", i++), mult * nf, dim, 7);
+    if (c.lstm_layers) keys_lstm(h, M("decoder", i++), mult * nf, c.lstm_layers);
+    for (int r = 0; r < nr; ++r) {
+      i++;
+      keys_wn_convtr(h, M("decoder", i++), mult * nf, mult * nf / 2, 2 * c.enc_ratios[r]);
+      keys_resblock(h, M("decoder", i++), mult * nf / 2);
+      mult /= 2;
+    }
+    i++;
+    keys_wn_conv(h, M("decoder", i), 1, nf, 7);
+  }
+  if (c.quantization) {
+    for (int q = 0; q < c.n_q; ++q) {
+      const std::string p = "quantizer.vq.layers." + std::to_string(q) + "._codebook";
+      add_key(h, p + ".inited", {1});
+      add_key(h, p + ".cluster_size", {kBins});
+      add_key(h, p + ".embed", {kBins, dim});
+      add_key(h, p + ".embed_avg", {kBins, dim});
+    }
+  }
+  if (c.run_diff) {
+    keys_unet(h, "diff_model", false);
+    for (int i = 0; i < 13; ++i) add_key(h, std::string("diffusion.") + kSchedNames[i], {kTimesteps});
+    keys_unet(h, "diffusion.model", true);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ folds
+float* Wp(H* h, const std::string& n) {
+  auto it = h->key_index.find(n);
+  return it == h->key_index.end() ? nullptr : h->dev[it->second];
+}
+template <class T> int dalloc(H* h, T** p, size_t n) {
+  void* q = nullptr;
+  LADIFF_CUDA_OK(cudaMalloc(&q, n * sizeof(T)));
+  h->owned.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return 0;
+}
+
+int fold_wn_conv(H* h, const std::string& p, int cout, int cin, int k, int stride, ConvW* out) {
+  float* w = nullptr;
+  TRY(dalloc(h, &w, (size_t)cout * cin * k));
+  TRY(weight_norm_fold_launch(Wp(h, p + ".conv.conv.weight_g"), Wp(h, p + ".conv.conv.weight_v"), w, cout, cin * k, 0));
+  out->w = w; out->bias = Wp(h, p + ".conv.conv.bias");
+  out->Cout = cout; out->Cin = cin; out->K = k; out->stride = stride;
+  return 0;
+}
+int fold_wn_convtr(H* h, const std::string& p, int cin, int cout, int s, ConvTrW* out) {
+  float *w = nullptr, *w2 = nullptr;
+  TRY(dalloc(h, &w, (size_t)cin * cout * 2 * s));
+  TRY(dalloc(h, &w2, (size_t)cin * cout * 2 * s));
+  TRY(weight_norm_fold_launch(Wp(h, p + ".convtr.convtr.weight_g"), Wp(h, p + ".convtr.convtr.weight_v"), w, cin, cout * 2 * s, 0));
+  TRY(convtr_pack_launch(w, w2, cin, cout, s, 0));
+  out->w2 = w2; out->bias = Wp(h, p + ".convtr.convtr.bias"); out->Cin = cin; out->Cout = cout; out->s = s;
+  return 0;
+}
+int fold_resblock(H* h, const std::string& p, int dim, ResBlockW* rb) {
+  TRY(fold_wn_conv(h, p + ".block.1", dim / 2, dim, 3, 1, &rb->c1));
+  TRY(fold_wn_conv(h, p + ".block.3", dim, dim / 2, 1, 1, &rb->c2));
+  TRY(fold_wn_conv(h, p + ".shortcut", dim, dim, 1, 1, &rb->sc));
+  return 0;
+}
+int fold_lstm(H* h, const std::string& p, int dim, int layers, LstmW* lw) {
+  lw->H = dim; lw->layers = layers;
+  for (int l = 0; l < layers; ++l) {
+    const std::string s = std::to_string(l);
+    lw->wih[l] = Wp(h, p + ".lstm.weight_ih_l" + s);
+    lw->whh[l] = Wp(h, p + ".lstm.weight_hh_l" + s);
+    float* b = nullptr;
+    TRY(dalloc(h, &b, (size_t)4 * dim));
+    TRY(add_vec_launch(Wp(h, p + ".lstm.bias_ih_l" + s), Wp(h, p + ".lstm.bias_hh_l" + s), b, 4 * dim, 0));
+    lw->bias[l] = b;
+  }
+  return 0;
+}
+
+int fold_codec(H* h) {
+  const LadiffConfig& c = h->cfg;
+  const int nf = c.n_filters, dim = c.rep_dims, nr = c.n_enc_ratios;
+  {
+    int i = 0, mult = 1;
+    TRY(fold_wn_conv(h, M("encoder", i++), nf, 1, 7, 1, &h->enc.first));
+    for (int r = nr - 1; r >= 0; --r) {
+      ResBlockW rb; TRY(fold_resblock(h, M("encoder", i++), mult * nf, &rb)); h->enc.rb.push_back(rb);
+      i++;
+      ConvW d; TRY(fold_wn_conv(h, M("encoder", i++), mult * nf * 2, mult * nf, 2 * c.enc_ratios[r], c.enc_ratios[r], &d));
+      h->enc.down.push_back(d);
+      mult *= 2;
+    }
+    if (c.lstm_layers) TRY(fold_lstm(h, M("encoder", i++), mult * nf, c.lstm_layers, &h->enc.lstm));
+    i++;
+    TRY(fold_wn_conv(h, M("encoder", i), dim, mult * nf, 7, 1, &h->enc.last));
+  }
+  {
+    int i = 0, mult = 1 << nr;
+    TRY(fold_wn_conv(h, M("decoder", i++), mult * nf, dim, 7, 1, &h->dec.first));
+    if (c.lstm_layers) TRY(fold_lstm(h, M("decoder", i++), mult * nf, c.lstm_layers, &h->dec.lstm));
+    for (int r = 0; r < nr; ++r) {
+      i++;
+      ConvTrW u; TRY(fold_wn_convtr(h, M("decoder", i++), mult * nf, mult * nf / 2, c.enc_ratios[r], &u)); h->dec.up.push_back(u);
+      ResBlockW rb; TRY(fold_resblock(h, M("decoder", i++), mult * nf / 2, &rb)); h->dec.rb.push_back(rb);
+      mult /= 2;
+    }
+    i++;
+    TRY(fold_wn_conv(h, M("decoder", i), 1, nf, 7, 1, &h->dec.last));
+  }
+  if (c.quantization) {
+    TRY(dalloc(h, &h->embed, (size_t)c.n_q * kBins * dim));
+    TRY(dalloc(h, &h->embed_sq, (size_t)c.n_q * kBins));
+    for (int q = 0; q < c.n_q; ++q) {
+      const std::string p = "quantizer.vq.layers." + std::to_string(q) + "._codebook";
+      LADIFF_CUDA_OK(cudaMemcpy(h->embed + (size_t)q * kBins * dim, Wp(h, p + ".embed"), sizeof(float) * kBins * dim,
+                                cudaMemcpyDeviceToDevice));
+      float inited = 0.f;
+      LADIFF_CUDA_OK(cudaMemcpy(&inited, Wp(h, p + ".inited"), sizeof(float), cudaMemcpyDeviceToHost));
+      LADIFF_REQUIRE(inited != 0.f, LADIFF_ERR_UNSUPPORTED,
+                     "%s.inited == 0: the reference would run k-means on the input batch (core_vq.py:209); not on the sampling path",
+                     p.c_str());
+    }
+    TRY(rowsq_launch(h->embed, h->embed_sq, c.n_q * kBins, dim, 0));
+  }
+  return 0;
+}
+
+int pack_unet_conv(H* h, const std::string& wname, const std::string& bname, int cout, int cin, int k, int kind, bool standardize,
+                   PackedConv* pc) {
+  const float* w = Wp(h, wname);
+  LADIFF_REQUIRE(w != nullptr, LADIFF_ERR_KEY, "missing %s", wname.c_str());
+  LADIFF_REQUIRE(cin % 64 == 0, LADIFF_ERR_UNSUPPORTED, "%s: Cin=%d is not a multiple of 64", wname.c_str(), cin);
+  pc->Cin = cin; pc->K = k; pc->kind = kind;
+  pc->bias = bname.empty() ? nullptr : Wp(h, bname);
+  if (kind == CK_UP) {
+    pc->CoutV = 2 * cout; pc->Ktot = 3 * cin;
+    TRY(dalloc(h, &pc->w, (size_t)pc->CoutV * pc->Ktot));
+    TRY(pack_up_launch(w, pc->w, cout, cin, 0));
+    float* b2 = nullptr;
+    TRY(dalloc(h, &b2, (size_t)2 * cout));
+    TRY(dup_bias_launch(pc->bias, b2, cout, 0));
+    pc->bias = b2;
+  } else {
+    pc->CoutV = cout; pc->Ktot = k * cin;
+    TRY(dalloc(h, &pc->w, (size_t)cout * pc->Ktot));
+    TRY(pack_conv_launch(w, pc->w, cout, cin, k, standardize ? 1 : 0, 0));
+  }
+  LADIFF_REQUIRE(pc->CoutV % 128 == 0, LADIFF_ERR_UNSUPPORTED, "%s: Cout=%d is not a multiple of 128", wname.c_str(), pc->CoutV);
+  TRY(tc_make_tmap_w(&pc->tmW, pc->w, pc->CoutV, pc->Ktot));
+  return 0;
+}
+
+int fold_resnet(H* h, const std::string& p, int cin, int cout, long long* film_cursor, ResnetW* r) {
+  r->Cin = cin; r->Cout = cout;
+  TRY(pack_unet_conv(h, p + ".block1.proj.weight", p + ".block1.proj.bias", cout, cin, 3, CK_PLAIN, true, &r->c1));
+  TRY(pack_unet_conv(h, p + ".block2.proj.weight", p + ".block2.proj.bias", cout, cout, 3, CK_PLAIN, true, &r->c2));
+  r->g1 = Wp(h, p + ".block1.norm.weight"); r->b1 = Wp(h, p + ".block1.norm.bias");
+  r->g2 = Wp(h, p + ".block2.norm.weight"); r->b2 = Wp(h, p + ".block2.norm.bias");
+  r->has_res = cin != cout;
+  if (r->has_res) TRY(pack_unet_conv(h, p + ".res_conv.weight", p + ".res_conv.bias", cout, cin, 1, CK_PLAIN, false, &r->res));
+  r->film_off = *film_cursor;
+  *film_cursor += 2 * cout;
+  return 0;
+}
+int fold_attn(H* h, const std::string& p, int C, bool linear, AttnW* a) {
+  a->C = C;
+  TRY(pack_unet_conv(h, p + ".fn.fn.to_qkv.weight", "", 384, C, 1, CK_PLAIN, false, &a->qkv));
+  if (linear) {
+    TRY(pack_unet_conv(h, p + ".fn.fn.to_out.0.weight", p + ".fn.fn.to_out.0.bias", C, 128, 1, CK_PLAIN, false, &a->out));
+    a->out_g = Wp(h, p + ".fn.fn.to_out.1.g");
+  } else {
+    TRY(pack_unet_conv(h, p + ".fn.fn.to_out.weight", p + ".fn.fn.to_out.bias", C, 128, 1, CK_PLAIN, false, &a->out));
+    a->out_g = nullptr;
+  }
+  a->norm_g = Wp(h, p + ".fn.norm.g");
+  return 0;
+}
+
+struct FilmJob { std::string prefix; long long off; int cout; };
+
+int fold_unet(H* h) {
+  const LadiffConfig& c = h->cfg;
+  UNetW& u = h->un;
+  const std::string pre = "diff_model";
+  const int dim = c.diff_dims, inp = c.rep_dims, td = 4 * dim;
+  LADIFF_REQUIRE(dim % 128 == 0 && inp == 128 && c.cond_channels == 128, LADIFF_ERR_UNSUPPORTED,
+                 "UNet kernels need diff_dims %% 128 == 0 and rep_dims == cond_channels == 128 (got %d, %d, %d)", dim, inp,
+                 c.cond_channels);
+  u.dims[0] = dim;
+  for (int i = 0; i < 5; ++i) u.dims[i + 1] = dim * kMults[i];
+  long long fc = 0;
+  std::vector<FilmJob> jobs;
+  auto RES = [&](const std::string& p, int cin, int cout, ResnetW* r) -> int {
+    jobs.push_back(FilmJob{p, fc, cout});
+    return fold_resnet(h, p, cin, cout, &fc, r);
+  };
+  TRY(pack_unet_conv(h, pre + ".init_conv.weight", pre + ".init_conv.bias", dim, inp + c.cond_channels, 7, CK_PLAIN, false, &u.init));
+  for (int i = 0; i < 5; ++i) {
+    const std::string p = pre + ".downs." + std::to_string(i);
+    TRY(RES(p + ".0", u.dims[i], u.dims[i], &u.d[i][0]));
+    TRY(RES(p + ".1", u.dims[i], u.dims[i], &u.d[i][1]));
+    TRY(fold_attn(h, p + ".2", u.dims[i], true, &u.da[i]));
+    TRY(pack_unet_conv(h, p + ".3.weight", p + ".3.bias", u.dims[i + 1], u.dims[i], i < 4 ? 4 : 3, i < 4 ? CK_DOWN : CK_PLAIN, false,
+                       &u.down[i]));
+  }
+  TRY(RES(pre + ".mid_block1", u.dims[5], u.dims[5], &u.mid1));
+  TRY(fold_attn(h, pre + ".mid_attn", u.dims[5], false, &u.mida));
+  TRY(RES(pre + ".mid_block2", u.dims[5], u.dims[5], &u.mid2));
+  for (int j = 0; j < 5; ++j) {
+    const int i = 4 - j, di = u.dims[i], dout = u.dims[i + 1];
+    const std::string p = pre + ".ups." + std::to_string(j);
+    TRY(RES(p + ".0", dout + di, dout, &u.u[j][0]));
+    TRY(RES(p + ".1", dout + di, dout, &u.u[j][1]));
+    TRY(fold_attn(h, p + ".2", dout, true, &u.ua[j]));
+    const std::string q = p + (j < 4 ? ".3.1" : ".3");
+    TRY(pack_unet_conv(h, q + ".weight", q + ".bias", di, dout, 3, j < 4 ? CK_UP : CK_PLAIN, false, &u.up[j]));
+  }
+  TRY(RES(pre + ".final_res_block", 2 * dim, dim, &u.fin));
+  TRY(pack_unet_conv(h, pre + ".final_conv.weight", pre + ".final_conv.bias", inp, dim, 1, CK_PLAIN, false, &u.finalc));
+  // FiLM table: time_mlp (unet.py:327-332) and every block's mlp (unet.py:162-165,183-186) depend only on t
+  u.film_stride = fc;
+  TRY(dalloc(h, &u.film, (size_t)kTimesteps * fc));
+  float *emb = nullptr, *t1 = nullptr, *t2 = nullptr;
+  LADIFF_CUDA_OK(cudaMalloc(&emb, sizeof(float) * kTimesteps * dim));
+  LADIFF_CUDA_OK(cudaMalloc(&t1, sizeof(float) * kTimesteps * td));
+  LADIFF_CUDA_OK(cudaMalloc(&t2, sizeof(float) * kTimesteps * td));
+  int rc = sinusoid_launch(emb, kTimesteps, dim, 0);
+  if (!rc) rc = linear_f32_launch(emb, dim, Wp(h, pre + ".time_mlp.1.weight"), Wp(h, pre + ".time_mlp.1.bias"), t1, td, kTimesteps, td,
+                                  dim, 0, 1, 0);
+  if (!rc) rc = linear_f32_launch(t1, td, Wp(h, pre + ".time_mlp.3.weight"), Wp(h, pre + ".time_mlp.3.bias"), t2, td, kTimesteps, td, td,
+                                  0, 0, 0);
+  for (size_t k = 0; !rc && k < jobs.size(); ++k)
+    rc = linear_f32_launch(t2, td, Wp(h, jobs[k].prefix + ".mlp.1.weight"), Wp(h, jobs[k].prefix + ".mlp.1.bias"),
+                           u.film + jobs[k].off, (int)fc, kTimesteps, 2 * jobs[k].cout, td, 1, 0, 0);
+  cudaError_t e = cudaDeviceSynchronize();
+  cudaFree(emb); cudaFree(t1); cudaFree(t2);
+  if (rc) return rc;
+  LADIFF_CUDA_OK(e);
+  u.tb.sqrt_recip_ac = Wp(h, "diffusion.sqrt_recip_alphas_cumprod");
+  u.tb.sqrt_recipm1_ac = Wp(h, "diffusion.sqrt_recipm1_alphas_cumprod");
+  u.tb.coef1 = Wp(h, "diffusion.posterior_mean_coef1");
+  u.tb.coef2 = Wp(h, "diffusion.posterior_mean_coef2");
+  u.tb.logvar = Wp(h, "diffusion.posterior_log_variance_clipped");
+  for (int j = 0; j < c.n_upsampling_ratios; ++j) {   // cond upsamplers: plain ConvTranspose1d (no weight-norm)
+    const std::string p = pre + ".upsampling_layers." + std::to_string(j) + ".convtr.convtr";
+    const int s = c.upsampling_ratios[j], cc = c.cond_channels;
+    ConvTrW t;
+    float* w2 = nullptr;
+    TRY(dalloc(h, &w2, (size_t)cc * cc * 2 * s));
+    TRY(convtr_pack_launch(Wp(h, p + ".weight"), w2, cc, cc, s, 0));
+    t.w2 = w2; t.bias = Wp(h, p + ".bias"); t.Cin = cc; t.Cout = cc; t.s = s;
+    u.cond_up.push_back(t);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ codec stages
+struct Pool {   // rotating activation buffers of equal size
+  std::vector<float*> free_;
+  float* get() { float* p = free_.back(); free_.pop_back(); return p; }
+  void put(float* p) { free_.push_back(p); }
+};
+
+int conv_out_len(int Lin, int K, int stride) {   // conv.py:56-63 with padding_total = (K-1) - (stride-1)
+  const int pt = (K - 1) - (stride - 1);
+  return (Lin - K + pt + stride - 1) / stride + 1;
+}
+
+int run_conv(H* h, const ConvW& cw, const float* x, int Lin, float* y, int act_in, const float* res, int B, cudaStream_t st) {
+  ConvF32Args a;
+  memset(&a, 0, sizeof(a));
+  a.x = x; a.Cin = cw.Cin; a.Lin = Lin; a.w = cw.w; a.bias = cw.bias; a.y = y; a.CoutV = cw.Cout;
+  a.LoutV = conv_out_len(Lin, cw.K, cw.stride);
+  a.K = cw.K; a.stride = cw.stride; a.padL = (cw.K - 1) - (cw.stride - 1); a.pad_reflect = 1; a.act_in = act_in; a.res = res;
+  h->launches++;
+  return conv1d_f32_launch(a, B, st);
+}
+// SConvTranspose1d (conv.py:252-274): y [B][Cout][Lin*s]; causal -> trim right only, else left = ceil((k-s)/2)
+int run_convtr(H* h, const ConvTrW& cw, const float* x, int Lin, float* y, int act_in, bool causal, int B, cudaStream_t st) {
+  ConvF32Args a;
+  memset(&a, 0, sizeof(a));
+  a.x = x; a.Cin = cw.Cin; a.Lin = Lin; a.w = cw.w2; a.bias = cw.bias; a.y = y; a.CoutV = cw.s * cw.Cout; a.LoutV = Lin + 1;
+  a.K = 2; a.stride = 1; a.padL = 1; a.pad_reflect = 0; a.act_in = act_in; a.res = nullptr;
+  a.il_s = cw.s; a.il_cout = cw.Cout; a.il_lout = Lin * cw.s;
+  const int total = cw.s;                    // k - s
+  a.il_trim = causal ? 0 : total - total / 2;
+  h->launches++;
+  return conv1d_f32_launch(a, B, st);
+}
+int run_resblock(H* h, const ResBlockW& rb, float*& x, int L, Pool& pool, int B, cudaStream_t st) {
+  float* hbuf = pool.get(); float* s = pool.get(); float* y = pool.get();
+  TRY(run_conv(h, rb.c1, x, L, hbuf, 1, nullptr, B, st));
+  TRY(run_conv(h, rb.sc, x, L, s, 0, nullptr, B, st));
+  TRY(run_conv(h, rb.c2, hbuf, L, y, 1, s, B, st));
+  pool.put(hbuf); pool.put(s); pool.put(x);
+  x = y;
+  return 0;
+}
+// SLSTM (lstm.py:22-28): y = lstm(x) + x on [B][H][T]
+int run_lstm(H* h, const LstmW& lw, float*& x, int T, Pool& pool, float* hbuf, float* cbuf, int B, cudaStream_t st) {
+  float* in = x;
+  float* pre = pool.get();
+  float* y = nullptr;
+  for (int l = 0; l < lw.layers; ++l) {
+    ConvW ip; ip.w = lw.wih[l]; ip.bias = lw.bias[l]; ip.Cout = 4 * lw.H; ip.Cin = lw.H; ip.K = 1; ip.stride = 1;
+    TRY(run_conv(h, ip, in, T, pre, 0, nullptr, B, st));
+    y = pool.get();
+    const float* skip = (l == lw.layers - 1) ? x : nullptr;
+    if (lw.H == 64 || lw.H == 128) {
+      TRY(lstm_seq_launch(pre, lw.whh[l], skip, y, B, lw.H, T, st));
+      h->launches++;
+    } else {
+      TRY(lstm_steps_launch(pre, lw.whh[l], skip, y, hbuf, cbuf, B, lw.H, T, st, &h->launches));
+    }
+    if (in != x) pool.put(in);
+    in = y;
+  }
+  pool.put(pre); pool.put(x);
+  x = y;
+  return 0;
+}
+
+size_t codec_buf_elems(const H* h, int B, int T) {
+  // the largest activation on either codec path is n_filters x T; LSTM gate pre-activations are 4H x T/hop
+  const LadiffConfig& c = h->cfg;
+  size_t per = (size_t)c.n_filters * T;
+  const int hop = h->enc_hop;
+  const size_t lstm = (size_t)4 * c.n_filters * (1 << c.n_enc_ratios) * (T / hop + 1);
+  if (lstm > per) per = lstm;
+  return per * B + 1024;
+}
+const int kPoolBufs = 6;
+
+int setup_pool(H* h, Bump& bp, int B, int T, Pool& pool, float** hbuf, float** cbuf) {
+  const size_t n = codec_buf_elems(h, B, T);
+  for (int i = 0; i < kPoolBufs; ++i) pool.put(bp.get<float>(n));
+  const int Hmax = h->cfg.n_filters * (1 << h->cfg.n_enc_ratios);
+  *hbuf = bp.get<float>((size_t)2 * B * Hmax);
+  *cbuf = bp.get<float>((size_t)B * Hmax);
+  return 0;
+}
+
+int run_encoder(H* h, const float* wav, int B, int T, float* z, Bump bp, cudaStream_t st) {
+  Pool pool; float *hbuf, *cbuf;
+  setup_pool(h, bp, B, T, pool, &hbuf, &cbuf);
+  float* x = pool.get();
+  int L = T;
+  TRY(run_conv(h, h->enc.first, wav, L, x, 0, nullptr, B, st));
+  for (size_t i = 0; i < h->enc.down.size(); ++i) {
+    TRY(run_resblock(h, h->enc.rb[i], x, L, pool, B, st));
+    float* y = pool.get();
+    TRY(run_conv(h, h->enc.down[i], x, L, y, 1, nullptr, B, st));
+    L = conv_out_len(L, h->enc.down[i].K, h->enc.down[i].stride);
+    pool.put(x); x = y;
+  }
+  if (h->cfg.lstm_layers) TRY(run_lstm(h, h->enc.lstm, x, L, pool, hbuf, cbuf, B, st));
+  TRY(run_conv(h, h->enc.last, x, L, z, 1, nullptr, B, st));
+  return 0;
+}
+
+int run_decoder(H* h, const float* zin, int B, int L, float* wav, Bump bp, cudaStream_t st) {
+  Pool pool; float *hbuf, *cbuf;
+  setup_pool(h, bp, B, L * h->enc_hop, pool, &hbuf, &cbuf);
+  float* x = pool.get();
+  TRY(run_conv(h, h->dec.first, zin, L, x, 0, nullptr, B, st));
+  if (h->cfg.lstm_layers) TRY(run_lstm(h, h->dec.lstm, x, L, pool, hbuf, cbuf, B, st));
+  for (size_t i = 0; i < h->dec.up.size(); ++i) {
+    float* y = pool.get();
+    TRY(run_convtr(h, h->dec.up[i], x, L, y, 1, true, B, st));
+    L *= h->dec.up[i].s;
+    pool.put(x); x = y;
+    TRY(run_resblock(h, h->dec.rb[i], x, L, pool, B, st));
+  }
+  TRY(run_conv(h, h->dec.last, x, L, wav, 1, nullptr, B, st));
+  return 0;
+}
+
+// upsampling_layers loop (sample.py:125-128 / unet.py:412-414): cond [B][128][F] -> out [B][128][F*prod]
+int run_cond_upsample(H* h, const float* cond, int B, int F, float* out, float* tmp_a, float* tmp_b, cudaStream_t st) {
+  const auto& ups = h->un.cond_up;
+  const float* x = cond;
+  int L = F;
+  for (size_t j = 0; j < ups.size(); ++j) {
+    float* y = (j + 1 == ups.size()) ? out : ((j & 1) ? tmp_b : tmp_a);
+    TRY(run_convtr(h, ups[j], x, L, y, 0, false, B, st));
+    L *= ups[j].s;
+    x = y;
+  }
+  if (ups.empty()) LADIFF_CUDA_OK(cudaMemcpyAsync(out, cond, sizeof(float) * B * 128 * F, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ UNet plan
+void carve_unet(const H* h, Bump& bp, int B, int L, UnetBufs* u) {
+  const int* d = h->un.dims;
+  const size_t BL = (size_t)B * L;
+  u->xin = bp.get<bf16>(BL * 256);
+  u->FC = bp.get<bf16>(BL * 2 * d[0]);
+  for (int i = 0; i < 5; ++i) {
+    const size_t n = (size_t)B * (L >> i) * (d[i + 1] + d[i]);
+    u->CA[i] = bp.get<bf16>(n);
+    u->CB[i] = bp.get<bf16>(n);
+  }
+  u->X[0] = nullptr;
+  for (int i = 1; i <= 5; ++i) u->X[i] = bp.get<bf16>((size_t)B * (L >> (i < 5 ? i : 4)) * d[i]);
+  size_t tmax = 0;
+  for (int i = 0; i < 5; ++i) { const size_t n = (size_t)B * (L >> i) * d[i + 1]; if (n > tmax) tmax = n; }
+  u->tY = bp.get<bf16>(tmax); u->tH = bp.get<bf16>(tmax); u->tO = bp.get<bf16>(tmax); u->tR = bp.get<bf16>(tmax);
+  u->tA = bp.get<bf16>(tmax);
+  u->qkv = bp.get<bf16>(BL * 384);
+  u->ao = bp.get<bf16>(BL * 128);
+  u->eps = bp.get<float>(BL * 128);
+  u->ctx = bp.get<float>((size_t)B * 4096);
+  u->stats_slots = (L / 16 + 2) * 32;
+  u->stats = bp.get<float2>((size_t)B * u->stats_slots);
+  u->t_dev = bp.get<int>(B);
+  u->inv_scale = bp.get<float>(B);
+  u->condup = bp.get<float>(BL * 128);
+  u->condtmp = bp.get<float>(BL * 128);
+}
+
+ClView view(bf16* p, int L, int pitch, int C, int ch0 = 0) {
+  ClView v; v.p = p + ch0; v.bstride = (long long)L * pitch; v.pitch = pitch; v.C = C; return v;
+}
+
+struct PlanBuilder {
+  H* h; Plan* pl; int B;
+  // conv: `in` has Lin rows; writes Lout rows into `out` (bf16) or out32 (fp32, contiguous [B][Lout][CoutV])
+  int conv(const PackedConv& pc, ClView in, int Lin, ClView out, float* out32, bool want_stats, int* n_ntiles, ClView res) {
+    TcConvParams p;
+    memset(&p, 0, sizeof(p));
+    TcRefView rv;
+    int Lout = Lin, Lv = Lin, Cv = in.C, pitch_v = in.pitch;
+    LADIFF_REQUIRE(in.C == pc.Cin, LADIFF_ERR_ARG, "plan: conv input has %d channels, weights expect %d", in.C, pc.Cin);
+    const int nch = pc.Cin / 64;
+    if (pc.kind == CK_DOWN) {
+      LADIFF_REQUIRE(Lin % 2 == 0, LADIFF_ERR_ARG, "plan: stride-2 conv needs an even length (%d)", Lin);
+      Lout = Lin / 2; Lv = Lin / 2; pitch_v = 2 * in.pitch; Cv = in.pitch + in.C;
+      const int sh[4] = {-1, 0, 0, 1}, c0[4] = {in.pitch, 0, in.pitch, 0};
+      p.nseg = 4;
+      for (int s = 0; s < 4; ++s) p.seg[s] = TcSeg{sh[s], c0[s], nch, 0, pc.CoutV};
+    } else if (pc.kind == CK_UP) {
+      p.nseg = 3;
+      p.seg[0] = TcSeg{-1, 0, nch, 0, pc.CoutV / 2};
+      p.seg[1] = TcSeg{0, 0, nch, 0, pc.CoutV};
+      p.seg[2] = TcSeg{1, 0, nch, pc.CoutV / 2, pc.CoutV};
+    } else {
+      p.nseg = pc.K;
+      LADIFF_REQUIRE(pc.K <= TC_MAX_SEG, LADIFF_ERR_ARG, "plan: K=%d", pc.K);
+      for (int s = 0; s < pc.K; ++s) p.seg[s] = TcSeg{s - (pc.K - 1) / 2, 0, nch, 0, pc.CoutV};
+    }
+    int nt_tiles = 0;
+    p.NT = tc_pick_nt(Lout, &nt_tiles);
+    p.stages = tc_pick_stages(p.NT);
+    p.Lout = Lout; p.Cout = pc.CoutV; p.bias = pc.bias;
+    p.tmW = pc.tmW;
+    TRY(tc_make_tmap_x(&p.tmX, in.p, B, Lv, Cv, pitch_v, in.bstride, p.NT));
+    if (out32) {
+      p.out = out32; p.out_f32 = 1; p.out_pitch = pc.CoutV; p.out_bstride = (long long)Lout * pc.CoutV; p.out_ch0 = 0;
+    } else if (pc.kind == CK_UP) {
+      p.out = out.p; p.out_pitch = 2 * out.pitch; p.out_bstride = out.bstride; p.out_ch0 = 0;
+      p.out_split = pc.CoutV / 2; p.out_jump = out.pitch - pc.CoutV / 2;
+    } else {
+      p.out = out.p; p.out_pitch = out.pitch; p.out_bstride = out.bstride; p.out_ch0 = 0;
+    }
+    if (want_stats) {
+      LADIFF_REQUIRE(nt_tiles * (pc.CoutV / 32) <= pl->bufs.stats_slots, LADIFF_ERR_WORKSPACE, "plan: stats buffer too small");
+      p.stats = pl->bufs.stats;
+    }
+    if (n_ntiles) *n_ntiles = nt_tiles;
+    if (res.p) { p.res = res.p; p.res_bstride = res.bstride; p.res_pitch = res.pitch; p.res_ch0 = 0; }
+    rv.x = in.p; rv.bstride = in.bstride; rv.pitch = pitch_v; rv.Lv = Lv; rv.Cv = Cv; rv.w = pc.w; rv.Ktot = pc.Ktot;
+    H* hh = h; const int BB = B;
+    pl->ops.push_back([hh, p, rv, BB](cudaStream_t st) {
+      return hh->conv_impl == 0 ? tc_conv_launch(p, BB, st) : tc_conv_ref_launch(p, rv, BB, st);
+    });
+    pl->launches_per_run++;
+    return 0;
+  }
+  int gn(ClView y, int L, int n_ntiles, const float* g, const float* b, const float* film, ClView res, ClView out, bool do_tanh) {
+    GnApplyArgs a;
+    memset(&a, 0, sizeof(a));
+    a.y = y; a.stats = pl->bufs.stats; a.n_ntiles = n_ntiles; a.gamma = g; a.beta = b; a.film = film;
+    a.film_stride = h->un.film_stride; a.t_dev = pl->bufs.t_dev; a.res = res; a.out = out; a.L = L; a.do_tanh = do_tanh ? 1 : 0;
+    const int BB = B;
+    pl->ops.push_back([a, BB](cudaStream_t st) { return gn_apply_launch(a, BB, st); });
+    pl->launches_per_run++;
+    return 0;
+  }
+  // ResnetBlock (unet.py:176-192): out = SiLU(GN(conv2(SiLU(FiLM(GN(conv1(x))))))) + res_conv(x)
+  int resnet(const ResnetW& r, ClView x, int L, ClView out, bool do_tanh = false) {
+    UnetBufs& u = pl->bufs;
+    ClView none; memset(&none, 0, sizeof(none));
+    ClView y = view(u.tY, L, r.Cout, r.Cout), hh = view(u.tH, L, r.Cout, r.Cout);
+    int nt = 0;
+    TRY(conv(r.c1, x, L, y, nullptr, true, &nt, none));
+    TRY(gn(y, L, nt, r.g1, r.b1, h->un.film + r.film_off, none, hh, false));
+    ClView resv = x;
+    if (r.has_res) {
+      resv = view(u.tR, L, r.Cout, r.Cout);
+      TRY(conv(r.res, x, L, resv, nullptr, false, nullptr, none));
+    }
+    TRY(conv(r.c2, hh, L, y, nullptr, true, &nt, none));
+    TRY(gn(y, L, nt, r.g2, r.b2, nullptr, resv, out, do_tanh));
+    return 0;
+  }
+  int layernorm(ClView x, const float* g, ClView res, ClView out, int L) {
+    const int BB = B;
+    pl->ops.push_back([x, g, res, out, BB, L](cudaStream_t st) { return layernorm_cl_launch(x, g, res, out, BB, L, st); });
+    pl->launches_per_run++;
+    return 0;
+  }
+  // Residual(PreNorm(LinearAttention)) (unet.py:194-222) / Residual(PreNorm(Attention)) (:224-246)
+  int attention(const AttnW& a, ClView x, int L, ClView out, bool linear) {
+    UnetBufs& u = pl->bufs;
+    ClView none; memset(&none, 0, sizeof(none));
+    ClView ln = view(u.tH, L, a.C, a.C), qkv = view(u.qkv, L, 384, 384), ao = view(u.ao, L, 128, 128);
+    TRY(layernorm(x, a.norm_g, none, ln, L));
+    TRY(conv(a.qkv, ln, L, qkv, nullptr, false, nullptr, none));
+    const int BB = B; float* ctx = u.ctx;
+    if (linear) {
+      pl->ops.push_back([qkv, ctx, ao, BB, L](cudaStream_t st) { return linattn_launch(qkv, ctx, ao, BB, L, st); });
+      pl->launches_per_run += 2;
+      ClView yo = view(u.tY, L, a.C, a.C);
+      TRY(conv(a.out, ao, L, yo, nullptr, false, nullptr, none));
+      TRY(layernorm(yo, a.out_g, x, out, L));
+    } else {
+      pl->ops.push_back([qkv, ao, BB, L](cudaStream_t st) { return fullattn_launch(qkv, ao, BB, L, st); });
+      pl->launches_per_run++;
+      TRY(conv(a.out, ao, L, out, nullptr, false, nullptr, x));
+    }
+    return 0;
+  }
+};
+
+int build_plan(H* h, void* ws_unet, int B, int L, Plan** out) {
+  for (Plan* p : h->plans)
+    if (p->ws == ws_unet && p->B == B && p->L == L) { *out = p; return 0; }
+  LADIFF_REQUIRE(L % 16 == 0 && L >= 16, LADIFF_ERR_ARG, "UNet needs a latent length that is a multiple of 16 (got %d)", L);
+  Plan* pl = new Plan();
+  pl->ws = ws_unet; pl->B = B; pl->L = L;
+  Bump bp(ws_unet);
+  carve_unet(h, bp, B, L, &pl->bufs);
+  UnetBufs& u = pl->bufs;
+  const UNetW& w = h->un;
+  const int* d = w.dims;
+  PlanBuilder pb{h, pl, B};
+  ClView none; memset(&none, 0, sizeof(none));
+  int rc = 0;
+  auto CHECK = [&](int r) { if (r && !rc) rc = r; };
+  // init_conv on cat(cond_up, x); its output is also `r` of the final concat (unet.py:430-435,464)
+  ClView xin = view(u.xin, L, 256, 256);
+  ClView r0 = view(u.FC, L, 2 * d[0], d[0], d[0]);
+  CHECK(pb.conv(w.init, xin, L, r0, nullptr, false, nullptr, none));
+  ClView x = r0;
+  for (int i = 0; i < 5 && !rc; ++i) {
+    const int Li = L >> i, C = d[i], pitchC = d[i + 1] + d[i];
+    ClView skip1 = view(u.CB[i], Li, pitchC, C, d[i + 1]);
+    ClView skip2 = view(u.CA[i], Li, pitchC, C, d[i + 1]);
+    ClView o2 = view(u.tO, Li, C, C);
+    CHECK(pb.resnet(w.d[i][0], x, Li, skip1));
+    CHECK(pb.resnet(w.d[i][1], skip1, Li, o2));
+    CHECK(pb.attention(w.da[i], o2, Li, skip2, true));
+    const int Ln = i < 4 ? Li / 2 : Li;
+    ClView xn = view(u.X[i + 1], Ln, d[i + 1], d[i + 1]);
+    CHECK(pb.conv(w.down[i], skip2, Li, xn, nullptr, false, nullptr, none));
+    x = xn;
+  }
+  const int Lm = L >> 4, Cm = d[5];
+  if (!rc) {
+    ClView m1 = view(u.tO, Lm, Cm, Cm), m2 = view(u.tA, Lm, Cm, Cm);
+    ClView m3 = view(u.CA[4], Lm, d[5] + d[4], d[5], 0);
+    CHECK(pb.resnet(w.mid1, x, Lm, m1));
+    CHECK(pb.attention(w.mida, m1, Lm, m2, false));
+    CHECK(pb.resnet(w.mid2, m2, Lm, m3));
+  }
+  for (int j = 0; j < 5 && !rc; ++j) {
+    const int i = 4 - j, Li = L >> i, Cout = d[i + 1], pitchC = d[i + 1] + d[i];
+    ClView ca = view(u.CA[i], Li, pitchC, pitchC), cb = view(u.CB[i], Li, pitchC, pitchC);
+    ClView b1 = view(u.CB[i], Li, pitchC, Cout, 0);
+    ClView o2 = view(u.tO, Li, Cout, Cout), at = view(u.tA, Li, Cout, Cout);
+    CHECK(pb.resnet(w.u[j][0], ca, Li, b1));
+    CHECK(pb.resnet(w.u[j][1], cb, Li, o2));
+    CHECK(pb.attention(w.ua[j], o2, Li, at, true));
+    if (j < 4) {
+      const int pn = d[i] + d[i - 1];   // pitch of CA[i-1]; x part = channels [0, d[i])
+      ClView dst = view(u.CA[i - 1], 2 * Li, pn, d[i], 0);
+      dst.bstride = (long long)(2 * Li) * pn;
+      CHECK(pb.conv(w.up[j], at, Li, dst, nullptr, false, nullptr, none));
+    } else {
+      ClView dst = view(u.FC, L, 2 * d[0], d[0], 0);
+      CHECK(pb.conv(w.up[j], at, Li, dst, nullptr, false, nullptr, none));
+    }
+  }
+  if (!rc) {
+    ClView fc = view(u.FC, L, 2 * d[0], 2 * d[0]);
+    ClView fo = view(u.tO, L, d[0], d[0]);
+    CHECK(pb.resnet(w.fin, fc, L, fo, true));                        // + tanh (unet.py:467)
+    CHECK(pb.conv(w.finalc, fo, L, none, u.eps, false, nullptr, none));
+  }
+  if (rc) { delete pl; return rc; }
+  if (h->plans.size() >= 4) { delete h->plans.front(); h->plans.erase(h->plans.begin()); }
+  h->plans.push_back(pl);
+  *out = pl;
+  return 0;
+}
+
+int run_plan(H* h, Plan* pl, cudaStream_t st) {
+  for (auto& op : pl->ops) TRY(op(st));
+  h->launches += pl->launches_per_run;
+  return 0;
+}
+
+// process_cond (unet.py:407-420) into xin[:, :, 0:128]
+int prepare_cond(H* h, Plan* pl, const float* cond, int B, int L, int F, cudaStream_t st) {
+  UnetBufs& u = pl->bufs;
+  int Lup = F;
+  for (auto& c : h->un.cond_up) Lup *= c.s;
+  LADIFF_REQUIRE(Lup == L, LADIFF_ERR_ARG, "cond frames %d x upsampling = %d != latent length %d", F, Lup, L);
+  TRY(run_cond_upsample(h, cond, B, F, u.condup, u.condtmp, (float*)u.eps, st));
+  const float* inv = nullptr;
+  if (h->cfg.unet_scale_cond) {
+    TRY(absmax_inv_launch(u.condup, u.inv_scale, B, (long long)128 * L, 1e-20f, st));
+    inv = u.inv_scale; h->launches++;
+  }
+  TRY(ncl_to_cl_launch(u.condup, inv, view(u.xin, L, 256, 128, 0), B, 128, L, st));
+  h->launches++;
+  return 0;
+}
+
+size_t unet_ws_bytes(const H* h, int B, int L) {
+  Bump bp(nullptr);
+  UnetBufs u;
+  carve_unet(h, bp, B, L, &u);
+  return bp.off + 4096;
+}
+size_t codec_ws_bytes(const H* h, int B, int T) {
+  const size_t n = codec_buf_elems(h, B, T);
+  const int Hmax = h->cfg.n_filters * (1 << h->cfg.n_enc_ratios);
+  const size_t z = align_up(sizeof(float) * (size_t)B * h->cfg.rep_dims * (T / h->enc_hop + 1), 1024);   // get_cond's encoder output
+  return (n * kPoolBufs + (size_t)3 * B * Hmax) * sizeof(float) + z + 16 * 1024;
+}
+// persistent region used by ladiff_synthesize: cond [B][128][F], x [B][128][L], two upsample temporaries
+size_t persist_bytes(int B, int T, int L) {
+  return ((size_t)B * 128 * (T / 320 + 1) + (size_t)3 * B * 128 * L) * sizeof(float) + 8 * 1024;
+}
+
+int check_ws(void* ws, int64_t have, size_t need) {
+  LADIFF_REQUIRE(ws != nullptr && ((uintptr_t)ws % 1024) == 0, LADIFF_ERR_WORKSPACE, "workspace must be non-null and 1024-byte aligned");
+  LADIFF_REQUIRE((size_t)have >= need, LADIFF_ERR_WORKSPACE, "workspace too small: have %lld, need %zu", (long long)have, need);
+  return 0;
+}
+
+int ddpm_run(H* h, Plan* pl, float* x, const float* cond, const float* noise, int64_t n_noise, uint64_t seed, int t_start, int n_steps,
+             int B, int L, int F, cudaStream_t st) {
+  UnetBufs& u = pl->bufs;
+  LADIFF_REQUIRE(t_start <= kTimesteps && n_steps >= 0 && t_start - n_steps >= 0, LADIFF_ERR_ARG, "ddpm: t_start=%d n_steps=%d",
+                 t_start, n_steps);
+  TRY(prepare_cond(h, pl, cond, B, L, F, st));
+  ClView xs = view(u.xin, L, 256, 128, 128);
+  TRY(ncl_to_cl_launch(x, nullptr, xs, B, 128, L, st));
+  h->launches++;
+  int64_t k = 0;
+  for (int s = 0; s < n_steps; ++s) {
+    const int t = t_start - 1 - s;
+    TRY(fill_t_launch(u.t_dev, t, B, st));
+    TRY(run_plan(h, pl, st));
+    const float* nz = nullptr;
+    if (t > 0 && noise) {
+      LADIFF_REQUIRE(k < n_noise, LADIFF_ERR_ARG, "ddpm: pre-drawn noise exhausted at step %d (have %lld)", s, (long long)n_noise);
+      nz = noise + (size_t)k * B * 128 * L;
+      ++k;
+    }
+    TRY(ddpm_step_launch(u.eps, x, nz, seed, s, u.t_dev, h->un.tb, xs, B, 128, L, st));
+    h->launches += 2;
+  }
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================================ C-ABI
+extern "C" int32_t ladiff_create(const LadiffConfig* cfg, LadiffHandle** out) {
+  LADIFF_REQUIRE(cfg && out, LADIFF_ERR_ARG, "ladiff_create: null argument");
+  LADIFF_REQUIRE(cfg->n_enc_ratios >= 1 && cfg->n_enc_ratios <= LADIFF_MAX_RATIOS && cfg->n_upsampling_ratios >= 0 &&
+                     cfg->n_upsampling_ratios <= LADIFF_MAX_RATIOS,
+                 LADIFF_ERR_ARG, "ladiff_create: bad ratio counts");
+  LADIFF_REQUIRE(cfg->lstm_layers >= 0 && cfg->lstm_layers <= 4, LADIFF_ERR_ARG, "ladiff_create: lstm_layers=%d", cfg->lstm_layers);
+  LADIFF_REQUIRE(!cfg->quantization || (cfg->n_q >= 1 && cfg->n_q_used >= 1 && cfg->n_q_used <= cfg->n_q), LADIFF_ERR_ARG,
+                 "ladiff_create: n_q=%d n_q_used=%d", cfg->n_q, cfg->n_q_used);
+  LadiffHandle* h = new LadiffHandle();
+  h->cfg = *cfg;
+  h->enc_hop = 1;
+  for (int i = 0; i < cfg->n_enc_ratios; ++i) h->enc_hop *= cfg->enc_ratios[i];
+  build_keys(h);
+  h->dev.assign(h->keys.size(), nullptr);
+  h->loaded.assign(h->keys.size(), 0);
+  *out = h;
+  return 0;
+}
+
+extern "C" int32_t ladiff_destroy(LadiffHandle* h) {
+  if (!h) return 0;
+  for (float* p : h->dev) if (p) cudaFree(p);
+  for (void* p : h->owned) cudaFree(p);
+  for (Plan* p : h->plans) delete p;
+  delete h;
+  return 0;
+}
+
+extern "C" int32_t ladiff_expected_keys(const LadiffHandle* h) { return h ? (int32_t)h->keys.size() : 0; }
+extern "C" int32_t ladiff_expected_key_at(const LadiffHandle* h, int32_t i, const char** name, int64_t* shape4, int32_t* ndim) {
+  LADIFF_REQUIRE(h && i >= 0 && i < (int)h->keys.size(), LADIFF_ERR_ARG, "ladiff_expected_key_at: index %d", i);
+  const KeySpec& k = h->keys[i];
+  if (name) *name = k.name.c_str();
+  if (ndim) *ndim = (int32_t)k.shape.size();
+  if (shape4) for (size_t d = 0; d < k.shape.size() && d < 4; ++d) shape4[d] = k.shape[d];
+  return 0;
+}
+
+extern "C" int32_t ladiff_load_weight(LadiffHandle* h, const char* name, const float* data, const int64_t* shape, int32_t ndim) {
+  LADIFF_REQUIRE(h && name && shape, LADIFF_ERR_ARG, "ladiff_load_weight: null argument");
+  LADIFF_REQUIRE(!h->finalized, LADIFF_ERR_STATE, "ladiff_load_weight after ladiff_finalize");
+  auto it = h->key_index.find(name);
+  LADIFF_REQUIRE(it != h->key_index.end(), LADIFF_ERR_KEY, "unexpected key in state_dict: %s", name);
+  const KeySpec& k = h->keys[it->second];
+  bool same = (int)k.shape.size() == ndim;
+  for (int d = 0; same && d < ndim; ++d) same = k.shape[d] == shape[d];
+  LADIFF_REQUIRE(same, LADIFF_ERR_KEY, "size mismatch for %s", name);
+  if (!k.alias) {
+    LADIFF_REQUIRE(data != nullptr, LADIFF_ERR_ARG, "ladiff_load_weight(%s): null data", name);
+    if (!h->dev[it->second]) LADIFF_CUDA_OK(cudaMalloc((void**)&h->dev[it->second], sizeof(float) * (size_t)k.numel()));
+    LADIFF_CUDA_OK(cudaMemcpy(h->dev[it->second], data, sizeof(float) * (size_t)k.numel(), cudaMemcpyDefault));
+  }
+  h->loaded[it->second] = 1;
+  return 0;
+}
+
+extern "C" int32_t ladiff_finalize(LadiffHandle* h) {
+  LADIFF_REQUIRE(h, LADIFF_ERR_ARG, "ladiff_finalize: null handle");
+  LADIFF_REQUIRE(!h->finalized, LADIFF_ERR_STATE, "ladiff_finalize called twice");
+  for (size_t i = 0; i < h->keys.size(); ++i)
+    LADIFF_REQUIRE(h->loaded[i], LADIFF_ERR_KEY, "missing key in state_dict: %s", h->keys[i].name.c_str());
+  TRY(fold_codec(h));
+  if (h->cfg.run_diff) TRY(fold_unet(h));
+  LADIFF_CUDA_OK(cudaDeviceSynchronize());
+  h->finalized = true;
+  return 0;
+}
+
+extern "C" int64_t ladiff_workspace_bytes(const LadiffHandle* h, int32_t B, int32_t T) {
+  if (!h || B <= 0 || T <= 0) return 0;
+  const int L = T / h->enc_hop;
+  size_t stage = codec_ws_bytes(h, B, T);
+  // the conditioning codec always runs at hop 320 on T samples; its own handle reports its own need
+  if (h->cfg.run_diff) { const size_t u = unet_ws_bytes(h, B, L); if (u > stage) stage = u; }
+  return (int64_t)(persist_bytes(B, T, L > 0 ? L : 1) + stage);
+}
+
+extern "C" int64_t ladiff_synthesize_workspace_bytes(const LadiffHandle* m, const LadiffHandle* cm, int32_t B, int32_t T) {
+  if (!m || !cm || B <= 0 || T <= 0) return 0;
+  const int L = T / m->enc_hop;
+  size_t stage = codec_ws_bytes(cm, B, T);
+  stage = std::max(stage, codec_ws_bytes(m, B, T));
+  if (m->cfg.run_diff && L > 0) stage = std::max(stage, unet_ws_bytes(m, B, L));
+  return (int64_t)(persist_bytes(B, T, L > 0 ? L : 1) + stage);
+}
+
+#define STAGE_PROLOGUE(hh)                                                                      \
+  LADIFF_REQUIRE((hh) != nullptr, LADIFF_ERR_ARG, "null handle");                                \
+  LADIFF_REQUIRE((hh)->finalized, LADIFF_ERR_STATE, "handle not finalized (call ladiff_finalize)"); \
+  cudaStream_t st = (cudaStream_t)stream;
+
+extern "C" int32_t ladiff_encode(LadiffHandle* h, const float* wav, int32_t B, int32_t T, float* z, void* ws, int64_t ws_bytes,
+                                 void* stream) {
+  STAGE_PROLOGUE(h);
+  LADIFF_REQUIRE(wav && z && B > 0 && T > 0 && T % h->enc_hop == 0, LADIFF_ERR_ARG, "ladiff_encode: T=%d must be a multiple of hop %d", T,
+                 h->enc_hop);
+  TRY(check_ws(ws, ws_bytes, codec_ws_bytes(h, B, T)));
+  return run_encoder(h, wav, B, T, z, Bump(ws), st);
+}
+
+extern "C" int32_t ladiff_rvq_encode(LadiffHandle* h, const float* z, int32_t n_q, int32_t B, int32_t F, int64_t* codes, float* quantized,
+                                     void* stream) {
+  STAGE_PROLOGUE(h);
+  LADIFF_REQUIRE(h->cfg.quantization, LADIFF_ERR_STATE, "this model has no quantizer");
+  LADIFF_REQUIRE(z && n_q >= 1 && n_q <= h->cfg.n_q && B > 0 && F > 0, LADIFF_ERR_ARG, "ladiff_rvq_encode: n_q=%d", n_q);
+  h->launches++;
+  return rvq_encode_launch(z, h->embed, h->embed_sq, n_q, kBins, h->cfg.rep_dims, B, F, quantized, (long long*)codes, st);
+}
+
+extern "C" int32_t ladiff_rvq_decode(LadiffHandle* h, const int64_t* codes, int32_t n_q, int32_t B, int32_t F, float* quantized,
+                                     void* stream) {
+  STAGE_PROLOGUE(h);
+  LADIFF_REQUIRE(h->cfg.quantization, LADIFF_ERR_STATE, "this model has no quantizer");
+  LADIFF_REQUIRE(codes && quantized && n_q >= 1 && n_q <= h->cfg.n_q && B > 0 && F > 0, LADIFF_ERR_ARG, "ladiff_rvq_decode: n_q=%d", n_q);
+  h->launches++;
+  return rvq_decode_launch((const long long*)codes, h->embed, n_q, kBins, h->cfg.rep_dims, B, F, quantized, st);
+}
+
+extern "C" int32_t ladiff_get_cond(LadiffHandle* h, const float* wav, int32_t B, int32_t T, float* cond, int64_t* codes, float* enc_out,
+                                   void* ws, int64_t ws_bytes, void* stream) {
+  STAGE_PROLOGUE(h);
+  LADIFF_REQUIRE(wav && cond && B > 0 && T > 0 && T % h->enc_hop == 0, LADIFF_ERR_ARG, "ladiff_get_cond: T=%d must be a multiple of hop %d",
+                 T, h->enc_hop);
+  const int F = T / h->enc_hop;
+  const size_t zbytes = align_up(sizeof(float) * (size_t)B * h->cfg.rep_dims * F, 1024);
+  TRY(check_ws(ws, ws_bytes, codec_ws_bytes(h, B, T)));
+  float* z = enc_out ? enc_out : reinterpret_cast<float*>(ws);
+  TRY(run_encoder(h, wav, B, T, z, Bump((char*)ws + zbytes), st));
+  if (!h->cfg.quantization) {   // model.py:227 — no quantizer: cond is the encoder output
+    if (z != cond) LADIFF_CUDA_OK(cudaMemcpyAsync(cond, z, sizeof(float) * (size_t)B * h->cfg.rep_dims * F, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+  h->launches++;
+  return rvq_encode_launch(z, h->embed, h->embed_sq, h->cfg.n_q_used, kBins, h->cfg.rep_dims, B, F, cond, (long long*)codes, st);
+}
+
+extern "C" int32_t ladiff_upsample_layer(LadiffHandle* h, int32_t i, const float* x, int32_t B, int32_t Lin, float* y, void* stream) {
+  STAGE_PROLOGUE(h);
+  LADIFF_REQUIRE(h->cfg.run_diff && i >= 0 && i < (int)h->un.cond_up.size(), LADIFF_ERR_ARG, "ladiff_upsample_layer: index %d", i);
+  LADIFF_REQUIRE(x && y && B > 0 && Lin > 0, LADIFF_ERR_ARG, "ladiff_upsample_layer: bad arguments");
+  return run_convtr(h, h->un.cond_up[i], x, Lin, y, 0, false, B, st);
+}
+
+extern "C" int32_t ladiff_unet_forward(LadiffHandle* h, const float* x, const int64_t* time, const float* cond, int32_t B, int32_t L,
+                                       int32_t F, float* eps, void* ws, int64_t ws_bytes, void* stream) {
+  STAGE_PROLOGUE(h);
+  LADIFF_REQUIRE(h->cfg.run_diff, LADIFF_ERR_STATE, "this model has no diffusion UNet (run_diff=False)");
+  LADIFF_REQUIRE(x && time && cond && eps && B > 0, LADIFF_ERR_ARG, "ladiff_unet_forward: null argument");
+  TRY(check_ws(ws, ws_bytes, unet_ws_bytes(h, B, L)));
+  Plan* pl = nullptr;
+  TRY(build_plan(h, ws, B, L, &pl));
+  UnetBufs& u = pl->bufs;
+  TRY(prepare_cond(h, pl, cond, B, L, F, st));
+  TRY(ncl_to_cl_launch(x, nullptr, view(u.xin, L, 256, 128, 128), B, 128, L, st));
+  TRY(time_to_int_launch((const long long*)time, u.t_dev, B, st));
+  TRY(run_plan(h, pl, st));
+  TRY(cl_to_ncl_f32_launch(u.eps, eps, B, 128, L, st));
+  h->launches += 3;
+  return 0;
+}
+
+extern "C" int32_t ladiff_ddpm_steps(LadiffHandle* h, float* x, const float* cond, const float* noise, int64_t n_noise, uint64_t seed,
+                                     int32_t t_start, int32_t n_steps, int32_t B, int32_t L, int32_t F, void* ws, int64_t ws_bytes,
+                                     void* stream) {
+  STAGE_PROLOGUE(h);
+  LADIFF_REQUIRE(h->cfg.run_diff, LADIFF_ERR_STATE, "this model has no diffusion UNet (run_diff=False)");
+  LADIFF_REQUIRE(x && cond && B > 0, LADIFF_ERR_ARG, "ladiff_ddpm_steps: null argument");
+  TRY(check_ws(ws, ws_bytes, unet_ws_bytes(h, B, L)));
+  Plan* pl = nullptr;
+  TRY(build_plan(h, ws, B, L, &pl));
+  return ddpm_run(h, pl, x, cond, noise, n_noise, seed, t_start, n_steps, B, L, F, st);
+}
+
+extern "C" int32_t ladiff_decode(LadiffHandle* h, const float* z, int32_t B, int32_t L, float* wav, void* ws, int64_t ws_bytes,
+                                 void* stream) {
+  STAGE_PROLOGUE(h);
+  LADIFF_REQUIRE(z && wav && B > 0 && L > 0, LADIFF_ERR_ARG, "ladiff_decode: bad arguments");
+  TRY(check_ws(ws, ws_bytes, codec_ws_bytes(h, B, L * h->enc_hop)));
+  return run_decoder(h, z, B, L, wav, Bump(ws), st);
+}
+
+extern "C" int32_t ladiff_normalize_clips(float* x, int32_t B, int64_t n, int32_t mode, void* stream) {
+  LADIFF_REQUIRE(x && B > 0 && n > 1 && mode >= 0 && mode <= 2, LADIFF_ERR_ARG, "ladiff_normalize_clips: bad arguments");
+  return normalize_clips_launch(x, B, n, mode, (cudaStream_t)stream);
+}
+
+extern "C" int32_t ladiff_synthesize(LadiffHandle* m, LadiffHandle* cm, const float* wav_in, int32_t B, int32_t T, int32_t n_steps,
+                                     const float* noise, int64_t n_noise, uint64_t seed, float* wav_out, float* latent_out, void* ws,
+                                     int64_t ws_bytes, void* stream) {
+  STAGE_PROLOGUE(m);
+  LADIFF_REQUIRE(cm && cm->finalized, LADIFF_ERR_STATE, "conditioning model not finalized");
+  LADIFF_REQUIRE(m->cfg.run_diff && cm->cfg.quantization, LADIFF_ERR_STATE, "synthesize needs a diffusion model and a quantising cond codec");
+  LADIFF_REQUIRE(wav_in && wav_out && B > 0 && T > 0 && T % 640 == 0, LADIFF_ERR_ARG,
+                 "ladiff_synthesize: T=%d must be a multiple of 640 (sample.py:87)", T);
+  LADIFF_REQUIRE(T % m->enc_hop == 0 && T % cm->enc_hop == 0, LADIFF_ERR_ARG, "T=%d is not a multiple of the codec hops", T);
+  const int L = T / m->enc_hop, F = T / cm->enc_hop;
+  const size_t pb = persist_bytes(B, T, L);
+  TRY(check_ws(ws, ws_bytes, (size_t)ladiff_synthesize_workspace_bytes(m, cm, B, T)));
+  Bump bp(ws);
+  float* cond = bp.get<float>((size_t)B * 128 * F);
+  float* x = latent_out ? latent_out : bp.get<float>((size_t)B * 128 * L);
+  float* ta = bp.get<float>((size_t)B * 128 * L);
+  float* tb = bp.get<float>((size_t)B * 128 * L);
+  void* scratch = (char*)ws + pb;
+  const int64_t scratch_bytes = ws_bytes - (int64_t)pb;
+  TRY(ladiff_get_cond(cm, wav_in, B, T, cond, nullptr, nullptr, scratch, scratch_bytes, stream));       // sample.py:94
+  TRY(run_cond_upsample(m, cond, B, F, x, ta, tb, st));                                                 // :125-128
+  TRY(normalize_clips_launch(x, B, (long long)128 * L, 0, st));                                         // :129
+  Plan* pl = nullptr;
+  TRY(build_plan(m, scratch, B, L, &pl));
+  TRY(ddpm_run(m, pl, x, cond, noise, n_noise, seed, n_steps, n_steps, B, L, F, st));                   // :130
+  TRY(run_decoder(m, x, B, L, wav_out, Bump(scratch), st));                                             // :131
+  TRY(normalize_clips_launch(wav_out, B, T, 1, st));                                                    // :133-134
+  m->launches += 2;
+  return 0;
+}
+
+extern "C" int32_t ladiff_set_conv_impl(LadiffHandle* h, int32_t impl) {
+  LADIFF_REQUIRE(h && (impl == 0 || impl == 1), LADIFF_ERR_ARG, "ladiff_set_conv_impl: impl=%d", impl);
+  h->conv_impl = impl;
+  return 0;
+}
+extern "C" int64_t ladiff_take_launch_count(LadiffHandle* h) {
+  if (!h) return 0;
+  const long long n = h->launches;
+  h->launches = 0;
+  return n;
+}
+
+extern "C" int32_t ladiff_op_conv1d_cl(const void* x_bf16, const float* w, const float* bias, int32_t B, int32_t L, int32_t Cin,
+                                       int32_t Cout, int32_t k, void* y, int32_t y_f32, int32_t impl, float* gn_stats) {
+  LADIFF_REQUIRE(x_bf16 && w && y && Cin % 64 == 0 && Cout % 128 == 0 && k >= 1 && k <= TC_MAX_SEG && (k & 1), LADIFF_ERR_ARG,
+                 "ladiff_op_conv1d_cl: Cin %% 64, Cout %% 128, odd k <= %d required", TC_MAX_SEG);
+  bf16* wp = nullptr; float2* stats = nullptr;
+  LADIFF_CUDA_OK(cudaMalloc((void**)&wp, sizeof(bf16) * (size_t)Cout * Cin * k));
+  int rc = pack_conv_launch(w, wp, Cout, Cin, k, 0, 0);
+  TcConvParams p;
+  memset(&p, 0, sizeof(p));
+  int nt_tiles = 0;
+  p.NT = tc_pick_nt(L, &nt_tiles);
+  p.stages = tc_pick_stages(p.NT);
+  p.nseg = k;
+  for (int s = 0; s < k; ++s) p.seg[s] = TcSeg{s - (k - 1) / 2, 0, Cin / 64, 0, Cout};
+  p.Lout = L; p.Cout = Cout; p.bias = bias; p.out = y; p.out_f32 = y_f32; p.out_pitch = Cout; p.out_bstride = (long long)L * Cout;
+  if (!rc) rc = tc_make_tmap_w(&p.tmW, wp, Cout, Cin * k);
+  if (!rc) rc = tc_make_tmap_x(&p.tmX, (const bf16*)x_bf16, B, L, Cin, Cin, (long long)L * Cin, p.NT);
+  if (!rc && gn_stats) {
+    if (cudaMalloc((void**)&stats, sizeof(float2) * (size_t)B * nt_tiles * (Cout / 32)) != cudaSuccess) rc = LADIFF_ERR_CUDA;
+    p.stats = stats;
+  }
+  TcRefView rv;
+  rv.x = (const bf16*)x_bf16; rv.bstride = (long long)L * Cin; rv.pitch = Cin; rv.Lv = L; rv.Cv = Cin; rv.w = wp; rv.Ktot = Cin * k;
+  if (!rc) rc = impl == 0 ? tc_conv_launch(p, B, 0) : tc_conv_ref_launch(p, rv, B, 0);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (!rc && e != cudaSuccess) { ladiff_set_error("ladiff_op_conv1d_cl: %s", cudaGetErrorString(e)); rc = LADIFF_ERR_CUDA; }
+  if (!rc && gn_stats) {   // reduce the per-tile partials on the host: [B][Cout/32][2]
+    std::vector<float2> hst((size_t)B * nt_tiles * (Cout / 32));
+    cudaMemcpy(hst.data(), stats, sizeof(float2) * hst.size(), cudaMemcpyDeviceToHost);
+    std::vector<float> red((size_t)B * (Cout / 32) * 2, 0.f);
+    for (int b = 0; b < B; ++b)
+      for (int t = 0; t < nt_tiles; ++t)
+        for (int s = 0; s < Cout / 32; ++s) {
+          const float2 v = hst[((size_t)b * nt_tiles + t) * (Cout / 32) + s];
+          red[((size_t)b * (Cout / 32) + s) * 2] += v.x;
+          red[((size_t)b * (Cout / 32) + s) * 2 + 1] += v.y;
+        }
+    cudaMemcpy(gn_stats, red.data(), sizeof(float) * red.size(), cudaMemcpyDefault);
+  }
+  cudaFree(wp);
+  if (stats) cudaFree(stats);
+  return rc;
+}

@@ -1,0 +1,499 @@
+// fp32 NCL kernels of the SEANet codec path (HBM/latency-bound side of the pipeline; plain SIMT fp32 so that the
+// encoder output feeding the RVQ argmax keeps fp32 fidelity).
+#include "codec_ops.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ Conv1d (implicit GEMM in registers)
+// block 256 = 16 (t) x 16 (co) threads, thread tile RC x RT, CTA tile (16 RC) x (16 RT)
+template <int RC, int RT>
+__global__ void __launch_bounds__(256) conv1d_f32_kernel(ConvF32Args a, int CI_T, int XW) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int CO_T = 16 * RC, T_T = 16 * RT, CO_TP = CO_T + 4;
+  const int K = a.K;
+  float* xs = sm;                                   // [CI_T][XW]
+  float* ws = sm + ((CI_T * XW + 3) & ~3);          // [CI_T*K][CO_TP]
+  const int b = blockIdx.z, co0 = blockIdx.y * CO_T, t0 = blockIdx.x * T_T;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[RC][RT];
+#pragma unroll
+  for (int i = 0; i < RC; ++i)
+#pragma unroll
+    for (int j = 0; j < RT; ++j) acc[i][j] = 0.f;
+  const float* xb = a.x + (long long)b * a.Cin * a.Lin;
+  const int g0 = t0 * a.stride - a.padL;
+  for (int ci0 = 0; ci0 < a.Cin; ci0 += CI_T) {
+    const int nci = min(CI_T, a.Cin - ci0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nci * XW; i += 256) {
+      const int ci = i / XW, p = i - ci * XW;
+      int gi = g0 + p;
+      if (gi < 0) gi = a.pad_reflect ? -gi : -1;
+      else if (gi >= a.Lin) gi = a.pad_reflect ? 2 * (a.Lin - 1) - gi : -1;
+      float v = 0.f;
+      if (gi >= 0 && gi < a.Lin) {
+        v = xb[(long long)(ci0 + ci) * a.Lin + gi];
+        if (a.act_in == 1) v = v > 0.f ? v : expm1f(v);
+      }
+      xs[i] = v;
+    }
+    const int nr = nci * K;
+    for (int i = threadIdx.x; i < nr * CO_T; i += 256) {
+      const int co = i / nr, r = i - co * nr;
+      ws[r * CO_TP + co] = (co0 + co < a.CoutV) ? a.w[((long long)(co0 + co) * a.Cin + ci0) * K + r] : 0.f;
+    }
+    __syncthreads();
+    for (int ci = 0; ci < nci; ++ci) {
+      const float* xrow = xs + ci * XW + tx * a.stride;
+      const float* wrow = ws + ci * K * CO_TP + ty * RC;
+      for (int k = 0; k < K; ++k) {
+        float av[RC], bv[RT];
+#pragma unroll
+        for (int i = 0; i < RC; ++i) av[i] = wrow[k * CO_TP + i];
+#pragma unroll
+        for (int j = 0; j < RT; ++j) bv[j] = xrow[16 * j * a.stride + k];
+#pragma unroll
+        for (int i = 0; i < RC; ++i)
+#pragma unroll
+          for (int j = 0; j < RT; ++j) acc[i][j] += av[i] * bv[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < RC; ++i) {
+    const int co = co0 + ty * RC + i;
+    if (co >= a.CoutV) continue;
+    if (a.il_s == 0) {
+      const float bias = a.bias ? a.bias[co] : 0.f;
+      const long long base = ((long long)b * a.CoutV + co) * a.LoutV;
+#pragma unroll
+      for (int j = 0; j < RT; ++j) {
+        const int t = t0 + tx + 16 * j;
+        if (t < a.LoutV) {
+          float v = acc[i][j] + bias;
+          if (a.res) v += a.res[base + t];
+          a.y[base + t] = v;
+        }
+      }
+    } else {
+      const int ph = co / a.il_cout, cr = co - ph * a.il_cout;
+      const float bias = a.bias ? a.bias[cr] : 0.f;
+      const long long base = ((long long)b * a.il_cout + cr) * a.il_lout;
+#pragma unroll
+      for (int j = 0; j < RT; ++j) {
+        const int t = t0 + tx + 16 * j;
+        const int pos = t * a.il_s + ph - a.il_trim;
+        if (t < a.LoutV && pos >= 0 && pos < a.il_lout) a.y[base + pos] = acc[i][j] + bias;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ LSTM, small H: one persistent CTA per clip
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+template <int H, int KREG>
+__global__ void __launch_bounds__(4 * H) lstm_seq_kernel(const float* __restrict__ pre, const float* __restrict__ whh,
+                                                         const float* __restrict__ skip, float* __restrict__ y, int T) {
+  constexpr int KS = H - KREG;
+  extern __shared__ __align__(16) float wsm[];      // [KS][4H] tail of the recurrent weights
+  __shared__ __align__(16) float hs[2][H];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int q = tid & 3, j = tid >> 2, row = q * H + j;   // lanes 4j..4j+3 = gates i,f,g,o of unit j
+  float w[KREG];
+#pragma unroll
+  for (int k = 0; k < KREG; ++k) w[k] = whh[(long long)row * H + k];
+  for (int k = 0; k < KS; ++k) wsm[k * 4 * H + tid] = whh[(long long)row * H + KREG + k];
+  if (tid < H) hs[0][tid] = 0.f;
+  float c = 0.f;
+  const float* prow = pre + ((long long)b * 4 * H + row) * T;
+  const long long ybase = ((long long)b * H + j) * T;
+  __syncthreads();
+  int cur = 0;
+  for (int t0 = 0; t0 < T; t0 += 8) {
+    float pbuf[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pbuf[i] = (t0 + i < T) ? prow[t0 + i] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (t0 + i < T) {   // uniform across the block
+        float acc0 = pbuf[i], acc1 = 0.f;
+        const float4* h4 = reinterpret_cast<const float4*>(hs[cur]);
+#pragma unroll
+        for (int k4 = 0; k4 < KREG / 4; ++k4) {
+          const float4 hv = h4[k4];
+          acc0 += w[4 * k4 + 0] * hv.x; acc1 += w[4 * k4 + 1] * hv.y;
+          acc0 += w[4 * k4 + 2] * hv.z; acc1 += w[4 * k4 + 3] * hv.w;
+        }
+        if (KS > 0) {
+#pragma unroll 8
+          for (int k = 0; k < KS; ++k) acc0 += wsm[k * 4 * H + tid] * hs[cur][KREG + k];
+        }
+        const float acc = acc0 + acc1;
+        const int base = (tid & 31) & ~3;
+        const float gi = __shfl_sync(0xffffffffu, acc, base + 0);
+        const float gf = __shfl_sync(0xffffffffu, acc, base + 1);
+        const float gg = __shfl_sync(0xffffffffu, acc, base + 2);
+        const float go = __shfl_sync(0xffffffffu, acc, base + 3);
+        c = sigmoid_f(gf) * c + sigmoid_f(gi) * tanhf(gg);
+        const float h = sigmoid_f(go) * tanhf(c);
+        if (q == 0) {
+          hs[cur ^ 1][j] = h;
+          y[ybase + t0 + i] = skip ? h + skip[ybase + t0 + i] : h;
+        }
+        __syncthreads();
+        cur ^= 1;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ LSTM, any H: one launch per time step
+// grid (H/4, ceil(B/32)), 128 threads; CTA = 4 hidden units (16 gate rows) x 32 clips
+__global__ void __launch_bounds__(128) lstm_step_kernel(const float* __restrict__ pre, const float* __restrict__ whh,
+                                                        const float* __restrict__ skip, float* __restrict__ y,
+                                                        const float* __restrict__ h_prev, float* __restrict__ h_next,
+                                                        float* __restrict__ cbuf, int B, int H, int T, int t) {
+  constexpr int KC = 64;
+  __shared__ float Ws[16][KC + 1];
+  __shared__ float hs[32][KC + 1];
+  __shared__ float gs[16][33];
+  const int j0 = blockIdx.x * 4, b0 = blockIdx.y * 32, tid = threadIdx.x;
+  const int rp = tid >> 4, bp = tid & 15;
+  float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
+  for (int k0 = 0; k0 < H; k0 += KC) {
+    __syncthreads();
+    for (int i = tid; i < 16 * KC; i += 128) {
+      const int lr = i / KC, k = i - lr * KC;           // local row lr = gate*4 + unit
+      const int grow = (lr >> 2) * H + j0 + (lr & 3);
+      Ws[lr][k] = (k0 + k < H) ? whh[(long long)grow * H + k0 + k] : 0.f;
+    }
+    for (int i = tid; i < 32 * KC; i += 128) {
+      const int bb = i / KC, k = i - bb * KC;
+      hs[bb][k] = (b0 + bb < B && k0 + k < H) ? h_prev[(long long)(b0 + bb) * H + k0 + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 16
+    for (int k = 0; k < KC; ++k) {
+      const float w0 = Ws[2 * rp][k], w1 = Ws[2 * rp + 1][k];
+      const float h0 = hs[2 * bp][k], h1 = hs[2 * bp + 1][k];
+      a00 += w0 * h0; a01 += w0 * h1; a10 += w1 * h0; a11 += w1 * h1;
+    }
+  }
+  gs[2 * rp][2 * bp] = a00; gs[2 * rp][2 * bp + 1] = a01;
+  gs[2 * rp + 1][2 * bp] = a10; gs[2 * rp + 1][2 * bp + 1] = a11;
+  __syncthreads();
+  const int u = tid >> 5, bb = tid & 31, bg = b0 + bb, j = j0 + u;
+  if (bg < B) {
+    const long long pbase = (long long)bg * 4 * H * T + t;
+    const float gi = gs[0 * 4 + u][bb] + pre[pbase + (long long)(0 * H + j) * T];
+    const float gf = gs[1 * 4 + u][bb] + pre[pbase + (long long)(1 * H + j) * T];
+    const float gg = gs[2 * 4 + u][bb] + pre[pbase + (long long)(2 * H + j) * T];
+    const float go = gs[3 * 4 + u][bb] + pre[pbase + (long long)(3 * H + j) * T];
+    const float c = sigmoid_f(gf) * cbuf[(long long)bg * H + j] + sigmoid_f(gi) * tanhf(gg);
+    const float h = sigmoid_f(go) * tanhf(c);
+    cbuf[(long long)bg * H + j] = c;
+    h_next[(long long)bg * H + j] = h;
+    const long long yi = ((long long)bg * H + j) * T + t;
+    y[yi] = skip ? h + skip[yi] : h;
+  }
+}
+
+// ------------------------------------------------------------------ RVQ
+// 8 frames per CTA, 256 threads; residual kept in smem across the n_q stages
+constexpr int RVQ_FR = 8;
+__global__ void __launch_bounds__(256) rvq_encode_kernel(const float* __restrict__ z, const float* __restrict__ embed,
+                                                         const float* __restrict__ embed_sq, int n_q, int bins, int D, int B, int F,
+                                                         float* __restrict__ quantized, long long* __restrict__ codes) {
+  extern __shared__ __align__(16) float sm[];
+  float* res = sm;                    // [FR][D]
+  float* outv = sm + RVQ_FR * D;      // [FR][D]
+  __shared__ float xx[RVQ_FR];
+  __shared__ float bestv[RVQ_FR][8];
+  __shared__ int besti[RVQ_FR][8];
+  __shared__ int chosen[RVQ_FR];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long f0 = (long long)blockIdx.x * RVQ_FR, NF = (long long)B * F;
+  for (int i = tid; i < RVQ_FR * D; i += 256) {
+    const int f = i / D, d = i - f * D;
+    const long long gf = f0 + f;
+    float v = 0.f;
+    if (gf < NF) { const long long bb = gf / F, ff = gf - bb * F; v = z[(bb * D + d) * F + ff]; }
+    res[i] = v; outv[i] = 0.f;
+  }
+  __syncthreads();
+  for (int q = 0; q < n_q; ++q) {
+    const float* E = embed + (long long)q * bins * D;
+    const float* ES = embed_sq + (long long)q * bins;
+    if (warp < RVQ_FR) {   // ||x||^2 per frame (x.pow(2).sum(1))
+      float s = 0.f;
+      for (int d = lane; d < D; d += 32) s += res[warp * D + d] * res[warp * D + d];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) xx[warp] = s;
+    }
+    __syncthreads();
+    float bv[RVQ_FR]; int bi[RVQ_FR];
+#pragma unroll
+    for (int f = 0; f < RVQ_FR; ++f) { bv[f] = -INFINITY; bi[f] = 0x7fffffff; }
+    for (int jc = tid; jc < bins; jc += 256) {
+      float dot[RVQ_FR];
+#pragma unroll
+      for (int f = 0; f < RVQ_FR; ++f) dot[f] = 0.f;
+      const float4* e4 = reinterpret_cast<const float4*>(E + (long long)jc * D);
+      for (int d4 = 0; d4 < D / 4; ++d4) {
+        const float4 e = e4[d4];
+#pragma unroll
+        for (int f = 0; f < RVQ_FR; ++f) {
+          const float4 r = *reinterpret_cast<const float4*>(res + f * D + 4 * d4);
+          dot[f] += r.x * e.x; dot[f] += r.y * e.y; dot[f] += r.z * e.z; dot[f] += r.w * e.w;
+        }
+      }
+      const float ee = ES[jc];
+#pragma unroll
+      for (int f = 0; f < RVQ_FR; ++f) {
+        const float dist = -((xx[f] - 2.f * dot[f]) + ee);      // core_vq.py:176-180
+        if (dist > bv[f]) { bv[f] = dist; bi[f] = jc; }          // ascending jc per thread: first max kept
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < RVQ_FR; ++f) {
+      float v = bv[f]; int ix = bi[f];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, ix, o);
+        if (ov > v || (ov == v && oi < ix)) { v = ov; ix = oi; }
+      }
+      if (lane == 0) { bestv[f][warp] = v; besti[f][warp] = ix; }
+    }
+    __syncthreads();
+    if (tid < RVQ_FR) {
+      float v = bestv[tid][0]; int ix = besti[tid][0];
+      for (int w = 1; w < 8; ++w) {
+        const float ov = bestv[tid][w]; const int oi = besti[tid][w];
+        if (ov > v || (ov == v && oi < ix)) { v = ov; ix = oi; }
+      }
+      chosen[tid] = ix;
+      const long long gf = f0 + tid;
+      if (codes && gf < NF) codes[(long long)q * NF + gf] = ix;
+    }
+    __syncthreads();
+    for (int i = tid; i < RVQ_FR * D; i += 256) {
+      const int f = i / D, d = i - f * D;
+      const float qv = E[(long long)chosen[f] * D + d];
+      res[i] = res[i] - qv;          // residual = residual - quantized   (core_vq.py:334)
+      outv[i] = outv[i] + qv;        // quantized_out = quantized_out + quantized (:335), starts from 0.0
+    }
+    __syncthreads();
+  }
+  if (quantized) {
+    for (int i = tid; i < RVQ_FR * D; i += 256) {
+      const int d = i / RVQ_FR, f = i - d * RVQ_FR;     // f fastest -> contiguous F in the NCL output
+      const long long gf = f0 + f;
+      if (gf < NF) { const long long bb = gf / F, ff = gf - bb * F; quantized[(bb * D + d) * F + ff] = outv[f * D + d]; }
+    }
+  }
+}
+
+// quantized[b][d][f] = sum_q embed[q][codes[q][b][f]][d]   (sum order q = 0.. as core_vq.py:356-362)
+__global__ void rvq_decode_kernel(const long long* __restrict__ codes, const float* __restrict__ embed, int n_q, int bins, int D, int B,
+                                  int F, float* __restrict__ quantized) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * D * F;
+  if (i >= total) return;
+  const int f = (int)(i % F);
+  const int d = (int)((i / F) % D);
+  const long long b = i / ((long long)F * D);
+  float s = 0.f;
+  for (int q = 0; q < n_q; ++q) {
+    long long ix = codes[((long long)q * B + b) * F + f];
+    ix = ix < 0 ? 0 : (ix >= bins ? bins - 1 : ix);
+    s = s + embed[((long long)q * bins + ix) * D + d];
+  }
+  quantized[i] = s;
+}
+
+__global__ void rowsq_kernel(const float* __restrict__ e, float* __restrict__ sq, int rows, int D) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float s = 0.f;
+  for (int d = 0; d < D; ++d) s += e[(long long)r * D + d] * e[(long long)r * D + d];
+  sq[r] = s;
+}
+
+// ------------------------------------------------------------------ per-clip normalisation (sample.py:129,133-134)
+__device__ float block_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+  return s;
+}
+__device__ float block_max(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s = fmaxf(s, red[w]);
+  return s;
+}
+__global__ void __launch_bounds__(1024) normalize_clips_kernel(float* __restrict__ x, long long n, int mode) {
+  __shared__ float red[32];
+  float* p = x + (long long)blockIdx.x * n;
+  float mx = 0.f, s = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) { const float v = p[i]; mx = fmaxf(mx, fabsf(v)); s += v; }
+  mx = block_max(mx, red);
+  if (mode == 0 || mode == 2) {
+    const float d = mx + (mode == 0 ? 1e-8f : 1e-20f);   // sample.py:129 / unet.py:401-403
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) p[i] = p[i] / d;
+    return;
+  }
+  const float mean = block_sum(s, red) / (float)n;
+  float q = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) { const float dlt = p[i] - mean; q += dlt * dlt; }
+  const float var = block_sum(q, red) / (float)(n - 1);      // torch.std: unbiased
+  const float d1 = sqrtf(var) + 1e-8f;
+  const float d2 = mx / d1 + 1e-8f;                          // max|x / d1| = max|x| / d1
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) p[i] = (p[i] / d1) / d2;
+}
+
+// ------------------------------------------------------------------ load-time folds
+__global__ void weight_norm_fold_kernel(const float* __restrict__ g, const float* __restrict__ v, float* __restrict__ w, int inner) {
+  __shared__ float red[32];
+  const int r = blockIdx.x;
+  const float* vr = v + (long long)r * inner;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < inner; i += blockDim.x) s += vr[i] * vr[i];
+  const float nrm = sqrtf(block_sum(s, red));
+  const float sc = g[r] / nrm;
+  for (int i = threadIdx.x; i < inner; i += blockDim.x) w[(long long)r * inner + i] = vr[i] * sc;
+}
+
+__global__ void convtr_pack_kernel(const float* __restrict__ w, float* __restrict__ w2, int Cin, int Cout, int s) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)s * Cout * Cin * 2;
+  if (i >= total) return;
+  const int kk = (int)(i & 1);
+  const int ci = (int)((i >> 1) % Cin);
+  const long long v = (i >> 1) / Cin;           // ph*Cout + co
+  const int ph = (int)(v / Cout), co = (int)(v % Cout);
+  const int tap = kk == 0 ? ph + s : ph;        // kk=0 multiplies x[i-1], kk=1 multiplies x[i]
+  w2[i] = w[((long long)ci * Cout + co) * (2 * s) + tap];
+}
+
+__global__ void add_vec_kernel(const float* a, const float* b, float* c, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) c[i] = a[i] + b[i];
+}
+
+}  // namespace
+
+int conv1d_f32_launch(const ConvF32Args& a, int B, cudaStream_t st) {
+  LADIFF_REQUIRE(a.K >= 1 && a.K <= 64 && a.stride >= 1, LADIFF_ERR_ARG, "conv1d_f32: K=%d stride=%d", a.K, a.stride);
+  int CI_T = 64 / a.K;
+  if (CI_T > 32) CI_T = 32;
+  if (CI_T < 1) CI_T = 1;
+  if (CI_T > a.Cin) CI_T = a.Cin;
+  const int variant = a.CoutV <= 16 ? 2 : (a.CoutV <= 32 ? 1 : 0);
+  const int RC = variant == 0 ? 4 : (variant == 1 ? 2 : 1);
+  const int RT = variant == 0 ? 4 : 8;
+  const int CO_T = 16 * RC, T_T = 16 * RT;
+  const int XW = (T_T - 1) * a.stride + a.K;
+  const size_t smem = (size_t)(((CI_T * XW + 3) & ~3) + CI_T * a.K * (CO_T + 4)) * sizeof(float);
+  LADIFF_REQUIRE(smem <= 48 * 1024, LADIFF_ERR_ARG, "conv1d_f32: smem %zu", smem);
+  dim3 grid(cdiv(a.LoutV, T_T), cdiv(a.CoutV, CO_T), B);
+  if (variant == 0) conv1d_f32_kernel<4, 4><<<grid, 256, smem, st>>>(a, CI_T, XW);
+  else if (variant == 1) conv1d_f32_kernel<2, 8><<<grid, 256, smem, st>>>(a, CI_T, XW);
+  else conv1d_f32_kernel<1, 8><<<grid, 256, smem, st>>>(a, CI_T, XW);
+  LADIFF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int lstm_seq_launch(const float* pre, const float* whh, const float* skip, float* y, int B, int H, int T, cudaStream_t st) {
+  if (H == 64) {
+    lstm_seq_kernel<64, 64><<<B, 256, 0, st>>>(pre, whh, skip, y, T);
+  } else if (H == 128) {
+    static bool attr = false;
+    const size_t smem = (size_t)64 * 512 * sizeof(float);
+    if (!attr) {
+      LADIFF_CUDA_OK(cudaFuncSetAttribute(lstm_seq_kernel<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = true;
+    }
+    lstm_seq_kernel<128, 64><<<B, 512, smem, st>>>(pre, whh, skip, y, T);
+  } else {
+    LADIFF_REQUIRE(false, LADIFF_ERR_ARG, "lstm_seq: H=%d unsupported", H);
+  }
+  LADIFF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int lstm_steps_launch(const float* pre, const float* whh, const float* skip, float* y, float* hbuf, float* cbuf, int B, int H, int T,
+                      cudaStream_t st, long long* launches) {
+  LADIFF_REQUIRE(H % 4 == 0, LADIFF_ERR_ARG, "lstm_steps: H=%d", H);
+  LADIFF_CUDA_OK(cudaMemsetAsync(hbuf, 0, sizeof(float) * 2 * B * H, st));
+  LADIFF_CUDA_OK(cudaMemsetAsync(cbuf, 0, sizeof(float) * B * H, st));
+  dim3 grid(H / 4, cdiv(B, 32));
+  for (int t = 0; t < T; ++t) {
+    const float* hp = hbuf + (size_t)(t & 1) * B * H;
+    float* hn = hbuf + (size_t)((t + 1) & 1) * B * H;
+    lstm_step_kernel<<<grid, 128, 0, st>>>(pre, whh, skip, y, hp, hn, cbuf, B, H, T, t);
+  }
+  LADIFF_CUDA_OK(cudaGetLastError());
+  if (launches) *launches += T;
+  return 0;
+}
+
+int rvq_encode_launch(const float* z, const float* embed, const float* embed_sq, int n_q, int bins, int D, int B, int F,
+                      float* quantized, long long* codes, cudaStream_t st) {
+  LADIFF_REQUIRE(D % 4 == 0 && D <= 512, LADIFF_ERR_ARG, "rvq: D=%d", D);
+  const long long NF = (long long)B * F;
+  const size_t smem = (size_t)2 * RVQ_FR * D * sizeof(float);
+  rvq_encode_kernel<<<(unsigned)((NF + RVQ_FR - 1) / RVQ_FR), 256, smem, st>>>(z, embed, embed_sq, n_q, bins, D, B, F, quantized, codes);
+  LADIFF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int rvq_decode_launch(const long long* codes, const float* embed, int n_q, int bins, int D, int B, int F, float* quantized,
+                      cudaStream_t st) {
+  const long long total = (long long)B * D * F;
+  rvq_decode_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(codes, embed, n_q, bins, D, B, F, quantized);
+  LADIFF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int rowsq_launch(const float* e, float* sq, int rows, int D, cudaStream_t st) {
+  rowsq_kernel<<<cdiv(rows, 128), 128, 0, st>>>(e, sq, rows, D);
+  LADIFF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int normalize_clips_launch(float* x, int B, long long n, int mode, cudaStream_t st) {
+  normalize_clips_kernel<<<B, 1024, 0, st>>>(x, n, mode);
+  LADIFF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int weight_norm_fold_launch(const float* g, const float* v, float* w, int rows, int inner, cudaStream_t st) {
+  weight_norm_fold_kernel<<<rows, 128, 0, st>>>(g, v, w, inner);
+  LADIFF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int convtr_pack_launch(const float* w, float* w2, int Cin, int Cout, int s, cudaStream_t st) {
+  const long long total = (long long)s * Cout * Cin * 2;
+  convtr_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, w2, Cin, Cout, s);
+  LADIFF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int add_vec_launch(const float* a, const float* b, float* c, int n, cudaStream_t st) {
+  add_vec_kernel<<<cdiv(n, 256), 256, 0, st>>>(a, b, c, n);
+  LADIFF_CUDA_OK(cudaGetLastError());
+  return 0;
+}

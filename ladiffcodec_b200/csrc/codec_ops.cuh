@@ -1,0 +1,47 @@
+// fp32 NCL kernels of the SEANet codec path: Conv1d / ConvTranspose1d, LSTM, RVQ, clip normalisation.
+#pragma once
+#include "common.cuh"
+
+// y[b,co,t] = bias[co] + sum_{ci,k} w[co,ci,k] * act(xpad[b,ci,t*stride + k - padL])  (+ res[b,co,t])
+// xpad: reflect (SConv1d, conv.py:217-232) or zero extension of x outside [0,Lin).
+struct ConvF32Args {
+  const float* x; int Cin; int Lin;
+  const float* w;          // [CoutV][Cin][K]
+  const float* bias;       // [Cout real] or null
+  float* y;
+  int CoutV;               // (virtual) output channels computed
+  int LoutV;               // (virtual) output positions computed
+  int K, stride, padL;
+  int pad_reflect;         // 1 reflect, 0 zeros
+  int act_in;              // 0 none, 1 ELU(alpha=1)
+  const float* res;        // optional residual, same layout as y
+  // transposed-conv interleave (SConvTranspose1d, conv.py:252-274): virtual channel v = ph*il_cout + co at
+  // virtual position i lands at y[b, co, i*il_s + ph - il_trim] if inside [0, il_lout).  il_s = 0: plain conv.
+  int il_s, il_cout, il_trim, il_lout;
+};
+int conv1d_f32_launch(const ConvF32Args& a, int B, cudaStream_t st);
+
+// nn.LSTM layer recurrence given pre[b][4H][T] = W_ih x_t + b_ih + b_hh (PyTorch gate order i,f,g,o; lstm.py:20)
+//   y[b][j][t] = h_t[j] (+ skip[b][j][t]).  small H (64/128): one persistent CTA per clip.
+int lstm_seq_launch(const float* pre, const float* whh, const float* skip, float* y, int B, int H, int T, cudaStream_t st);
+// any H % 4 == 0: one launch per time step; hbuf [2][B][H], cbuf [B][H] scratch (zeroed here)
+int lstm_steps_launch(const float* pre, const float* whh, const float* skip, float* y, float* hbuf, float* cbuf, int B, int H, int T,
+                      cudaStream_t st, long long* launches);
+
+// Residual VQ (core_vq.py:174-189, 324-362).  z [B][D][F] -> quantized [B][D][F] (nullable), codes [n_q][B][F] int64 (nullable)
+// embed [n_q][bins][D], embed_sq [n_q][bins] = sum_d e^2
+int rvq_encode_launch(const float* z, const float* embed, const float* embed_sq, int n_q, int bins, int D, int B, int F,
+                      float* quantized, long long* codes, cudaStream_t st);
+int rvq_decode_launch(const long long* codes, const float* embed, int n_q, int bins, int D, int B, int F, float* quantized,
+                      cudaStream_t st);
+int rowsq_launch(const float* e, float* sq, int rows, int D, cudaStream_t st);
+
+// sample.py:129 (mode 0) and :133-134 (mode 1), per clip
+int normalize_clips_launch(float* x, int B, long long n, int mode, cudaStream_t st);
+
+// load-time folds
+// weight_norm (conv.py:30): w[o,:,:] = g[o] * v[o,:,:] / ||v[o,:,:]||      rows = dim-0 size, inner = product of the rest
+int weight_norm_fold_launch(const float* g, const float* v, float* w, int rows, int inner, cudaStream_t st);
+// ConvTranspose1d weight [Cin][Cout][2s] -> virtual conv weight [s*Cout][Cin][2] (see ConvF32Args)
+int convtr_pack_launch(const float* w, float* w2, int Cin, int Cout, int s, cudaStream_t st);
+int add_vec_launch(const float* a, const float* b, float* c, int n, cudaStream_t st);

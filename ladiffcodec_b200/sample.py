@@ -1,0 +1,141 @@
+"""The sampling script — mirrors the reference's ``srcs/sample.py`` (same flags, same per-file
+procedure, :50-136) and adds the batched entry point ``synthesize``.
+
+    python -m ladiffcodec_b200.sample --model_for_cond cond.amlt --model_path ladiff.amlt --run_diff \
+        --scaling_global --cond_bandwidth 3 --unet_scale_cond --input_dir IN --output_dir OUT
+"""
+import ctypes
+import glob
+import os
+
+import torch
+
+from . import _lib
+from .config import build_parser
+from .layout import ladiff_model_kwargs, cond_model_kwargs
+from .model import DiffAudioRep, DiffAudioTime, _ptr, _stream
+from .utils import load_model
+
+MIDWAY_T = 100   # sample.py:69
+
+
+def build_models(inp_args, device=None):
+    """sample.py:52-65: the LaDiff model and the conditioning codec, weights loaded, eval mode."""
+    if inp_args.train_time_diff:
+        DiffAudioTime()
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    model = DiffAudioRep(**ladiff_model_kwargs(inp_args)).to(device)
+    load_model(model, inp_args.model_path, strict=True)
+    model.eval()
+    model_for_cond = None
+    if inp_args.model_for_cond:
+        model_for_cond = DiffAudioRep(**cond_model_kwargs(inp_args)).to(device)
+        load_model(model_for_cond, inp_args.model_for_cond)
+        model_for_cond.eval()
+    return model, model_for_cond
+
+
+@torch.no_grad()
+def synthesize(model, model_for_cond, wav, n_steps=MIDWAY_T, noise=None, seed=0, return_latent=False):
+    """Batched body of synthesis() (sample.py:94-134) in ONE library call: get_cond → upsample → max-normalise →
+    halfway_sampling(t=n_steps) → decoder → std/max-normalise, each normalisation per clip.
+
+    wav: [B,1,T] fp32, T a multiple of 640.  A host tensor is staged through pinned memory and the result is
+    returned on the host; a CUDA tensor stays on the device.
+    noise: None → in-kernel Philox(seed) (throughput mode; differs from torch's stream by design);
+           tensor [n_steps-1,B,128,L] → consumed exactly like the reference's per-step randn_like draws.
+    """
+    dev = model.device
+    on_host = wav.device.type != "cuda"
+    if on_host:
+        src = wav.to(torch.float32).contiguous()
+        src = src if src.is_pinned() else src.pin_memory()
+        x = src.to(dev, non_blocking=True)
+    else:
+        x = wav.to(device=dev, dtype=torch.float32).contiguous()
+    B, C, T = x.shape
+    if C != 1 or T % 640 != 0:
+        raise ValueError("wav must be [B,1,T] with T a multiple of 640 (sample.py:87)")
+    L = T // model.decoder.hop_length
+    out = torch.empty(B, 1, T, device=dev)
+    latent = torch.empty(B, model.cfg["rep_dims"], L, device=dev) if return_latent else None
+    n_noise = 0
+    if noise is not None:
+        noise = noise.to(device=dev, dtype=torch.float32).contiguous()
+        if noise.dim() != 4 or tuple(noise.shape[1:]) != (B, model.cfg["rep_dims"], L):
+            raise ValueError(f"noise must be [n,{B},{model.cfg['rep_dims']},{L}], got {tuple(noise.shape)}")
+        n_noise = noise.shape[0]
+    ws = model._workspace(B, T, other=model_for_cond)
+    _lib.check(model._lib.ladiff_synthesize(model._h, model_for_cond._h, _ptr(x), B, T, int(n_steps), _ptr(noise), n_noise,
+                                            ctypes.c_uint64(seed), _ptr(out), _ptr(latent), _ptr(ws), ws.numel(), _stream()),
+               "synthesize")
+    if on_host:
+        host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+        host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        out = host
+    return (out, latent) if return_latent else out
+
+
+def _load_wav(path):
+    """torchaudio.load (sample.py:83) with a scipy fallback for images without TorchCodec."""
+    try:
+        import torchaudio
+        return torchaudio.load(path)
+    except Exception:
+        from scipy.io import wavfile
+        sr, data = wavfile.read(path)
+        t = torch.from_numpy(data.copy())
+        if t.dtype == torch.int16:
+            t = t.to(torch.float32) / 32768.0
+        elif t.dtype == torch.int32:
+            t = t.to(torch.float32) / 2147483648.0
+        t = t.to(torch.float32)
+        return (t[None] if t.dim() == 1 else t.t().contiguous()), sr
+
+
+def _save_wav(path, wav, sr):
+    try:
+        import torchaudio
+        torchaudio.save(path, wav, sr)
+    except Exception:
+        from scipy.io import wavfile
+        wavfile.write(path, sr, wav.squeeze(0).numpy())
+
+
+def synthesis(inp_args):
+    """sample.py:50-136, file for file."""
+    import torchaudio
+    model, model_for_cond = build_models(inp_args)
+    device = model.device
+    midway_t = MIDWAY_T
+    with torch.no_grad():
+        for wav_file in sorted(glob.glob(os.path.join(inp_args.input_dir, "**/*.wav"), recursive=True)):
+            local_path = wav_file[len(inp_args.input_dir):][:-4]
+            save_path = inp_args.output_dir + local_path
+            output_folder = save_path[: -(len(save_path.split("/")[-1]) + 1)]
+            if output_folder and not os.path.exists(output_folder):
+                os.makedirs(output_folder)
+            wav, sr = _load_wav(wav_file)
+            wav = torchaudio.functional.resample(wav, orig_freq=sr, new_freq=16000)
+            wav = wav.unsqueeze(1).to(torch.float).to(device)
+            length = wav.shape[-1] // 640 * 640
+            wav = wav[:, :, :length]
+            model.diffusion.seq_length = int(wav.shape[-1] / inp_args.enc_ratios[0])
+            cond = None
+            if model_for_cond is not None:
+                cond = model_for_cond.get_cond(wav)
+            img = cond
+            if inp_args.upsampling_ratios is not None:
+                for layer in model.diff_model.upsampling_layers:
+                    img = layer(img)
+            img /= torch.max(torch.abs(img.flatten())) + 1e-8
+            sample = model.diffusion.halfway_sampling(img=img, condition=cond, t=midway_t)
+            x_sample_mid = model.decoder(sample)
+            x_sample_mid /= torch.std(x_sample_mid.flatten()) + 1e-8
+            x_sample_mid /= torch.max(torch.abs(x_sample_mid.flatten())) + 1e-8
+            _save_wav(f"{save_path}.wav", x_sample_mid.squeeze(1).cpu(), 16000)
+
+
+if __name__ == "__main__":
+    synthesis(build_parser().parse_args())
