@@ -13,7 +13,7 @@
  *    fp32, contiguous, NCL exactly as the reference passes them ([B,C,L]); indices are int64.
  *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Calls only enqueue
  *    work; they do not synchronise unless stated.
- *  - `ws` is caller-owned scratch of at least ladiff_workspace_bytes() bytes, 1024-byte aligned.
+ *  - `ws` is caller-owned scratch of at least ladiff_workspace_bytes() bytes, 256-byte aligned.
  *    The library allocates device memory only in ladiff_load_weight / ladiff_finalize.
  *  - one handle == one `DiffAudioRep` (srcs/model.py:32).  Handles are independent; a handle must
  *    not be used from two threads at once.
@@ -160,6 +160,11 @@ int32_t ladiff_op_conv1d_cl(const void* x_bf16, const float* w, const float* bia
                             float* gn_stats /* [B,Cout/32,2] or NULL */);
 /* Selects the conv implementation used inside the UNet: 0 = tcgen05 (default), 1 = SIMT check kernel. */
 int32_t ladiff_set_conv_impl(LadiffHandle* h, int32_t impl);
+/* Profiling for bench.py's roofline: when on, CUDA events are recorded on the launching stream around every
+ * tcgen05 conv launch of a UNet evaluation.  ladiff_profile_report (synchronises) returns for the most recent
+ * evaluation: out4 = {conv ms, conv algorithmic FLOPs, conv launches, whole-evaluation ms}. */
+int32_t ladiff_set_profiling(LadiffHandle* h, int32_t on);
+int32_t ladiff_profile_report(LadiffHandle* h, double* out4);
 /* Kernel launches issued by this handle since the last call (for bench.py's gpu_launches). */
 int64_t ladiff_take_launch_count(LadiffHandle* h);
 

@@ -52,6 +52,8 @@ SIGNATURES = {
     "ladiff_op_conv1d_cl": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp]),
     "ladiff_set_conv_impl": (c_i32, [c_vp, c_i32]),
     "ladiff_take_launch_count": (c_i64, [c_vp]),
+    "ladiff_set_profiling": (c_i32, [c_vp, c_i32]),
+    "ladiff_profile_report": (c_i32, [c_vp, ctypes.POINTER(ctypes.c_double)]),
 }
 
 _lib = None

@@ -78,7 +78,7 @@ struct Bump {
   uintptr_t base; size_t off = 0;
   explicit Bump(void* p) : base((uintptr_t)p) {}
   template <class T> T* get(size_t n) {
-    off = align_up(off, 1024);
+    off = align_up(base + off, 1024) - base;    // absolute 1 KB alignment whatever the caller's base alignment
     T* p = reinterpret_cast<T*>(base + off);
     off += n * sizeof(T);
     return p;
@@ -96,7 +96,10 @@ struct Plan {
   void* ws = nullptr; int B = 0, L = 0;
   UnetBufs bufs;
   std::vector<Op> ops;
+  std::vector<double> op_flops;          // algorithmic FLOPs of conv ops (2*Cout*Cin*k*Lout*B), 0 for the others
+  std::vector<cudaEvent_t> ev;           // profiling: [2*i], [2*i+1] around conv op i; last two around the whole evaluation
   long long launches_per_run = 0;
+  ~Plan() { for (auto e : ev) cudaEventDestroy(e); }
 };
 
 }  // namespace
@@ -110,6 +113,8 @@ struct LadiffHandle {
   std::vector<void*> owned;
   bool finalized = false;
   int conv_impl = 0;
+  int profiling = 0;
+  Plan* last_plan = nullptr;
   long long launches = 0;
   int enc_hop = 1;
   EncoderW enc; DecoderW dec;
@@ -722,6 +727,8 @@ struct PlanBuilder {
     pl->ops.push_back([hh, p, rv, BB](cudaStream_t st) {
       return hh->conv_impl == 0 ? tc_conv_launch(p, BB, st) : tc_conv_ref_launch(p, rv, BB, st);
     });
+    pl->op_flops.resize(pl->ops.size(), 0.0);
+    pl->op_flops.back() = 2.0 * pc.CoutV * (double)pc.Ktot * Lout * B;
     pl->launches_per_run++;
     return 0;
   }
@@ -854,7 +861,24 @@ int build_plan(H* h, void* ws_unet, int B, int L, Plan** out) {
 }
 
 int run_plan(H* h, Plan* pl, cudaStream_t st) {
-  for (auto& op : pl->ops) TRY(op(st));
+  pl->op_flops.resize(pl->ops.size(), 0.0);
+  if (!h->profiling) {
+    for (auto& op : pl->ops) TRY(op(st));
+  } else {   // CUDA events on the launching stream around every conv launch (bench.py roofline)
+    if (pl->ev.empty()) {
+      pl->ev.resize(2 * pl->ops.size() + 2);
+      for (auto& e : pl->ev) LADIFF_CUDA_OK(cudaEventCreate(&e));
+    }
+    LADIFF_CUDA_OK(cudaEventRecord(pl->ev[2 * pl->ops.size()], st));
+    for (size_t i = 0; i < pl->ops.size(); ++i) {
+      const bool is_conv = pl->op_flops[i] > 0.0;
+      if (is_conv) LADIFF_CUDA_OK(cudaEventRecord(pl->ev[2 * i], st));
+      TRY(pl->ops[i](st));
+      if (is_conv) LADIFF_CUDA_OK(cudaEventRecord(pl->ev[2 * i + 1], st));
+    }
+    LADIFF_CUDA_OK(cudaEventRecord(pl->ev[2 * pl->ops.size() + 1], st));
+    h->last_plan = pl;
+  }
   h->launches += pl->launches_per_run;
   return 0;
 }
@@ -880,7 +904,7 @@ size_t unet_ws_bytes(const H* h, int B, int L) {
   Bump bp(nullptr);
   UnetBufs u;
   carve_unet(h, bp, B, L, &u);
-  return bp.off + 4096;
+  return bp.off + 8192;
 }
 size_t codec_ws_bytes(const H* h, int B, int T) {
   const size_t n = codec_buf_elems(h, B, T);
@@ -890,11 +914,11 @@ size_t codec_ws_bytes(const H* h, int B, int T) {
 }
 // persistent region used by ladiff_synthesize: cond [B][128][F], x [B][128][L], two upsample temporaries
 size_t persist_bytes(int B, int T, int L) {
-  return ((size_t)B * 128 * (T / 320 + 1) + (size_t)3 * B * 128 * L) * sizeof(float) + 8 * 1024;
+  return align_up(((size_t)B * 128 * (T / 320 + 1) + (size_t)3 * B * 128 * L) * sizeof(float) + 8 * 1024, 1024);
 }
 
 int check_ws(void* ws, int64_t have, size_t need) {
-  LADIFF_REQUIRE(ws != nullptr && ((uintptr_t)ws % 1024) == 0, LADIFF_ERR_WORKSPACE, "workspace must be non-null and 1024-byte aligned");
+  LADIFF_REQUIRE(ws != nullptr && ((uintptr_t)ws % 256) == 0, LADIFF_ERR_WORKSPACE, "workspace must be non-null and 256-byte aligned");
   LADIFF_REQUIRE((size_t)have >= need, LADIFF_ERR_WORKSPACE, "workspace too small: have %lld, need %zu", (long long)have, need);
   return 0;
 }
@@ -1148,6 +1172,31 @@ extern "C" int32_t ladiff_synthesize(LadiffHandle* m, LadiffHandle* cm, const fl
 extern "C" int32_t ladiff_set_conv_impl(LadiffHandle* h, int32_t impl) {
   LADIFF_REQUIRE(h && (impl == 0 || impl == 1), LADIFF_ERR_ARG, "ladiff_set_conv_impl: impl=%d", impl);
   h->conv_impl = impl;
+  return 0;
+}
+extern "C" int32_t ladiff_set_profiling(LadiffHandle* h, int32_t on) {
+  LADIFF_REQUIRE(h, LADIFF_ERR_ARG, "null handle");
+  h->profiling = on ? 1 : 0;
+  if (!on) h->last_plan = nullptr;
+  return 0;
+}
+// out[0] = summed duration (ms) of the conv launches of the most recent UNet evaluation, out[1] = their algorithmic FLOPs,
+// out[2] = number of conv launches, out[3] = duration (ms) of that whole evaluation.  Synchronises the device.
+extern "C" int32_t ladiff_profile_report(LadiffHandle* h, double* out4) {
+  LADIFF_REQUIRE(h && out4, LADIFF_ERR_ARG, "null argument");
+  LADIFF_REQUIRE(h->last_plan != nullptr, LADIFF_ERR_STATE, "no profiled UNet evaluation yet");
+  LADIFF_CUDA_OK(cudaDeviceSynchronize());
+  Plan* pl = h->last_plan;
+  double ms = 0.0, fl = 0.0, n = 0.0;
+  for (size_t i = 0; i < pl->ops.size(); ++i) {
+    if (pl->op_flops[i] <= 0.0) continue;
+    float t = 0.f;
+    LADIFF_CUDA_OK(cudaEventElapsedTime(&t, pl->ev[2 * i], pl->ev[2 * i + 1]));
+    ms += t; fl += pl->op_flops[i]; n += 1.0;
+  }
+  float tot = 0.f;
+  LADIFF_CUDA_OK(cudaEventElapsedTime(&tot, pl->ev[2 * pl->ops.size()], pl->ev[2 * pl->ops.size() + 1]));
+  out4[0] = ms; out4[1] = fl; out4[2] = n; out4[3] = tot;
   return 0;
 }
 extern "C" int64_t ladiff_take_launch_count(LadiffHandle* h) {

@@ -320,13 +320,13 @@ int tc_conv_launch(const TcConvParams& p, int B, cudaStream_t st) {
   LADIFF_REQUIRE(p.Cout % TC_BM == 0 && p.NT % 16 == 0 && p.NT >= 16 && p.NT <= 256 && p.nseg >= 1 && p.nseg <= TC_MAX_SEG,
                  LADIFF_ERR_ARG, "tc_conv: bad tile config Cout=%d NT=%d nseg=%d", p.Cout, p.NT, p.nseg);
   LADIFF_REQUIRE(p.stages >= 2 && p.stages <= 8, LADIFF_ERR_ARG, "tc_conv: stages=%d", p.stages);
-  static bool attr_set = false;
-  if (!attr_set) {
-    LADIFF_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
   const size_t smem = tc_smem_bytes(p.NT, p.stages);
-  LADIFF_REQUIRE(smem <= 227 * 1024, LADIFF_ERR_ARG, "tc_conv: smem %zu too large", smem);
+  LADIFF_REQUIRE(smem <= 226 * 1024, LADIFF_ERR_ARG, "tc_conv: smem %zu too large", smem);
+  static size_t attr_set = 0;     // opt-in dynamic shared memory (static barriers take a few hundred bytes of the 227 KB)
+  if (smem > attr_set) {
+    LADIFF_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = smem;
+  }
   dim3 grid(cdiv(p.Lout, p.NT), p.Cout / TC_BM, B);
   tc_conv_kernel<<<grid, 128, smem, st>>>(p);
   LADIFF_CUDA_OK(cudaGetLastError());

@@ -1,0 +1,17 @@
+"""Per-launch CUDA-event timing of the tcgen05 conv kernel inside a UNet evaluation (bench.py roofline)."""
+import ctypes
+
+from . import _lib
+
+
+def enable(model, on=True):
+    _lib.check(model._lib.ladiff_set_profiling(model._h, 1 if on else 0), "set_profiling")
+
+
+def report(model):
+    """dict(conv_ms, conv_flops, conv_launches, eval_ms) for the most recent profiled UNet evaluation, or None."""
+    out = (ctypes.c_double * 4)()
+    rc = model._lib.ladiff_profile_report(model._h, out)
+    if rc != 0:
+        return None
+    return dict(conv_ms=out[0], conv_flops=out[1], conv_launches=int(out[2]), eval_ms=out[3])
