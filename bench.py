@@ -218,6 +218,13 @@ def run_ours(a, cfg):
     launches = model.take_launch_count() + cmodel.take_launch_count()
     launches = launches * a.steps // (a.steps + a.warmup)
     prof = profiling.report(model)
+    if a.dump_profile and rank == 0:
+        rows = profiling.dump(model)
+        os.makedirs(os.path.dirname(os.path.abspath(a.dump_profile)), exist_ok=True)
+        with open(a.dump_profile, "w") as f:
+            f.write("# per tcgen05-conv launch of one UNet evaluation: ms, algorithmic GFLOP, TFLOP/s, shape\n")
+            for ms_i, gf, label in rows:
+                f.write(f"{ms_i:.4f} {gf:9.3f} {gf / ms_i if ms_i > 0 else 0:8.1f}  {label}\n")
     profiling.enable(model, False)
     # ---- end-to-end through the public API with HOST buffers (H2D + D2H inside the timed region)
     ms_e2e = timed(lambda w, i: keep.__setitem__(slice(0, 1), [synthesize(model, cmodel, w, n_steps=N, noise=None, seed=i)]), host_sets)
@@ -265,6 +272,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="clips per GPU (default: the config's)")
     ap.add_argument("--ddpm_steps", type=int, default=0)
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--dump_profile", default="", help="write the per-conv-launch table of one UNet evaluation here")
     a = ap.parse_args()
     cfg = dict(CONFIGS[a.config])
     if a.ddpm_steps:

@@ -165,6 +165,8 @@ int32_t ladiff_set_conv_impl(LadiffHandle* h, int32_t impl);
  * evaluation: out4 = {conv ms, conv algorithmic FLOPs, conv launches, whole-evaluation ms}. */
 int32_t ladiff_set_profiling(LadiffHandle* h, int32_t on);
 int32_t ladiff_profile_report(LadiffHandle* h, double* out4);
+/* Text table of the same evaluation, one line per conv launch: "<ms> <algorithmic GFLOP> <shape label>". */
+int32_t ladiff_profile_dump(LadiffHandle* h, char* buf, int64_t cap);
 /* Kernel launches issued by this handle since the last call (for bench.py's gpu_launches). */
 int64_t ladiff_take_launch_count(LadiffHandle* h);
 

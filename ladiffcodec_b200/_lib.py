@@ -54,6 +54,7 @@ SIGNATURES = {
     "ladiff_take_launch_count": (c_i64, [c_vp]),
     "ladiff_set_profiling": (c_i32, [c_vp, c_i32]),
     "ladiff_profile_report": (c_i32, [c_vp, ctypes.POINTER(ctypes.c_double)]),
+    "ladiff_profile_dump": (c_i32, [c_vp, ctypes.c_char_p, c_i64]),
 }
 
 _lib = None

@@ -97,6 +97,7 @@ struct Plan {
   UnetBufs bufs;
   std::vector<Op> ops;
   std::vector<double> op_flops;          // algorithmic FLOPs of conv ops (2*Cout*Cin*k*Lout*B), 0 for the others
+  std::vector<std::string> op_label;
   std::vector<cudaEvent_t> ev;           // profiling: [2*i], [2*i+1] around conv op i; last two around the whole evaluation
   long long launches_per_run = 0;
   ~Plan() { for (auto e : ev) cudaEventDestroy(e); }
@@ -729,6 +730,13 @@ struct PlanBuilder {
     });
     pl->op_flops.resize(pl->ops.size(), 0.0);
     pl->op_flops.back() = 2.0 * pc.CoutV * (double)pc.Ktot * Lout * B;
+    pl->op_label.resize(pl->ops.size());
+    {
+      char buf[160];
+      snprintf(buf, sizeof(buf), "conv kind=%d Cout=%d Cin=%d k=%d Lout=%d NT=%d tiles=%d stages=%d stats=%d", pc.kind, pc.CoutV, pc.Cin,
+               pc.K, Lout, p.NT, nt_tiles * (pc.CoutV / TC_BM) * B, p.stages, want_stats ? 1 : 0);
+      pl->op_label.back() = buf;
+    }
     pl->launches_per_run++;
     return 0;
   }
@@ -1197,6 +1205,24 @@ extern "C" int32_t ladiff_profile_report(LadiffHandle* h, double* out4) {
   float tot = 0.f;
   LADIFF_CUDA_OK(cudaEventElapsedTime(&tot, pl->ev[2 * pl->ops.size()], pl->ev[2 * pl->ops.size() + 1]));
   out4[0] = ms; out4[1] = fl; out4[2] = n; out4[3] = tot;
+  return 0;
+}
+// Per-conv-launch table of the most recent profiled evaluation, one text line per launch: "<ms> <gflop> <label>".
+extern "C" int32_t ladiff_profile_dump(LadiffHandle* h, char* buf, int64_t cap) {
+  LADIFF_REQUIRE(h && buf && cap > 0, LADIFF_ERR_ARG, "null argument");
+  LADIFF_REQUIRE(h->last_plan != nullptr, LADIFF_ERR_STATE, "no profiled UNet evaluation yet");
+  LADIFF_CUDA_OK(cudaDeviceSynchronize());
+  Plan* pl = h->last_plan;
+  std::string out;
+  for (size_t i = 0; i < pl->ops.size(); ++i) {
+    if (pl->op_flops[i] <= 0.0) continue;
+    float t = 0.f;
+    LADIFF_CUDA_OK(cudaEventElapsedTime(&t, pl->ev[2 * i], pl->ev[2 * i + 1]));
+    char line[256];
+    snprintf(line, sizeof(line), "%.4f %.3f %s\n", t, pl->op_flops[i] * 1e-9, i < pl->op_label.size() ? pl->op_label[i].c_str() : "");
+    out += line;
+  }
+  snprintf(buf, (size_t)cap, "%s", out.c_str());
   return 0;
 }
 extern "C" int64_t ladiff_take_launch_count(LadiffHandle* h) {

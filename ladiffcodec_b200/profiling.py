@@ -15,3 +15,15 @@ def report(model):
     if rc != 0:
         return None
     return dict(conv_ms=out[0], conv_flops=out[1], conv_launches=int(out[2]), eval_ms=out[3])
+
+
+def dump(model):
+    """Per-launch table [(ms, gflop, label)] of the most recent profiled UNet evaluation."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    if model._lib.ladiff_profile_dump(model._h, buf, len(buf)) != 0:
+        return []
+    rows = []
+    for line in buf.value.decode().splitlines():
+        ms, gf, label = line.split(" ", 2)
+        rows.append((float(ms), float(gf), label))
+    return rows
