@@ -52,7 +52,7 @@ struct EncoderW { ConvW first, last; std::vector<ResBlockW> rb; std::vector<Conv
 struct DecoderW { ConvW first, last; std::vector<ConvTrW> up; std::vector<ResBlockW> rb; LstmW lstm; };
 
 // ---- folded UNet parameters
-enum ConvKind { CK_PLAIN = 0, CK_DOWN = 1, CK_UP = 2 };
+enum ConvKind { CK_PLAIN = TC_KIND_PLAIN, CK_DOWN = TC_KIND_DOWN, CK_UP = TC_KIND_UP };
 struct PackedConv {
   bf16* w = nullptr; const float* bias = nullptr;
   int CoutV = 0, Cin = 0, K = 1, Ktot = 0, kind = CK_PLAIN;
@@ -681,60 +681,37 @@ struct PlanBuilder {
   H* h; Plan* pl; int B;
   // conv: `in` has Lin rows; writes Lout rows into `out` (bf16) or out32 (fp32, contiguous [B][Lout][CoutV])
   int conv(const PackedConv& pc, ClView in, int Lin, ClView out, float* out32, bool want_stats, int* n_ntiles, ClView res) {
-    TcConvParams p;
-    memset(&p, 0, sizeof(p));
-    TcRefView rv;
-    int Lout = Lin, Lv = Lin, Cv = in.C, pitch_v = in.pitch;
     LADIFF_REQUIRE(in.C == pc.Cin, LADIFF_ERR_ARG, "plan: conv input has %d channels, weights expect %d", in.C, pc.Cin);
-    const int nch = pc.Cin / 64;
-    if (pc.kind == CK_DOWN) {
-      LADIFF_REQUIRE(Lin % 2 == 0, LADIFF_ERR_ARG, "plan: stride-2 conv needs an even length (%d)", Lin);
-      Lout = Lin / 2; Lv = Lin / 2; pitch_v = 2 * in.pitch; Cv = in.pitch + in.C;
-      const int sh[4] = {-1, 0, 0, 1}, c0[4] = {in.pitch, 0, in.pitch, 0};
-      p.nseg = 4;
-      for (int s = 0; s < 4; ++s) p.seg[s] = TcSeg{sh[s], c0[s], nch, 0, pc.CoutV};
-    } else if (pc.kind == CK_UP) {
-      p.nseg = 3;
-      p.seg[0] = TcSeg{-1, 0, nch, 0, pc.CoutV / 2};
-      p.seg[1] = TcSeg{0, 0, nch, 0, pc.CoutV};
-      p.seg[2] = TcSeg{1, 0, nch, pc.CoutV / 2, pc.CoutV};
-    } else {
-      p.nseg = pc.K;
-      LADIFF_REQUIRE(pc.K <= TC_MAX_SEG, LADIFF_ERR_ARG, "plan: K=%d", pc.K);
-      for (int s = 0; s < pc.K; ++s) p.seg[s] = TcSeg{s - (pc.K - 1) / 2, 0, nch, 0, pc.CoutV};
-    }
-    int nt_tiles = 0;
-    p.NT = tc_pick_nt(Lout, &nt_tiles);
-    p.stages = tc_pick_stages(p.NT);
-    p.Lout = Lout; p.Cout = pc.CoutV; p.bias = pc.bias;
-    p.tmW = pc.tmW;
-    TRY(tc_make_tmap_x(&p.tmX, in.p, B, Lv, Cv, pitch_v, in.bstride, p.NT));
-    if (out32) {
-      p.out = out32; p.out_f32 = 1; p.out_pitch = pc.CoutV; p.out_bstride = (long long)Lout * pc.CoutV; p.out_ch0 = 0;
-    } else if (pc.kind == CK_UP) {
-      p.out = out.p; p.out_pitch = 2 * out.pitch; p.out_bstride = out.bstride; p.out_ch0 = 0;
-      p.out_split = pc.CoutV / 2; p.out_jump = out.pitch - pc.CoutV / 2;
-    } else {
-      p.out = out.p; p.out_pitch = out.pitch; p.out_bstride = out.bstride; p.out_ch0 = 0;
-    }
-    if (want_stats) {
-      LADIFF_REQUIRE(nt_tiles * (pc.CoutV / 32) <= pl->bufs.stats_slots, LADIFF_ERR_WORKSPACE, "plan: stats buffer too small");
-      p.stats = pl->bufs.stats;
-    }
-    if (n_ntiles) *n_ntiles = nt_tiles;
-    if (res.p) { p.res = res.p; p.res_bstride = res.bstride; p.res_pitch = res.pitch; p.res_ch0 = 0; }
-    rv.x = in.p; rv.bstride = in.bstride; rv.pitch = pitch_v; rv.Lv = Lv; rv.Cv = Cv; rv.w = pc.w; rv.Ktot = pc.Ktot;
-    H* hh = h; const int BB = B;
-    pl->ops.push_back([hh, p, rv, BB](cudaStream_t st) {
-      return hh->conv_impl == 0 ? tc_conv_launch(p, BB, st) : tc_conv_ref_launch(p, rv, BB, st);
+    TcConvDesc d;
+    memset(&d, 0, sizeof(d));
+    d.kind = pc.kind; d.Cin = pc.Cin; d.K = pc.K; d.CoutV = pc.CoutV; d.w = pc.w; d.tmW = &pc.tmW; d.Ktot = pc.Ktot; d.bias = pc.bias;
+    d.x = in.p; d.x_bstride = in.bstride; d.x_pitch = in.pitch; d.Lin = Lin;
+    d.out = out.p; d.out_bstride = out.bstride; d.out_pitch = out.pitch; d.out32 = out32;
+    d.stats = want_stats ? pl->bufs.stats : nullptr;
+    if (res.p) { d.res = res.p; d.res_bstride = res.bstride; d.res_pitch = res.pitch; }
+    d.B = B;
+    TcConvParams ps, pu;
+    TcRefView rv;
+    d.tap_share = 1;
+    TRY(tc_conv_plan(d, &ps, &rv));
+    d.tap_share = 0;
+    TRY(tc_conv_plan(d, &pu, nullptr));
+    LADIFF_REQUIRE(ps.n_ptiles == pu.n_ptiles || !want_stats, LADIFF_ERR_ARG, "plan: tap-shared and per-tap tilings disagree");
+    if (want_stats)
+      LADIFF_REQUIRE(ps.n_ptiles * (pc.CoutV / 32) <= pl->bufs.stats_slots, LADIFF_ERR_WORKSPACE, "plan: stats buffer too small");
+    if (n_ntiles) *n_ntiles = ps.n_ptiles;
+    H* hh = h;
+    pl->ops.push_back([hh, ps, pu, rv](cudaStream_t st) {
+      if (hh->conv_impl == 1) return tc_conv_ref_launch(ps, rv, st);
+      return tc_conv_launch(hh->conv_impl == 2 ? pu : ps, st);
     });
     pl->op_flops.resize(pl->ops.size(), 0.0);
-    pl->op_flops.back() = 2.0 * pc.CoutV * (double)pc.Ktot * Lout * B;
+    pl->op_flops.back() = 2.0 * pc.CoutV * (double)pc.Ktot * ps.Lout * B;
     pl->op_label.resize(pl->ops.size());
     {
-      char buf[160];
-      snprintf(buf, sizeof(buf), "conv kind=%d Cout=%d Cin=%d k=%d Lout=%d NT=%d tiles=%d stages=%d stats=%d", pc.kind, pc.CoutV, pc.Cin,
-               pc.K, Lout, p.NT, nt_tiles * (pc.CoutV / TC_BM) * B, p.stages, want_stats ? 1 : 0);
+      char buf[200];
+      snprintf(buf, sizeof(buf), "conv kind=%d Cout=%d Cin=%d k=%d Lout=%d NT=%d nclip=%d tiles=%d sa=%d sb=%d stats=%d direct=%d", pc.kind,
+               pc.CoutV, pc.Cin, pc.K, ps.Lout, ps.NT, ps.NCLIP, ps.MT * ps.n_ntiles, ps.sa, ps.sb, want_stats ? 1 : 0, ps.direct);
       pl->op_label.back() = buf;
     }
     pl->launches_per_run++;
@@ -1178,7 +1155,7 @@ extern "C" int32_t ladiff_synthesize(LadiffHandle* m, LadiffHandle* cm, const fl
 }
 
 extern "C" int32_t ladiff_set_conv_impl(LadiffHandle* h, int32_t impl) {
-  LADIFF_REQUIRE(h && (impl == 0 || impl == 1), LADIFF_ERR_ARG, "ladiff_set_conv_impl: impl=%d", impl);
+  LADIFF_REQUIRE(h && impl >= 0 && impl <= 2, LADIFF_ERR_ARG, "ladiff_set_conv_impl: impl=%d", impl);
   h->conv_impl = impl;
   return 0;
 }
@@ -1234,38 +1211,40 @@ extern "C" int64_t ladiff_take_launch_count(LadiffHandle* h) {
 
 extern "C" int32_t ladiff_op_conv1d_cl(const void* x_bf16, const float* w, const float* bias, int32_t B, int32_t L, int32_t Cin,
                                        int32_t Cout, int32_t k, void* y, int32_t y_f32, int32_t impl, float* gn_stats) {
-  LADIFF_REQUIRE(x_bf16 && w && y && Cin % 64 == 0 && Cout % 128 == 0 && k >= 1 && k <= TC_MAX_SEG && (k & 1), LADIFF_ERR_ARG,
-                 "ladiff_op_conv1d_cl: Cin %% 64, Cout %% 128, odd k <= %d required", TC_MAX_SEG);
+  LADIFF_REQUIRE(x_bf16 && w && y && Cin % 64 == 0 && Cout % 128 == 0 && k >= 1 && k <= TC_MAX_TAPS && (k & 1), LADIFF_ERR_ARG,
+                 "ladiff_op_conv1d_cl: Cin %% 64, Cout %% 128, odd k <= %d required", TC_MAX_TAPS);
+  LADIFF_REQUIRE(impl >= 0 && impl <= 2, LADIFF_ERR_ARG, "ladiff_op_conv1d_cl: impl=%d", impl);
   bf16* wp = nullptr; float2* stats = nullptr;
   LADIFF_CUDA_OK(cudaMalloc((void**)&wp, sizeof(bf16) * (size_t)Cout * Cin * k));
   int rc = pack_conv_launch(w, wp, Cout, Cin, k, 0, 0);
+  CUtensorMap tmW;
+  if (!rc) rc = tc_make_tmap_w(&tmW, wp, Cout, Cin * k);
+  TcConvDesc d;
+  memset(&d, 0, sizeof(d));
+  d.kind = TC_KIND_PLAIN; d.Cin = Cin; d.K = k; d.CoutV = Cout; d.w = wp; d.tmW = &tmW; d.Ktot = Cin * k; d.bias = bias;
+  d.x = (const bf16*)x_bf16; d.x_bstride = (long long)L * Cin; d.x_pitch = Cin; d.Lin = L;
+  if (y_f32) d.out32 = (float*)y;
+  else { d.out = (bf16*)y; d.out_bstride = (long long)L * Cout; d.out_pitch = Cout; }
+  d.B = B; d.tap_share = impl == 2 ? 0 : 1;
   TcConvParams p;
-  memset(&p, 0, sizeof(p));
-  int nt_tiles = 0;
-  p.NT = tc_pick_nt(L, &nt_tiles);
-  p.stages = tc_pick_stages(p.NT);
-  p.nseg = k;
-  for (int s = 0; s < k; ++s) p.seg[s] = TcSeg{s - (k - 1) / 2, 0, Cin / 64, 0, Cout};
-  p.Lout = L; p.Cout = Cout; p.bias = bias; p.out = y; p.out_f32 = y_f32; p.out_pitch = Cout; p.out_bstride = (long long)L * Cout;
-  if (!rc) rc = tc_make_tmap_w(&p.tmW, wp, Cout, Cin * k);
-  if (!rc) rc = tc_make_tmap_x(&p.tmX, (const bf16*)x_bf16, B, L, Cin, Cin, (long long)L * Cin, p.NT);
+  TcRefView rv;
+  if (!rc) rc = tc_conv_plan(d, &p, &rv);
   if (!rc && gn_stats) {
-    if (cudaMalloc((void**)&stats, sizeof(float2) * (size_t)B * nt_tiles * (Cout / 32)) != cudaSuccess) rc = LADIFF_ERR_CUDA;
+    if (cudaMalloc((void**)&stats, sizeof(float2) * (size_t)B * p.n_ptiles * (Cout / 32)) != cudaSuccess) rc = LADIFF_ERR_CUDA;
     p.stats = stats;
   }
-  TcRefView rv;
-  rv.x = (const bf16*)x_bf16; rv.bstride = (long long)L * Cin; rv.pitch = Cin; rv.Lv = L; rv.Cv = Cin; rv.w = wp; rv.Ktot = Cin * k;
-  if (!rc) rc = impl == 0 ? tc_conv_launch(p, B, 0) : tc_conv_ref_launch(p, rv, B, 0);
+  if (!rc) rc = impl == 1 ? tc_conv_ref_launch(p, rv, 0) : tc_conv_launch(p, 0);
   cudaError_t e = cudaDeviceSynchronize();
   if (!rc && e != cudaSuccess) { ladiff_set_error("ladiff_op_conv1d_cl: %s", cudaGetErrorString(e)); rc = LADIFF_ERR_CUDA; }
   if (!rc && gn_stats) {   // reduce the per-tile partials on the host: [B][Cout/32][2]
-    std::vector<float2> hst((size_t)B * nt_tiles * (Cout / 32));
+    const int npt = p.n_ptiles;
+    std::vector<float2> hst((size_t)B * npt * (Cout / 32));
     cudaMemcpy(hst.data(), stats, sizeof(float2) * hst.size(), cudaMemcpyDeviceToHost);
     std::vector<float> red((size_t)B * (Cout / 32) * 2, 0.f);
     for (int b = 0; b < B; ++b)
-      for (int t = 0; t < nt_tiles; ++t)
+      for (int t = 0; t < npt; ++t)
         for (int s = 0; s < Cout / 32; ++s) {
-          const float2 v = hst[((size_t)b * nt_tiles + t) * (Cout / 32) + s];
+          const float2 v = hst[((size_t)b * npt + t) * (Cout / 32) + s];
           red[((size_t)b * (Cout / 32) + s) * 2] += v.x;
           red[((size_t)b * (Cout / 32) + s) * 2 + 1] += v.y;
         }

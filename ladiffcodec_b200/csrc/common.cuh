@@ -33,54 +33,91 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ------------------------------------------------------------------ tcgen05 implicit-GEMM conv (tc_conv.cu)
-// out[b, l, m] = bias[m] + sum over K-segments s, channels c:  W[m, kofs_s + c] * X[b, l + shift_s, ch0_s + c]
-// X is a channels-last bf16 view [B][Lv][Cv] (row pitch / batch stride in elements), zero outside [0,Lv).
-#define TC_MAX_SEG 8
+// out[b, l, m] = bias[m] + sum over groups g, taps t of g, channels c < 64*nchunk_g:
+//                  W[m, kofs_t + c] * X[b, l + shift_g + row_off_t, ch0_g + c]
+// X is a channels-last bf16 view [B][Lv][Cv] (row pitch / clip stride in elements), zero outside [0,Lv).
+// A group is one activation tile in shared memory (one TMA load per 64-channel chunk) that all of its taps read at
+// different row offsets — a k-tap conv loads its activations once, not k times.
+#define TC_MAX_GRP 7
+#define TC_MAX_TAPS 7
 #define TC_BM 128
 #define TC_BK 64
 
-struct TcSeg {
-  int shift;    // position shift of this tap (in view rows)
-  int ch0;      // first channel of this segment in the view
-  int nchunk;   // number of 64-channel chunks
-  int m_lo;     // segment contributes only to output-channel tiles m0 in [m_lo, m_hi)
+struct TcTap {
+  int row_off;  // row offset of this tap inside the group's shared-memory tile (0..7)
+  int kofs;     // K offset of this tap's weights (chunk c adds 64*c)
+  int m_lo;     // the tap contributes only to output-channel tiles m0 in [m_lo, m_hi)
   int m_hi;
+};
+struct TcGroup {
+  int ch0;      // first channel of the group in the view
+  int shift;    // view row of tile row 0 relative to the first output position of the tile
+  int nchunk;   // 64-channel chunks
+  int ntaps;
+  TcTap tap[TC_MAX_TAPS];
+};
+
+enum { TC_KIND_PLAIN = 0, TC_KIND_DOWN = 1, TC_KIND_UP = 2 };
+
+// What one conv launch computes (host-side description; tc_conv_plan turns it into launch parameters).
+struct TcConvDesc {
+  int kind;                 // TC_KIND_*: plain (odd k, zero pad (k-1)/2), stride-2 k=4 pad 1, nearest-x2 + k=3 folded
+  int Cin, K;               // real input channels, taps
+  int CoutV;                // output channels computed (2*Cout for TC_KIND_UP), multiple of 128
+  const bf16* w;            // packed [CoutV][Ktot]
+  const CUtensorMap* tmW;   // box {64, 128}, SWIZZLE_128B
+  int Ktot;
+  const float* bias;        // [CoutV] or null
+  const bf16* x; long long x_bstride; int x_pitch; int Lin;   // input view (Lin rows of Cin channels per clip)
+  bf16* out; long long out_bstride; int out_pitch;            // bf16 output view (Lout rows; 2*Lout rows for UP)
+  float* out32;             // if set: fp32 output, contiguous [B][Lout][CoutV] (direct epilogue)
+  float2* stats;            // optional GroupNorm partials [B][n_ptiles][CoutV/32]
+  const bf16* res; long long res_bstride; int res_pitch;      // optional residual (direct epilogue)
+  int B;
+  int tap_share;            // 1: all taps of a chunk read one shared activation tile; 0: one tile load per tap
 };
 
 struct TcConvParams {
-  CUtensorMap tmW;  // weights  [Cout][Ktot] bf16 row-major, box {64, 128}, SWIZZLE_128B
-  CUtensorMap tmX;  // activations view [B][Lv][Cv] bf16, box {64, NT, 1}, SWIZZLE_128B, OOB -> 0
-  TcSeg seg[TC_MAX_SEG];
-  int nseg;
-  int NT;            // positions per tile (multiple of 16, 16..256)
-  int stages;        // pipeline depth
-  int Lout;          // valid output rows per clip
-  int Cout;          // total output channels (multiple of 128)
+  CUtensorMap tmW;   // weights  [Cout][Ktot] bf16 row-major, box {64, 128}, SWIZZLE_128B
+  CUtensorMap tmX;   // activations view [B][Lv][Cv] bf16, box {64, BOXROWS, 1}, SWIZZLE_128B, OOB -> 0
+  CUtensorMap tmY;   // output {Cc, phases, rows, B} bf16, box {128, 1, CR, 1}
+  CUtensorMap tmYr;  // same, box rows = NT % CR (last chunk of a single-clip tile)
+  TcGroup grp[TC_MAX_GRP];
+  int ngrp;
+  int NT;            // output rows per clip region of a tile
+  int NCLIP;         // clip regions per tile (1 = single-clip position tiles)
+  int BOXROWS;       // rows per activation TMA box
+  int NMMA;          // MMA N = NCLIP*NT (multiple of 16, <= 256)
+  int CR;            // rows per store chunk
+  int n_ptiles;      // position tiles per clip (1 when NCLIP > 1)
+  int n_ntiles;      // N tiles in total
+  int MT;            // Cout/128
+  int sa, sb;        // weight / activation ring depths
+  int b_slot_bytes;
+  int direct;        // 1: direct register->global epilogue (fp32 output and/or residual); 0: smem-staged TMA store
+  int up_cout;       // TC_KIND_UP: real Cout (output phase = m0 / up_cout); else 0
+  int B, Lout, Cout;
   const float* bias; // [Cout] or null
-  void* out;         // bf16 or f32, channels-last
-  long long out_bstride;  // elements between clips
-  int out_pitch;     // elements between rows
-  int out_ch0;       // channel offset of m = 0
-  int out_split;     // channels m >= out_split land at m + out_jump (nearest-x2 upsample interleave); 0 = off
-  int out_jump;
-  int out_f32;       // 1: float output
-  float2* stats;     // optional GroupNorm partials [B][n_ntiles][Cout/32] (sum, sumsq) of the fp32 result
-  const bf16* res;   // optional residual added in the epilogue (channels-last bf16, same rows/channels as the output)
+  float2* stats;     // optional GroupNorm partials [B][n_ptiles][Cout/32] (sum, sumsq) of the fp32 result
+  // direct epilogue only
+  void* out;
+  long long out_bstride;
+  int out_pitch;
+  int out_f32;
+  const bf16* res;
   long long res_bstride;
   int res_pitch;
-  int res_ch0;
 };
 
-// X view description used by the SIMT check kernel (same math, no tensor maps)
+// X view description used by the SIMT check kernel (same math, no tensor maps, no tensor cores)
 struct TcRefView {
   const bf16* x; long long bstride; int pitch; int Lv; int Cv;
   const bf16* w; int Ktot;
+  bf16* out; long long out_bstride; int out_pitch;   // bf16 output view incl. the UP phase interleave (host fills)
 };
 
-int tc_conv_launch(const TcConvParams& p, int B, cudaStream_t st);
-int tc_conv_ref_launch(const TcConvParams& p, const TcRefView& v, int B, cudaStream_t st);
+int tc_conv_plan(const TcConvDesc& d, TcConvParams* p, TcRefView* rv);
+int tc_conv_launch(const TcConvParams& p, cudaStream_t st);
+int tc_conv_ref_launch(const TcConvParams& p, const TcRefView& v, cudaStream_t st);
 int tc_make_tmap_w(CUtensorMap* tm, const bf16* w, int Cout, int Ktot);
-int tc_make_tmap_x(CUtensorMap* tm, const bf16* x, int B, int Lv, int Cv, int pitch, long long bstride, int NT);
-int tc_pick_nt(int L, int* n_tiles);
-size_t tc_smem_bytes(int NT, int stages);
-int tc_pick_stages(int NT);
+int tc_num_sms();

@@ -4,18 +4,30 @@
 // on channels-last bf16 activations with fp32 accumulation in TMEM.
 //
 //   D[m, n] (TMEM, fp32; lane = output channel m, column = position n)
-//     = sum over K-segments (conv taps / concat halves) and 64-channel chunks of
-//       A = W[m0:m0+128, k:k+64]      (bf16, K-major, TMA 2D, SWIZZLE_128B)
-//       B = X[b, l0+shift : +NT, c:c+64] (bf16, K-major, TMA 3D, SWIZZLE_128B, OOB rows -> 0 = conv zero padding)
+//     = sum over groups / 64-channel chunks / taps of
+//       A = W[m0:m0+128, kofs_tap + 64c : +64]            (bf16, K-major, TMA 2D, SWIZZLE_128B)
+//       B = X[b, l0+shift+row_off_tap : +N, ch0+64c : +64] (bf16, K-major, TMA 3D, SWIZZLE_128B, OOB rows -> 0 = zero padding)
 //
-// One CTA per (position tile, 128-channel tile, clip).  Warp 0 lane 0 = TMA producer, warp 1 lane 0 =
-// MMA issuer (tcgen05.mma cta_group::1 kind::f16, M=128, N=NT, K=16), all four warps = epilogue
-// (tcgen05.ld 32x32b -> +bias -> GroupNorm partial sums -> channels-last store).
+// The activation tile of a chunk is loaded ONCE with its halo rows; every tap reads it through a shared-memory
+// descriptor whose start address is advanced by row_off*128 B (the 128B-swizzle XOR is a function of the absolute
+// shared-memory address, so a row-shifted start stays consistent with what TMA wrote).
+//
+// Persistent, warp-specialised CTAs (one per SM):
+//   warp 0    TMA producer (two rings: weights 16 KB slots, activations)
+//   warp 1    TMEM allocator + MMA issuer (tcgen05.mma cta_group::1 kind::f16, M=128, N<=256, K=16)
+//   warps 2-5 epilogue: tcgen05.ld -> +bias -> GroupNorm partial sums -> bf16 -> smem staging -> TMA store
+// Two TMEM accumulator stages, so the epilogue of tile i overlaps the main loop of tile i+1.
+// Short clips (L < 128) are packed several per tile (one TMA box per clip, per-clip zero padding kept).
 #include <cudaTypedefs.h>
 
 #include "common.cuh"
 
 namespace {
+
+constexpr int kThreads = 192;
+constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;  // 16 KB
+constexpr int kMaxSA = 8, kMaxSB = 4;
+constexpr size_t kSmemLimit = 232448 - 1024;     // 227 KB minus the static barriers
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -24,6 +36,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // Parity wait with a watchdog: a protocol bug traps (launch error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -40,7 +55,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     if (ok) return;
     if (spins == 64) t0 = clock64();
-    if (spins > 64 && (spins & 1023) == 0 && clock64() - t0 > 8000000000LL) __trap();
+    if (spins > 64 && (spins & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();
   }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
@@ -55,6 +70,16 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -82,32 +107,46 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;  // 16 KB
+struct TileCoord { int m0, b0, l0, pt; };
+__device__ __forceinline__ TileCoord decode_tile(const TcConvParams& p, int t) {
+  TileCoord c;
+  const int mt = t % p.MT, nt = t / p.MT;
+  c.m0 = mt * TC_BM;
+  if (p.NCLIP == 1) { c.pt = nt % p.n_ptiles; c.b0 = nt / p.n_ptiles; c.l0 = c.pt * p.NT; }
+  else { c.pt = 0; c.b0 = nt * p.NCLIP; c.l0 = 0; }
+  return c;
+}
 
-__global__ void __launch_bounds__(128) tc_conv_kernel(const __grid_constant__ TcConvParams p) {
+__global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_constant__ TcConvParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[8];
-  __shared__ __align__(8) uint64_t empty_bar[8];
-  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ __align__(8) uint64_t full_a[kMaxSA];
+  __shared__ __align__(8) uint64_t empty_a[kMaxSA];
+  __shared__ __align__(8) uint64_t full_b[kMaxSB];
+  __shared__ __align__(8) uint64_t empty_b[kMaxSB];
+  __shared__ __align__(8) uint64_t tmem_full[2];
+  __shared__ __align__(8) uint64_t tmem_empty[2];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nt_idx = blockIdx.x, m0 = blockIdx.y * TC_BM, b = blockIdx.z;
-  const int l0 = nt_idx * p.NT;
-  const uint32_t b_bytes = (uint32_t)p.NT * 128u;
-  const uint32_t stage_bytes = A_BYTES + b_bytes;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < p.NT) tmem_cols <<= 1;
+  const uint32_t a_ring = smem_base;
+  const uint32_t b_ring = a_ring + (uint32_t)p.sa * A_BYTES;
+  const uint32_t stage0 = b_ring + (uint32_t)p.sb * (uint32_t)p.b_slot_bytes;
+  uint32_t acc_stride = 32;
+  while ((int)acc_stride < p.NMMA) acc_stride <<= 1;
+  const uint32_t tmem_cols = 2 * acc_stride;
+  const int total_tiles = p.MT * p.n_ntiles;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&accum_bar, 1);
+    for (int s = 0; s < p.sa; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
+    for (int s = 0; s < p.sb; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmW) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmX) : "memory");
+    if (!p.direct) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmY) : "memory");
   }
-  if (warp == 2) {
+  if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -116,123 +155,206 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const __grid_constant__ Tc
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp == 0 && lane == 0) {
-    // ---------------- TMA producer
-    int it = 0, kofs = 0;
-    for (int s = 0; s < p.nseg; ++s) {
-      const TcSeg sg = p.seg[s];
-      if (m0 >= sg.m_lo && m0 < sg.m_hi) {
-        for (int c = 0; c < sg.nchunk; ++c, ++it) {
-          const int st = it % p.stages;
-          mbar_wait(&empty_bar[st], ((it / p.stages) & 1) ^ 1);
-          mbar_expect_tx(&full_bar[st], stage_bytes);
-          const uint32_t a_dst = smem_base + st * stage_bytes;
-          tma_load_2d(a_dst, &p.tmW, &full_bar[st], kofs + c * TC_BK, m0);
-          tma_load_3d(a_dst + A_BYTES, &p.tmX, &full_bar[st], sg.ch0 + c * TC_BK, l0 + sg.shift, b);
-        }
-      }
-      kofs += sg.nchunk * TC_BK;
-    }
-  } else if (warp == 1 && lane == 0) {
-    // ---------------- MMA issuer.  Instruction descriptor (InstrDescriptor, mma_sm100_desc.hpp):
-    // c_format F32 (1<<4) | a_format BF16 (1<<7) | b_format BF16 (1<<10) | K-major A,B | N>>3 <<17 | M>>4 <<24
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-    int it = 0;
-    for (int s = 0; s < p.nseg; ++s) {
-      const TcSeg sg = p.seg[s];
-      if (m0 >= sg.m_lo && m0 < sg.m_hi) {
-        for (int c = 0; c < sg.nchunk; ++c, ++it) {
-          const int st = it % p.stages;
-          mbar_wait(&full_bar[st], (it / p.stages) & 1);
-          tc_fence_after();
-          const uint32_t a_addr = smem_base + st * stage_bytes;
-          const uint32_t b_addr = a_addr + A_BYTES;
-#pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k)
-            umma_bf16(tmem_base, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), idesc, (it > 0 || k > 0) ? 1u : 0u);
-          tc_commit(&empty_bar[st]);   // frees the smem slot once these MMAs have read it
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer
+      const uint32_t b_bytes = (uint32_t)(p.NCLIP * p.BOXROWS) * 128u;
+      int ia = 0, ib = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        for (int g = 0; g < p.ngrp; ++g) {
+          const TcGroup& gr = p.grp[g];
+          for (int c = 0; c < gr.nchunk; ++c) {
+            const int sbi = ib % p.sb;
+            mbar_wait(&empty_b[sbi], ((ib / p.sb) & 1) ^ 1);
+            mbar_expect_tx(&full_b[sbi], b_bytes);
+            const uint32_t b_dst = b_ring + (uint32_t)sbi * (uint32_t)p.b_slot_bytes;
+            for (int j = 0; j < p.NCLIP; ++j)
+              tma_load_3d(b_dst + (uint32_t)(j * p.BOXROWS) * 128u, &p.tmX, &full_b[sbi], gr.ch0 + c * TC_BK, tc.l0 + gr.shift, tc.b0 + j);
+            ++ib;
+            for (int tp = 0; tp < gr.ntaps; ++tp) {
+              const TcTap& tap = gr.tap[tp];
+              if (tc.m0 < tap.m_lo || tc.m0 >= tap.m_hi) continue;
+              const int sai = ia % p.sa;
+              mbar_wait(&empty_a[sai], ((ia / p.sa) & 1) ^ 1);
+              mbar_expect_tx(&full_a[sai], A_BYTES);
+              tma_load_2d(a_ring + (uint32_t)sai * A_BYTES, &p.tmW, &full_a[sai], tap.kofs + c * TC_BK, tc.m0);
+              ++ia;
+            }
+          }
         }
       }
     }
-    tc_commit(&accum_bar);             // accumulator complete
-  }
-  __syncwarp();
-
-  // ---------------- epilogue (all 4 warps; warp w owns TMEM lanes 32w..32w+31)
-  mbar_wait(&accum_bar, 0);
-  tc_fence_after();
-  {
-    const int ch = m0 + warp * 32 + lane;
-    const float bias = p.bias ? p.bias[ch] : 0.f;
-    const int oc = p.out_ch0 + ch + ((p.out_split && ch >= p.out_split) ? p.out_jump : 0);
-    const long long obase = (long long)b * p.out_bstride + oc;
-    float s1 = 0.f, s2 = 0.f;
-    const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (int c0 = 0; c0 < p.NT; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld16(tlane + (uint32_t)c0, r);
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer.  Instruction descriptor (InstrDescriptor, mma_sm100_desc.hpp):
+      // c_format F32 (1<<4) | a_format BF16 (1<<7) | b_format BF16 (1<<10) | K-major A,B | N>>3 <<17 | M>>4 <<24
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NMMA >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      int ia = 0, ib = 0, tl = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+        const TileCoord tc = decode_tile(p, t);
+        const int acc = tl & 1;
+        mbar_wait(&tmem_empty[acc], ((tl >> 1) & 1) ^ 1);     // the epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_stride;
+        uint32_t accumulate = 0;
+        for (int g = 0; g < p.ngrp; ++g) {
+          const TcGroup& gr = p.grp[g];
+          for (int c = 0; c < gr.nchunk; ++c) {
+            const int sbi = ib % p.sb;
+            mbar_wait(&full_b[sbi], (ib / p.sb) & 1);
+            const uint32_t b_addr = b_ring + (uint32_t)sbi * (uint32_t)p.b_slot_bytes;
+            for (int tp = 0; tp < gr.ntaps; ++tp) {
+              const TcTap& tap = gr.tap[tp];
+              if (tc.m0 < tap.m_lo || tc.m0 >= tap.m_hi) continue;
+              const int sai = ia % p.sa;
+              mbar_wait(&full_a[sai], (ia / p.sa) & 1);
+              tc_fence_after();
+              const uint32_t a_addr = a_ring + (uint32_t)sai * A_BYTES;
+              const uint32_t bt_addr = b_addr + (uint32_t)tap.row_off * 128u;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int l = l0 + c0 + j;
-        if (l < p.Lout) {
-          float v = __uint_as_float(r[j]) + bias;
-          s1 += v; s2 += v * v;
-          if (p.res) v += __bfloat162float(p.res[(long long)b * p.res_bstride + (long long)l * p.res_pitch + p.res_ch0 + ch]);
-          const long long o = obase + (long long)l * p.out_pitch;
-          if (p.out_f32) reinterpret_cast<float*>(p.out)[o] = v;
-          else reinterpret_cast<bf16*>(p.out)[o] = __float2bfloat16(v);
+              for (int k = 0; k < TC_BK / 16; ++k) {
+                umma_bf16(d_tmem, umma_desc(a_addr + k * 32), umma_desc(bt_addr + k * 32), idesc, accumulate);
+                accumulate = 1;
+              }
+              tc_commit(&empty_a[sai]);    // frees the weight slot once these MMAs have read it
+              ++ia;
+            }
+            tc_commit(&empty_b[sbi]);      // frees the activation slot after its last tap
+            ++ib;
+          }
+        }
+        tc_commit(&tmem_full[acc]);        // accumulator complete
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------- epilogue warps (warp w owns TMEM lanes 32*(w&3) .. +31)
+    const int q = warp & 3;
+    const bool issuer = threadIdx.x == 64;
+    const int Cc = p.up_cout ? p.up_cout : p.Cout;
+    int tl = 0, cc = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+      const TileCoord tc = decode_tile(p, t);
+      const int acc = tl & 1;
+      const int ch = tc.m0 + q * 32 + lane;
+      const float bias = p.bias ? p.bias[ch] : 0.f;
+      mbar_wait(&tmem_full[acc], (tl >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tlane = tmem_base + (uint32_t)acc * acc_stride + ((uint32_t)(q * 32) << 16);
+      for (int j = 0; j < p.NCLIP; ++j) {
+        const int b = tc.b0 + j;
+        int vr = p.Lout - tc.l0;                 // valid rows of this clip region
+        vr = vr > p.NT ? p.NT : vr;
+        if (b >= p.B) vr = 0;
+        float s1 = 0.f, s2 = 0.f;
+        for (int r0 = 0; r0 < p.NT; r0 += p.CR) {
+          if (vr <= r0) break;                   // uniform over the 128 epilogue threads
+          const int nrows = (p.NT - r0) < p.CR ? (p.NT - r0) : p.CR;
+          uint32_t stg = 0;
+          if (!p.direct) {
+            if (issuer) bulk_wait_read_1();      // the store issued two chunks ago has finished reading its buffer
+            epi_bar();
+            stg = stage0 + (uint32_t)(cc & 1) * (uint32_t)p.CR * 256u + (uint32_t)(q * 32 + lane) * 2u;
+          }
+          for (int c0 = 0; c0 < nrows; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(tlane + (uint32_t)(j * p.NT + r0 + c0), r);
+            if (!p.direct) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float v = __uint_as_float(r[i]) + bias;
+                if (r0 + c0 + i < vr) { s1 += v; s2 += v * v; }
+                const unsigned short hv = __bfloat16_as_ushort(__float2bfloat16(v));
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(stg + (uint32_t)(c0 + i) * 256u), "h"(hv) : "memory");
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int row = r0 + c0 + i;
+                if (row < vr) {
+                  const int l = tc.l0 + row;
+                  float v = __uint_as_float(r[i]) + bias;
+                  s1 += v; s2 += v * v;
+                  if (p.res) v += __bfloat162float(p.res[(long long)b * p.res_bstride + (long long)l * p.res_pitch + ch]);
+                  const long long o = (long long)b * p.out_bstride + (long long)l * p.out_pitch + ch;
+                  if (p.out_f32) reinterpret_cast<float*>(p.out)[o] = v;
+                  else reinterpret_cast<bf16*>(p.out)[o] = __float2bfloat16(v);
+                }
+              }
+            }
+          }
+          if (!p.direct) {
+            fence_async_smem();
+            epi_bar();
+            if (issuer) {
+              const uint32_t src = stage0 + (uint32_t)(cc & 1) * (uint32_t)p.CR * 256u;
+              tma_store_4d(nrows == p.CR ? &p.tmY : &p.tmYr, src, tc.m0 % Cc, tc.m0 / Cc, tc.l0 + r0, b);
+              bulk_commit();
+            }
+            ++cc;
+          }
+        }
+        if (p.stats && vr > 0) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+          }
+          if (lane == 0)
+            p.stats[((long long)b * p.n_ptiles + tc.pt) * (p.Cout / 32) + (tc.m0 / 32 + q)] = make_float2(s1, s2);
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);   // 4 warps -> accumulator stage free for the MMA issuer
     }
-    if (p.stats) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-      }
-      if (lane == 0)
-        p.stats[((long long)b * gridDim.x + nt_idx) * (p.Cout / 32) + (m0 / 32 + warp)] = make_float2(s1, s2);
-    }
+    if (issuer) bulk_wait_all();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
 
 // SIMT check kernel: identical operands, tiling and epilogue semantics, plain FMA loop.
-// grid (n_ntiles, Cout/32, B), 128 threads: lane = channel, warp w handles rows w, w+4, ...
+// grid (n_ptiles, Cout/32, B), 128 threads: lane = channel, warp w handles rows w, w+4, ...
 __global__ void __launch_bounds__(128) tc_conv_ref_kernel(TcConvParams p, TcRefView v) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nt_idx = blockIdx.x, ch = blockIdx.y * 32 + lane, b = blockIdx.z;
+  const int pt = blockIdx.x, ch = blockIdx.y * 32 + lane, b = blockIdx.z;
   const int m0 = (ch / TC_BM) * TC_BM;
-  const int l0 = nt_idx * p.NT;
+  const int l0 = pt * p.NT;
+  const int Cc = p.up_cout ? p.up_cout : p.Cout;
   const float bias = p.bias ? p.bias[ch] : 0.f;
-  const int oc = p.out_ch0 + ch + ((p.out_split && ch >= p.out_split) ? p.out_jump : 0);
-  const long long obase = (long long)b * p.out_bstride + oc;
   float s1 = 0.f, s2 = 0.f;
   for (int r = warp; r < p.NT; r += 4) {
     const int l = l0 + r;
     if (l >= p.Lout) break;
     float acc = 0.f;
-    int kofs = 0;
-    for (int s = 0; s < p.nseg; ++s) {
-      const TcSeg sg = p.seg[s];
-      const int row = l + sg.shift;
-      if (m0 >= sg.m_lo && m0 < sg.m_hi && row >= 0 && row < v.Lv) {
-        const bf16* xr = v.x + (long long)b * v.bstride + (long long)row * v.pitch + sg.ch0;
-        const bf16* wr = v.w + (long long)ch * v.Ktot + kofs;
-        for (int c = 0; c < sg.nchunk * TC_BK; ++c) acc += __bfloat162float(wr[c]) * __bfloat162float(xr[c]);
+    for (int g = 0; g < p.ngrp; ++g) {
+      const TcGroup& gr = p.grp[g];
+      for (int tp = 0; tp < gr.ntaps; ++tp) {
+        const TcTap& tap = gr.tap[tp];
+        const int row = l + gr.shift + tap.row_off;
+        if (m0 < tap.m_lo || m0 >= tap.m_hi || row < 0 || row >= v.Lv) continue;
+        const bf16* xr = v.x + (long long)b * v.bstride + (long long)row * v.pitch + gr.ch0;
+        const bf16* wr = v.w + (long long)ch * v.Ktot + tap.kofs;
+        for (int c = 0; c < gr.nchunk * TC_BK; ++c) acc += __bfloat162float(wr[c]) * __bfloat162float(xr[c]);
       }
-      kofs += sg.nchunk * TC_BK;
     }
     float val = acc + bias;
     s1 += val; s2 += val * val;
-    if (p.res) val += __bfloat162float(p.res[(long long)b * p.res_bstride + (long long)l * p.res_pitch + p.res_ch0 + ch]);
-    const long long o = obase + (long long)l * p.out_pitch;
-    if (p.out_f32) reinterpret_cast<float*>(p.out)[o] = val;
-    else reinterpret_cast<bf16*>(p.out)[o] = __float2bfloat16(val);
+    if (p.direct) {
+      if (p.res) val += __bfloat162float(p.res[(long long)b * p.res_bstride + (long long)l * p.res_pitch + ch]);
+      const long long o = (long long)b * p.out_bstride + (long long)l * p.out_pitch + ch;
+      if (p.out_f32) reinterpret_cast<float*>(p.out)[o] = val;
+      else reinterpret_cast<bf16*>(p.out)[o] = __float2bfloat16(val);
+    } else {
+      const int phase = ch / Cc, cc = ch % Cc, nph = p.up_cout ? 2 : 1;
+      v.out[(long long)b * v.out_bstride + (long long)(l * nph + phase) * v.out_pitch + cc] = __float2bfloat16(val);
+    }
   }
   if (p.stats) {
     __shared__ float red[2][4][32];
@@ -246,7 +368,7 @@ __global__ void __launch_bounds__(128) tc_conv_ref_kernel(TcConvParams p, TcRefV
         a += __shfl_xor_sync(0xffffffffu, a, o);
         c += __shfl_xor_sync(0xffffffffu, c, o);
       }
-      if (lane == 0) p.stats[((long long)b * gridDim.x + nt_idx) * (p.Cout / 32) + blockIdx.y] = make_float2(a, c);
+      if (lane == 0) p.stats[((long long)b * p.n_ptiles + pt) * (p.Cout / 32) + blockIdx.y] = make_float2(a, c);
     }
   }
 }
@@ -263,30 +385,45 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   return fn;
 }
 
-}  // namespace
-
-size_t tc_smem_bytes(int NT, int stages) { return (size_t)stages * (A_BYTES + (size_t)NT * 128) + 1024; }
-
-int tc_pick_stages(int NT) {
-  // as deep as fits in ~200 KB, at most 6
-  int s = (int)((200 * 1024) / (A_BYTES + NT * 128));
-  return s > 6 ? 6 : (s < 2 ? 2 : s);
+int make_tmap_x(CUtensorMap* tm, const bf16* x, int B, int Lv, int Cv, int pitch, long long bstride, int boxrows) {
+  auto enc = get_encode();
+  LADIFF_REQUIRE(enc != nullptr, LADIFF_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[3] = {(cuuint64_t)Cv, (cuuint64_t)Lv, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)pitch * 2, (cuuint64_t)bstride * 2};
+  cuuint32_t box[3] = {TC_BK, (cuuint32_t)boxrows, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)x, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LADIFF_REQUIRE(r == CUDA_SUCCESS, LADIFF_ERR_CUDA, "cuTensorMapEncodeTiled(X B%d L%d C%d pitch %d box %d) failed: %d", B, Lv, Cv,
+                 pitch, boxrows, (int)r);
+  return 0;
 }
 
-// Position-tile size for clips of length L: multiple of 16, <= 256, minimising padded work.
-int tc_pick_nt(int L, int* n_tiles) {
-  int best_nt = 0, best_n = 0;
-  long best_cost = -1;
-  const int nmin = cdiv(L, 256);
-  for (int n = nmin; n <= nmin + 3; ++n) {
-    int nt = cdiv(cdiv(L, n), 16) * 16;
-    if (nt > 256) continue;
-    if (nt < 16) nt = 16;
-    const long cost = (long)n * nt;
-    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_nt = nt; best_n = cdiv(L, nt); }
+// output map {Cc, phases, rows, B}: element (c, ph, l, b) at out[b*bstride + (l*phases + ph)*pitch + c]
+int make_tmap_y(CUtensorMap* tm, const bf16* out, int Cc, int phases, int rows, int B, int pitch, long long bstride, int boxrows) {
+  auto enc = get_encode();
+  LADIFF_REQUIRE(enc != nullptr, LADIFF_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[4] = {(cuuint64_t)Cc, (cuuint64_t)phases, (cuuint64_t)rows, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)pitch * 2 * phases, (cuuint64_t)bstride * 2};
+  cuuint32_t box[4] = {TC_BM, 1, (cuuint32_t)boxrows, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LADIFF_REQUIRE(r == CUDA_SUCCESS, LADIFF_ERR_CUDA, "cuTensorMapEncodeTiled(Y C%d ph%d rows%d B%d pitch %d box %d) failed: %d", Cc,
+                 phases, rows, B, pitch, boxrows, (int)r);
+  return 0;
+}
+
+}  // namespace
+
+int tc_num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
   }
-  if (n_tiles) *n_tiles = best_n;
-  return best_nt;
+  return n;
 }
 
 int tc_make_tmap_w(CUtensorMap* tm, const bf16* w, int Cout, int Ktot) {
@@ -302,39 +439,144 @@ int tc_make_tmap_w(CUtensorMap* tm, const bf16* w, int Cout, int Ktot) {
   return 0;
 }
 
-int tc_make_tmap_x(CUtensorMap* tm, const bf16* x, int B, int Lv, int Cv, int pitch, long long bstride, int NT) {
-  auto enc = get_encode();
-  LADIFF_REQUIRE(enc != nullptr, LADIFF_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-  cuuint64_t dims[3] = {(cuuint64_t)Cv, (cuuint64_t)Lv, (cuuint64_t)B};
-  cuuint64_t strides[2] = {(cuuint64_t)pitch * 2, (cuuint64_t)bstride * 2};
-  cuuint32_t box[3] = {TC_BK, (cuuint32_t)NT, 1};
-  cuuint32_t es[3] = {1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)x, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  LADIFF_REQUIRE(r == CUDA_SUCCESS, LADIFF_ERR_CUDA, "cuTensorMapEncodeTiled(X B%d L%d C%d pitch %d NT %d) failed: %d", B, Lv, Cv,
-                 pitch, NT, (int)r);
+// Tile shape for clips of Lout rows: minimise rounds-over-the-SMs x per-tile cost; ties go to the wider tile (less operand traffic).
+static void pick_tiling(int Lout, int B, int MT, int halo2, int* NT, int* NCLIP, int* n_ptiles) {
+  const int nsm = tc_num_sms();
+  long best = -1;
+  const int maxn = halo2 ? 240 : 256;
+  if (Lout + halo2 <= 120) {                      // several clips per tile: region = clip + halo rows, multiple of 16
+    const int rp = cdiv(Lout + halo2, 16) * 16;
+    for (int nc = 256 / rp; nc >= 1; --nc) {
+      if (nc > B && nc > 1) continue;
+      const long tiles = (long)MT * cdiv(B, nc);
+      const long cost = (long)cdiv((int)tiles, nsm) * (nc * rp + 32);
+      if (best < 0 || cost < best) { best = cost; *NT = rp; *NCLIP = nc; *n_ptiles = 1; }
+    }
+    return;
+  }
+  for (int nt = maxn; nt >= 64; nt -= 16) {
+    const int np = cdiv(Lout, nt);
+    const long tiles = (long)MT * B * np;
+    const long cost = (long)cdiv((int)tiles, nsm) * (nt + 32);
+    if (best < 0 || cost < best) { best = cost; *NT = nt; *NCLIP = 1; *n_ptiles = np; }
+  }
+}
+
+int tc_conv_plan(const TcConvDesc& d, TcConvParams* pp, TcRefView* rv) {
+  TcConvParams& p = *pp;
+  memset(&p, 0, sizeof(p));
+  LADIFF_REQUIRE(d.CoutV % TC_BM == 0 && d.Cin % TC_BK == 0 && d.B >= 1, LADIFF_ERR_ARG, "tc_conv: CoutV=%d Cin=%d B=%d", d.CoutV, d.Cin, d.B);
+  const int nch = d.Cin / TC_BK;
+  int Lout = d.Lin, Lv = d.Lin, Cv = d.Cin, pitch_v = d.x_pitch, halo2 = 0;
+  // taps as (view-row shift, view channel offset, weight K offset, m range)
+  struct T { int shift, ch0, kofs, m_lo, m_hi; } taps[8];
+  int ntap = 0;
+  if (d.kind == TC_KIND_DOWN) {         // Conv1d(k4, s2, p1) on the row-pair view: even rows = channels [0,C), odd rows = [pitch, pitch+C)
+    LADIFF_REQUIRE(d.K == 4 && d.Lin % 2 == 0, LADIFF_ERR_ARG, "tc_conv: stride-2 conv needs k=4 and an even length (%d)", d.Lin);
+    Lout = d.Lin / 2; Lv = d.Lin / 2; pitch_v = 2 * d.x_pitch; Cv = d.x_pitch + d.Cin;
+    const int sh[4] = {-1, 0, 0, 1}, c0[4] = {d.x_pitch, 0, d.x_pitch, 0};
+    for (int s = 0; s < 4; ++s) taps[ntap++] = T{sh[s], c0[s], s * d.Cin, 0, d.CoutV};
+    halo2 = 2;
+  } else if (d.kind == TC_KIND_UP) {    // nearest x2 + Conv1d(k3, p1): even phase rows [0, Cout), odd phase [Cout, 2Cout)
+    LADIFF_REQUIRE(d.K == 3, LADIFF_ERR_ARG, "tc_conv: upsample conv needs k=3");
+    taps[ntap++] = T{-1, 0, 0, 0, d.CoutV / 2};
+    taps[ntap++] = T{0, 0, d.Cin, 0, d.CoutV};
+    taps[ntap++] = T{1, 0, 2 * d.Cin, d.CoutV / 2, d.CoutV};
+    halo2 = 2;
+    LADIFF_REQUIRE((d.CoutV / 2) % TC_BM == 0, LADIFF_ERR_ARG, "tc_conv: upsample conv needs Cout %% 128 == 0");
+  } else {
+    LADIFF_REQUIRE(d.K >= 1 && d.K <= TC_MAX_TAPS && (d.K & 1), LADIFF_ERR_ARG, "tc_conv: K=%d", d.K);
+    for (int s = 0; s < d.K; ++s) taps[ntap++] = T{s - (d.K - 1) / 2, 0, s * d.Cin, 0, d.CoutV};
+    halo2 = d.K - 1;
+  }
+  // groups: taps that read the same channel range share one shared-memory tile
+  p.ngrp = 0;
+  for (int i = 0; i < ntap; ++i) {
+    int g = -1;
+    if (d.tap_share)
+      for (int k = 0; k < p.ngrp; ++k) if (p.grp[k].ch0 == taps[i].ch0) g = k;
+    if (g < 0) {
+      g = p.ngrp++;
+      p.grp[g].ch0 = taps[i].ch0; p.grp[g].shift = taps[i].shift; p.grp[g].nchunk = nch; p.grp[g].ntaps = 0;
+    }
+    TcGroup& gr = p.grp[g];
+    TcTap& tp = gr.tap[gr.ntaps++];
+    tp.row_off = taps[i].shift - gr.shift;      // taps are listed by increasing shift, so row_off >= 0
+    tp.kofs = taps[i].kofs; tp.m_lo = taps[i].m_lo; tp.m_hi = taps[i].m_hi;
+    LADIFF_REQUIRE(tp.row_off >= 0 && tp.row_off <= 7, LADIFF_ERR_ARG, "tc_conv: tap row offset %d", tp.row_off);
+  }
+  const int tile_halo = d.tap_share ? halo2 : 0;   // extra rows a shared tile needs
+  p.MT = d.CoutV / TC_BM;
+  p.B = d.B; p.Lout = Lout; p.Cout = d.CoutV; p.bias = d.bias; p.stats = d.stats;
+  p.up_cout = d.kind == TC_KIND_UP ? d.CoutV / 2 : 0;
+  pick_tiling(Lout, d.B, p.MT, tile_halo, &p.NT, &p.NCLIP, &p.n_ptiles);
+  p.NMMA = p.NT * p.NCLIP;
+  p.n_ntiles = p.NCLIP == 1 ? d.B * p.n_ptiles : cdiv(d.B, p.NCLIP);
+  p.BOXROWS = p.NCLIP == 1 ? p.NT + (tile_halo ? 8 : 0) : p.NT;
+  LADIFF_REQUIRE(p.NMMA % 16 == 0 && p.NMMA >= 16 && p.NMMA <= 256 && p.BOXROWS <= 256, LADIFF_ERR_ARG, "tc_conv: tile N=%d box=%d", p.NMMA,
+                 p.BOXROWS);
+  LADIFF_REQUIRE(p.NCLIP == 1 || Lout + tile_halo <= p.NT, LADIFF_ERR_ARG, "tc_conv: clip region too small");
+  p.direct = (d.out32 != nullptr || d.res != nullptr) ? 1 : 0;
+  p.CR = p.NCLIP == 1 ? (p.NT < 64 ? p.NT : 64) : p.NT;
+  p.b_slot_bytes = (int)align_up((size_t)p.NCLIP * p.BOXROWS * 128, 1024);
+  // shared-memory budget: [weights ring][activation ring][2 staging chunks] + 1 KB alignment + 1 KB tap over-read
+  const size_t stage_bytes = p.direct ? 0 : (size_t)2 * p.CR * 256;
+  int max_taps = 1;
+  for (int g = 0; g < p.ngrp; ++g) max_taps = p.grp[g].ntaps > max_taps ? p.grp[g].ntaps : max_taps;
+  p.sb = 3;
+  for (;;) {
+    const long rest = (long)kSmemLimit - 2048 - (long)stage_bytes - (long)p.sb * p.b_slot_bytes;
+    p.sa = (int)(rest / A_BYTES);
+    if (p.sa > kMaxSA) p.sa = kMaxSA;
+    if (p.sa >= max_taps + 1 || p.sb == 2) break;
+    p.sb = 2;
+  }
+  LADIFF_REQUIRE(p.sa >= 2, LADIFF_ERR_ARG, "tc_conv: no shared memory left for the weight ring (N=%d)", p.NMMA);
+  p.tmW = *d.tmW;
+  int rc = make_tmap_x(&p.tmX, d.x, d.B, Lv, Cv, pitch_v, d.x_bstride, p.BOXROWS);
+  if (rc) return rc;
+  if (p.direct) {
+    if (d.out32) { p.out = d.out32; p.out_f32 = 1; p.out_pitch = d.CoutV; p.out_bstride = (long long)Lout * d.CoutV; }
+    else { p.out = d.out; p.out_f32 = 0; p.out_pitch = d.out_pitch; p.out_bstride = d.out_bstride; }
+    p.res = d.res; p.res_bstride = d.res_bstride; p.res_pitch = d.res_pitch;
+    LADIFF_REQUIRE(d.kind != TC_KIND_UP, LADIFF_ERR_ARG, "tc_conv: the upsample conv has no direct epilogue");
+  } else {
+    const int phases = p.up_cout ? 2 : 1, Cc = p.up_cout ? p.up_cout : d.CoutV;
+    LADIFF_REQUIRE(((uintptr_t)d.out % 16) == 0 && d.out_pitch % 8 == 0 && d.out_bstride % 8 == 0, LADIFF_ERR_ARG,
+                   "tc_conv: output view is not 16-byte aligned");
+    rc = make_tmap_y(&p.tmY, d.out, Cc, phases, Lout, d.B, d.out_pitch, d.out_bstride, p.CR);
+    if (rc) return rc;
+    const int rem = p.NT % p.CR;
+    rc = make_tmap_y(&p.tmYr, d.out, Cc, phases, Lout, d.B, d.out_pitch, d.out_bstride, rem ? rem : p.CR);
+    if (rc) return rc;
+  }
+  if (rv) {
+    rv->x = d.x; rv->bstride = d.x_bstride; rv->pitch = pitch_v; rv->Lv = Lv; rv->Cv = Cv; rv->w = d.w; rv->Ktot = d.Ktot;
+    rv->out = d.out; rv->out_bstride = d.out_bstride; rv->out_pitch = d.out_pitch;
+  }
   return 0;
 }
 
-int tc_conv_launch(const TcConvParams& p, int B, cudaStream_t st) {
-  LADIFF_REQUIRE(p.Cout % TC_BM == 0 && p.NT % 16 == 0 && p.NT >= 16 && p.NT <= 256 && p.nseg >= 1 && p.nseg <= TC_MAX_SEG,
-                 LADIFF_ERR_ARG, "tc_conv: bad tile config Cout=%d NT=%d nseg=%d", p.Cout, p.NT, p.nseg);
-  LADIFF_REQUIRE(p.stages >= 2 && p.stages <= 8, LADIFF_ERR_ARG, "tc_conv: stages=%d", p.stages);
-  const size_t smem = tc_smem_bytes(p.NT, p.stages);
-  LADIFF_REQUIRE(smem <= 226 * 1024, LADIFF_ERR_ARG, "tc_conv: smem %zu too large", smem);
-  static size_t attr_set = 0;     // opt-in dynamic shared memory (static barriers take a few hundred bytes of the 227 KB)
-  if (smem > attr_set) {
-    LADIFF_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = smem;
+static size_t tc_smem_bytes(const TcConvParams& p) {
+  return (size_t)p.sa * A_BYTES + (size_t)p.sb * p.b_slot_bytes + (p.direct ? 0 : (size_t)2 * p.CR * 256) + 2048;
+}
+
+int tc_conv_launch(const TcConvParams& p, cudaStream_t st) {
+  const size_t smem = tc_smem_bytes(p);
+  LADIFF_REQUIRE(smem <= kSmemLimit, LADIFF_ERR_ARG, "tc_conv: smem %zu too large", smem);
+  static bool attr_set = false;     // opt in to the full dynamic shared memory once
+  if (!attr_set) {
+    LADIFF_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    attr_set = true;
   }
-  dim3 grid(cdiv(p.Lout, p.NT), p.Cout / TC_BM, B);
-  tc_conv_kernel<<<grid, 128, smem, st>>>(p);
+  const int tiles = p.MT * p.n_ntiles, nsm = tc_num_sms();
+  tc_conv_kernel<<<tiles < nsm ? tiles : nsm, kThreads, smem, st>>>(p);
   LADIFF_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-int tc_conv_ref_launch(const TcConvParams& p, const TcRefView& v, int B, cudaStream_t st) {
-  dim3 grid(cdiv(p.Lout, p.NT), p.Cout / 32, B);
+int tc_conv_ref_launch(const TcConvParams& p, const TcRefView& v, cudaStream_t st) {
+  dim3 grid(p.NCLIP == 1 ? p.n_ptiles : 1, p.Cout / 32, p.B);
   tc_conv_ref_kernel<<<grid, 128, 0, st>>>(p, v);
   LADIFF_CUDA_OK(cudaGetLastError());
   return 0;

@@ -29,8 +29,10 @@ def stage_conv_op(res):
     lib = _lib.get_lib()
     shapes = [  # (B, L, Cin, Cout, k)
         (2, 75, 128, 128, 1), (2, 80, 256, 256, 3), (1, 300, 1024, 1024, 3), (3, 1200, 256, 384, 1),
-        (2, 640, 256, 256, 7), (2, 37, 2048, 1024, 3), (1, 4800, 512, 256, 3), (2, 16, 64, 128, 3),
+        (2, 640, 256, 256, 7), (5, 37, 2048, 1024, 3), (1, 4800, 512, 256, 3), (2, 16, 64, 128, 3),
+        (7, 75, 1024, 1024, 3), (32, 75, 256, 128, 3), (3, 150, 512, 512, 3), (2, 1200, 256, 256, 3),
     ]
+    P = ctypes.c_void_p
     for (B, L, Cin, Cout, k) in shapes:
         g = torch.Generator().manual_seed(L * 7 + Cin)
         x = torch.randn(B, L, Cin, generator=g).to(torch.bfloat16)
@@ -39,20 +41,23 @@ def stage_conv_op(res):
         ref = F.conv1d(x.float().permute(0, 2, 1), w.to(torch.bfloat16).float(), bias, padding=(k - 1) // 2).permute(0, 2, 1)
         xd, wd, bd = x.cuda(), w.cuda(), bias.cuda()
         out = {}
-        for impl in (1, 0):
-            y = torch.full((B, L, Cout), float("nan"), device="cuda", dtype=torch.float32)
-            st = torch.zeros(B, Cout // 32, 2, device="cuda")
-            rc = lib.ladiff_op_conv1d_cl(ctypes.c_void_p(xd.data_ptr()), ctypes.c_void_p(wd.data_ptr()), ctypes.c_void_p(bd.data_ptr()),
-                                         B, L, Cin, Cout, k, ctypes.c_void_p(y.data_ptr()), 1, impl, ctypes.c_void_p(st.data_ptr()))
-            if rc != 0:
-                out[impl] = "rc=%d %s" % (rc, lib.ladiff_last_error().decode())
-                continue
-            err = (y.cpu() - ref).abs().max().item()
-            s_ref = ref.reshape(B, L, Cout // 32, 32).sum(dim=(1, 3))
-            out[impl] = dict(max_abs_err=err, nan=int(torch.isnan(y).sum().item()),
-                             stats_err=(st[:, :, 0].cpu() - s_ref).abs().max().item())
-        res[f"B{B}_L{L}_Cin{Cin}_Cout{Cout}_k{k}"] = dict(simt=out.get(1), tc=out.get(0), ref_absmax=ref.abs().max().item())
-        print(f"conv B{B} L{L} Cin{Cin} Cout{Cout} k{k}: simt={out.get(1)} tc={out.get(0)}", flush=True)
+        for impl in (1, 2, 0):          # SIMT check, tcgen05 per-tap tiles, tcgen05 tap-shared tiles
+            for f32 in (1, 0):
+                y = torch.full((B, L, Cout), float("nan"), device="cuda", dtype=torch.float32 if f32 else torch.bfloat16)
+                st = torch.zeros(B, Cout // 32, 2, device="cuda")
+                rc = lib.ladiff_op_conv1d_cl(P(xd.data_ptr()), P(wd.data_ptr()), P(bd.data_ptr()), B, L, Cin, Cout, k, P(y.data_ptr()),
+                                             f32, impl, P(st.data_ptr()))
+                key = f"impl{impl}_{'f32' if f32 else 'bf16'}"
+                if rc != 0:
+                    out[key] = "rc=%d %s" % (rc, lib.ladiff_last_error().decode())
+                    torch.cuda.synchronize()
+                    continue
+                err = (y.float().cpu() - ref).abs().max().item()
+                s_ref = ref.reshape(B, L, Cout // 32, 32).sum(dim=(1, 3))
+                out[key] = dict(max_abs_err=round(err, 6), nan=int(torch.isnan(y).sum().item()),
+                                stats_err=round((st[:, :, 0].cpu() - s_ref).abs().max().item(), 5))
+        res[f"B{B}_L{L}_Cin{Cin}_Cout{Cout}_k{k}"] = dict(out=out, ref_absmax=ref.abs().max().item())
+        print(f"conv B{B} L{L} Cin{Cin} Cout{Cout} k{k}: " + " ".join(f"{k2}={v}" for k2, v in out.items()), flush=True)
 
 
 def _setup(name="A_3kbps"):

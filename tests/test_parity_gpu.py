@@ -92,8 +92,11 @@ def test_unet_forward_tcgen05(case):
     # the tcgen05 kernel and the SIMT check kernel consume identical packed operands
     m.set_conv_impl(1)
     eps_s = m.diff_model(img.cuda(), tp.cuda(), fx["cond"].cuda()).cpu()
+    m.set_conv_impl(2)          # tcgen05 with one activation tile per tap (no row-shifted descriptors)
+    eps_u = m.diff_model(img.cuda(), tp.cuda(), fx["cond"].cuda()).cpu()
     m.set_conv_impl(0)
     assert pc.rel_l2(eps, eps_s) <= pc.TOL["unet_simt_vs_tc_rel_l2"]
+    assert pc.rel_l2(eps, eps_u) <= pc.TOL["unet_simt_vs_tc_rel_l2"]
     # per-sample time indices: a batch with mixed t equals the per-t evaluations
     if fx["B"] > 1:
         tmix = tp.clone(); tmix[0] = 3
@@ -197,25 +200,30 @@ def test_strict_loader_errors():
 
 
 def test_tc_conv_operator_shapes():
-    """tcgen05 conv operator vs torch on bf16-rounded operands: ragged L (not a tile multiple), k in {1,3,7},
-    Cin up to 2048, minimum size."""
+    """tcgen05 conv operator vs torch on bf16-rounded operands: ragged L (not a tile multiple), k in {1,3,7}, Cin up to 2048,
+    minimum size, several short clips packed per tile; fp32 (direct epilogue) and bf16 (smem-staged TMA-store epilogue)
+    outputs; tap-shared (impl 0) and per-tap (impl 2) activation tiles."""
     import torch.nn.functional as F
     from ladiffcodec_b200 import _lib
     lib = _lib.get_lib()
-    for (B, L, Cin, Cout, k) in [(2, 75, 128, 128, 1), (1, 300, 1024, 1024, 3), (2, 640, 256, 256, 7), (2, 37, 2048, 1024, 3),
-                                 (1, 4800, 512, 256, 3), (2, 16, 64, 128, 3), (1, 1201, 256, 384, 1)]:
+    P = ctypes.c_void_p
+    for (B, L, Cin, Cout, k) in [(2, 75, 128, 128, 1), (1, 300, 1024, 1024, 3), (2, 640, 256, 256, 7), (5, 37, 2048, 1024, 3),
+                                 (1, 4800, 512, 256, 3), (2, 16, 64, 128, 3), (1, 1201, 256, 384, 1), (7, 75, 1024, 1024, 3),
+                                 (3, 150, 512, 512, 3)]:
         g = torch.Generator().manual_seed(L + Cin)
         x = torch.randn(B, L, Cin, generator=g).to(torch.bfloat16)
         w = torch.randn(Cout, Cin, k, generator=g) * (Cin * k) ** -0.5
         bias = torch.randn(Cout, generator=g) * 0.1
         ref = F.conv1d(x.float().permute(0, 2, 1), w.to(torch.bfloat16).float(), bias, padding=(k - 1) // 2).permute(0, 2, 1)
-        xd, wd, bd = x.cuda(), w.cuda(), bias.cuda()
-        y = torch.full((B, L, Cout), float("nan"), device="cuda")
-        st = torch.zeros(B, Cout // 32, 2, device="cuda")
-        P = ctypes.c_void_p
-        rc = lib.ladiff_op_conv1d_cl(P(xd.data_ptr()), P(wd.data_ptr()), P(bd.data_ptr()), B, L, Cin, Cout, k, P(y.data_ptr()), 1, 0,
-                                     P(st.data_ptr()))
-        assert rc == 0, lib.ladiff_last_error()
-        assert (y.cpu() - ref).abs().max().item() < 2e-4
         s_ref = ref.reshape(B, L, Cout // 32, 32).sum(dim=(1, 3))
-        assert (st[:, :, 0].cpu() - s_ref).abs().max().item() < 1e-2 * max(1.0, s_ref.abs().max().item())
+        xd, wd, bd = x.cuda(), w.cuda(), bias.cuda()
+        for impl in (0, 2):
+            for f32 in (1, 0):
+                y = torch.full((B, L, Cout), float("nan"), device="cuda", dtype=torch.float32 if f32 else torch.bfloat16)
+                st = torch.zeros(B, Cout // 32, 2, device="cuda")
+                rc = lib.ladiff_op_conv1d_cl(P(xd.data_ptr()), P(wd.data_ptr()), P(bd.data_ptr()), B, L, Cin, Cout, k, P(y.data_ptr()),
+                                             f32, impl, P(st.data_ptr()))
+                assert rc == 0, lib.ladiff_last_error()
+                tol = 2e-4 if f32 else 2e-4 + ref.abs().max().item() * 2 ** -8       # bf16 output rounding
+                assert (y.float().cpu() - ref).abs().max().item() < tol, (B, L, Cin, Cout, k, impl, f32)
+                assert (st[:, :, 0].cpu() - s_ref).abs().max().item() < 1e-2 * max(1.0, s_ref.abs().max().item())
