@@ -56,10 +56,11 @@ enum ConvKind { CK_PLAIN = TC_KIND_PLAIN, CK_DOWN = TC_KIND_DOWN, CK_UP = TC_KIN
 struct PackedConv {
   bf16* w = nullptr; const float* bias = nullptr;
   int CoutV = 0, Cin = 0, K = 1, Ktot = 0, kind = CK_PLAIN;
+  int split_m = 0;     // > 0: rows [split_m, CoutV) are a fused 1x1 res_conv of the same input (second output)
   CUtensorMap tmW;
 };
 struct ResnetW {
-  PackedConv c1, c2, res; bool has_res = false;
+  PackedConv c1, c2; bool has_res = false;
   const float *g1 = nullptr, *b1 = nullptr, *g2 = nullptr, *b2 = nullptr;
   long long film_off = 0; int Cin = 0, Cout = 0;
 };
@@ -87,7 +88,7 @@ struct Bump {
 
 struct UnetBufs {
   bf16 *xin, *FC, *CA[5], *CB[5], *X[6], *tY, *tH, *tO, *tR, *tA, *qkv, *ao;
-  float* eps; float* ctx; float2* stats; int* t_dev; float* inv_scale; float* condup; float* condtmp;
+  float* eps; float* ctx; float* la_part; int* la_cnt; float2* stats; int* t_dev; float* inv_scale; float* condup; float* condtmp;
   int stats_slots;
 };
 
@@ -404,14 +405,35 @@ int pack_unet_conv(H* h, const std::string& wname, const std::string& bname, int
   return 0;
 }
 
+// block1.proj (weight-standardised k3) with res_conv (1x1, when Cin != Cout) fused as extra output rows [cout, 2cout):
+// both read the same input tile, so the 1x1 shares block1's activation loads and costs no launch of its own
+int pack_block1_fused(H* h, const std::string& p, int cin, int cout, PackedConv* pc) {
+  const float* w1 = Wp(h, p + ".block1.proj.weight");
+  const float* wr = Wp(h, p + ".res_conv.weight");
+  LADIFF_REQUIRE(w1 && wr, LADIFF_ERR_KEY, "missing %s block1/res_conv weights", p.c_str());
+  LADIFF_REQUIRE(cin % 64 == 0 && cout % 128 == 0, LADIFF_ERR_UNSUPPORTED, "%s: Cin=%d Cout=%d", p.c_str(), cin, cout);
+  pc->Cin = cin; pc->K = 3; pc->kind = CK_PLAIN; pc->CoutV = 2 * cout; pc->Ktot = 3 * cin; pc->split_m = cout;
+  TRY(dalloc(h, &pc->w, (size_t)pc->CoutV * pc->Ktot));
+  LADIFF_CUDA_OK(cudaMemset(pc->w, 0, sizeof(bf16) * (size_t)pc->CoutV * pc->Ktot));
+  TRY(pack_conv_launch(w1, pc->w, cout, cin, 3, 1, 0));
+  TRY(pack_conv_launch(wr, pc->w + (size_t)cout * pc->Ktot, cout, cin, 1, 0, 0, pc->Ktot));
+  float* b2 = nullptr;
+  TRY(dalloc(h, &b2, (size_t)2 * cout));
+  LADIFF_CUDA_OK(cudaMemcpy(b2, Wp(h, p + ".block1.proj.bias"), sizeof(float) * cout, cudaMemcpyDeviceToDevice));
+  LADIFF_CUDA_OK(cudaMemcpy(b2 + cout, Wp(h, p + ".res_conv.bias"), sizeof(float) * cout, cudaMemcpyDeviceToDevice));
+  pc->bias = b2;
+  TRY(tc_make_tmap_w(&pc->tmW, pc->w, pc->CoutV, pc->Ktot));
+  return 0;
+}
+
 int fold_resnet(H* h, const std::string& p, int cin, int cout, long long* film_cursor, ResnetW* r) {
   r->Cin = cin; r->Cout = cout;
-  TRY(pack_unet_conv(h, p + ".block1.proj.weight", p + ".block1.proj.bias", cout, cin, 3, CK_PLAIN, true, &r->c1));
+  r->has_res = cin != cout;
+  if (r->has_res) TRY(pack_block1_fused(h, p, cin, cout, &r->c1));
+  else TRY(pack_unet_conv(h, p + ".block1.proj.weight", p + ".block1.proj.bias", cout, cin, 3, CK_PLAIN, true, &r->c1));
   TRY(pack_unet_conv(h, p + ".block2.proj.weight", p + ".block2.proj.bias", cout, cout, 3, CK_PLAIN, true, &r->c2));
   r->g1 = Wp(h, p + ".block1.norm.weight"); r->b1 = Wp(h, p + ".block1.norm.bias");
   r->g2 = Wp(h, p + ".block2.norm.weight"); r->b2 = Wp(h, p + ".block2.norm.bias");
-  r->has_res = cin != cout;
-  if (r->has_res) TRY(pack_unet_conv(h, p + ".res_conv.weight", p + ".res_conv.bias", cout, cin, 1, CK_PLAIN, false, &r->res));
   r->film_off = *film_cursor;
   *film_cursor += 2 * cout;
   return 0;
@@ -665,6 +687,8 @@ void carve_unet(const H* h, Bump& bp, int B, int L, UnetBufs* u) {
   u->ao = bp.get<bf16>(BL * 128);
   u->eps = bp.get<float>(BL * 128);
   u->ctx = bp.get<float>((size_t)B * 4096);
+  u->la_part = bp.get<float>(linattn_part_floats(B, L));
+  u->la_cnt = bp.get<int>((size_t)4 * B);
   u->stats_slots = (L / 16 + 2) * 32;
   u->stats = bp.get<float2>((size_t)B * u->stats_slots);
   u->t_dev = bp.get<int>(B);
@@ -680,7 +704,8 @@ ClView view(bf16* p, int L, int pitch, int C, int ch0 = 0) {
 struct PlanBuilder {
   H* h; Plan* pl; int B;
   // conv: `in` has Lin rows; writes Lout rows into `out` (bf16) or out32 (fp32, contiguous [B][Lout][CoutV])
-  int conv(const PackedConv& pc, ClView in, int Lin, ClView out, float* out32, bool want_stats, int* n_ntiles, ClView res) {
+  int conv(const PackedConv& pc, ClView in, int Lin, ClView out, float* out32, bool want_stats, int* n_ntiles, ClView res,
+           ClView out2 = ClView{nullptr, 0, 0, 0}) {
     LADIFF_REQUIRE(in.C == pc.Cin, LADIFF_ERR_ARG, "plan: conv input has %d channels, weights expect %d", in.C, pc.Cin);
     TcConvDesc d;
     memset(&d, 0, sizeof(d));
@@ -689,6 +714,10 @@ struct PlanBuilder {
     d.out = out.p; d.out_bstride = out.bstride; d.out_pitch = out.pitch; d.out32 = out32;
     d.stats = want_stats ? pl->bufs.stats : nullptr;
     if (res.p) { d.res = res.p; d.res_bstride = res.bstride; d.res_pitch = res.pitch; }
+    if (pc.split_m) {
+      LADIFF_REQUIRE(out2.p != nullptr, LADIFF_ERR_ARG, "plan: fused res_conv needs a second output");
+      d.split_m = pc.split_m; d.out2 = out2.p; d.out2_bstride = out2.bstride; d.out2_pitch = out2.pitch;
+    }
     d.B = B;
     TcConvParams ps, pu;
     TcRefView rv;
@@ -698,7 +727,7 @@ struct PlanBuilder {
     TRY(tc_conv_plan(d, &pu, nullptr));
     LADIFF_REQUIRE(ps.n_ptiles == pu.n_ptiles || !want_stats, LADIFF_ERR_ARG, "plan: tap-shared and per-tap tilings disagree");
     if (want_stats)
-      LADIFF_REQUIRE(ps.n_ptiles * (pc.CoutV / 32) <= pl->bufs.stats_slots, LADIFF_ERR_WORKSPACE, "plan: stats buffer too small");
+      LADIFF_REQUIRE(ps.n_ptiles * ps.stat_slots <= pl->bufs.stats_slots, LADIFF_ERR_WORKSPACE, "plan: stats buffer too small");
     if (n_ntiles) *n_ntiles = ps.n_ptiles;
     H* hh = h;
     pl->ops.push_back([hh, ps, pu, rv](cudaStream_t st) {
@@ -706,12 +735,13 @@ struct PlanBuilder {
       return tc_conv_launch(hh->conv_impl == 2 ? pu : ps, st);
     });
     pl->op_flops.resize(pl->ops.size(), 0.0);
-    pl->op_flops.back() = 2.0 * pc.CoutV * (double)pc.Ktot * ps.Lout * B;
+    pl->op_flops.back() = pc.split_m ? 2.0 * ((double)pc.split_m * pc.Ktot + (double)(pc.CoutV - pc.split_m) * pc.Cin) * ps.Lout * B
+                                     : 2.0 * pc.CoutV * (double)pc.Ktot * ps.Lout * B;
     pl->op_label.resize(pl->ops.size());
     {
       char buf[200];
-      snprintf(buf, sizeof(buf), "conv kind=%d Cout=%d Cin=%d k=%d Lout=%d NT=%d nclip=%d tiles=%d sa=%d sb=%d stats=%d direct=%d", pc.kind,
-               pc.CoutV, pc.Cin, pc.K, ps.Lout, ps.NT, ps.NCLIP, ps.MT * ps.n_ntiles, ps.sa, ps.sb, want_stats ? 1 : 0, ps.direct);
+      snprintf(buf, sizeof(buf), "conv kind=%d Cout=%d Cin=%d k=%d Lout=%d NT=%d nclip=%d tiles=%d S=%d taps/stage=%d stats=%d direct=%d", pc.kind,
+               pc.CoutV, pc.Cin, pc.K, ps.Lout, ps.NT, ps.NCLIP, ps.MT * ps.n_ntiles, ps.S, ps.a_cap, want_stats ? 1 : 0, ps.direct);
       pl->op_label.back() = buf;
     }
     pl->launches_per_run++;
@@ -733,13 +763,14 @@ struct PlanBuilder {
     ClView none; memset(&none, 0, sizeof(none));
     ClView y = view(u.tY, L, r.Cout, r.Cout), hh = view(u.tH, L, r.Cout, r.Cout);
     int nt = 0;
-    TRY(conv(r.c1, x, L, y, nullptr, true, &nt, none));
-    TRY(gn(y, L, nt, r.g1, r.b1, h->un.film + r.film_off, none, hh, false));
     ClView resv = x;
-    if (r.has_res) {
+    if (r.has_res) {                  // res_conv(x) rides along as the second output of block1's conv
       resv = view(u.tR, L, r.Cout, r.Cout);
-      TRY(conv(r.res, x, L, resv, nullptr, false, nullptr, none));
+      TRY(conv(r.c1, x, L, y, nullptr, true, &nt, none, resv));
+    } else {
+      TRY(conv(r.c1, x, L, y, nullptr, true, &nt, none));
     }
+    TRY(gn(y, L, nt, r.g1, r.b1, h->un.film + r.film_off, none, hh, false));
     TRY(conv(r.c2, hh, L, y, nullptr, true, &nt, none));
     TRY(gn(y, L, nt, r.g2, r.b2, nullptr, resv, out, do_tanh));
     return 0;
@@ -757,9 +788,9 @@ struct PlanBuilder {
     ClView ln = view(u.tH, L, a.C, a.C), qkv = view(u.qkv, L, 384, 384), ao = view(u.ao, L, 128, 128);
     TRY(layernorm(x, a.norm_g, none, ln, L));
     TRY(conv(a.qkv, ln, L, qkv, nullptr, false, nullptr, none));
-    const int BB = B; float* ctx = u.ctx;
+    const int BB = B; float* ctx = u.ctx; float* lap = u.la_part; int* lac = u.la_cnt;
     if (linear) {
-      pl->ops.push_back([qkv, ctx, ao, BB, L](cudaStream_t st) { return linattn_launch(qkv, ctx, ao, BB, L, st); });
+      pl->ops.push_back([qkv, ctx, lap, lac, ao, BB, L](cudaStream_t st) { return linattn_launch(qkv, ctx, lap, lac, ao, BB, L, st); });
       pl->launches_per_run += 2;
       ClView yo = view(u.tY, L, a.C, a.C);
       TRY(conv(a.out, ao, L, yo, nullptr, false, nullptr, none));
@@ -874,6 +905,7 @@ int prepare_cond(H* h, Plan* pl, const float* cond, int B, int L, int F, cudaStr
   int Lup = F;
   for (auto& c : h->un.cond_up) Lup *= c.s;
   LADIFF_REQUIRE(Lup == L, LADIFF_ERR_ARG, "cond frames %d x upsampling = %d != latent length %d", F, Lup, L);
+  LADIFF_CUDA_OK(cudaMemsetAsync(u.la_cnt, 0, sizeof(int) * 4 * B, st));   // linear-attention tickets (the workspace is shared with the codec stages)
   TRY(run_cond_upsample(h, cond, B, F, u.condup, u.condtmp, (float*)u.eps, st));
   const float* inv = nullptr;
   if (h->cfg.unet_scale_cond) {

@@ -73,6 +73,10 @@ struct TcConvDesc {
   float* out32;             // if set: fp32 output, contiguous [B][Lout][CoutV] (direct epilogue)
   float2* stats;            // optional GroupNorm partials [B][n_ptiles][CoutV/32]
   const bf16* res; long long res_bstride; int res_pitch;      // optional residual (direct epilogue)
+  // optional second output (ResnetBlock: res_conv fused into block1's conv): output channels m >= split_m are a 1x1 conv of the
+  // same input (weights at K offset 0 of rows [split_m, CoutV)) written to out2; GroupNorm partials cover m < split_m only
+  int split_m;
+  bf16* out2; long long out2_bstride; int out2_pitch;
   int B;
   int tap_share;            // 1: all taps of a chunk read one shared activation tile; 0: one tile load per tap
 };
@@ -82,6 +86,8 @@ struct TcConvParams {
   CUtensorMap tmX;   // activations view [B][Lv][Cv] bf16, box {64, BOXROWS, 1}, SWIZZLE_128B, OOB -> 0
   CUtensorMap tmY;   // output {Cc, phases, rows, B} bf16, box {128, 1, CR, 1}
   CUtensorMap tmYr;  // same, box rows = NT % CR (last chunk of a single-clip tile)
+  CUtensorMap tmY2;  // second output (channels m >= split_m), box {128, 1, CR, 1}
+  CUtensorMap tmY2r;
   TcGroup grp[TC_MAX_GRP];
   int ngrp;
   int NT;            // output rows per clip region of a tile
@@ -92,10 +98,14 @@ struct TcConvParams {
   int n_ptiles;      // position tiles per clip (1 when NCLIP > 1)
   int n_ntiles;      // N tiles in total
   int MT;            // Cout/128
-  int sa, sb;        // weight / activation ring depths
+  int S;             // pipeline stages; a stage = a_cap weight tiles (16 KB each) + one activation tile
+  int a_cap;
+  int stage_bytes;
   int b_slot_bytes;
   int direct;        // 1: direct register->global epilogue (fp32 output and/or residual); 0: smem-staged TMA store
   int up_cout;       // TC_KIND_UP: real Cout (output phase = m0 / up_cout); else 0
+  int split_m;       // second-output split (0 = none)
+  int stat_slots;    // GroupNorm slots per tile row block: (split_m ? split_m : Cout) / 32
   int B, Lout, Cout;
   const float* bias; // [Cout] or null
   float2* stats;     // optional GroupNorm partials [B][n_ptiles][Cout/32] (sum, sumsq) of the fp32 result
@@ -107,6 +117,7 @@ struct TcConvParams {
   const bf16* res;
   long long res_bstride;
   int res_pitch;
+  unsigned long long* prof;   // debug (LADIFF_TC_PROF): per-CTA wait-cycle counters [grid][8]
 };
 
 // X view description used by the SIMT check kernel (same math, no tensor maps, no tensor cores)
@@ -114,6 +125,7 @@ struct TcRefView {
   const bf16* x; long long bstride; int pitch; int Lv; int Cv;
   const bf16* w; int Ktot;
   bf16* out; long long out_bstride; int out_pitch;   // bf16 output view incl. the UP phase interleave (host fills)
+  bf16* out2; long long out2_bstride; int out2_pitch;
 };
 
 int tc_conv_plan(const TcConvDesc& d, TcConvParams* p, TcRefView* rv);

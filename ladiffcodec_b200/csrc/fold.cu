@@ -15,7 +15,7 @@ __device__ float block_sum128(float v, float* red) {
 // w [Cout][Cin][K] fp32 -> packed [Cout][K*Cin] bf16 with k-index = tap*Cin + c.
 // standardize: per output channel (w - mean) * rsqrt(var_biased + 1e-5) over (Cin, K).     one block (128 thr) per o
 __global__ void __launch_bounds__(128) pack_conv_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cin, int K,
-                                                        int standardize) {
+                                                        int standardize, int out_ld) {
   __shared__ float red[4];
   const int o = blockIdx.x, n = Cin * K;
   const float* wr = w + (long long)o * n;
@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(128) pack_conv_kernel(const float* __restrict_
   }
   for (int i = threadIdx.x; i < n; i += 128) {
     const int c = i / K, tap = i - c * K;
-    out[(long long)o * n + tap * Cin + c] = __float2bfloat16((wr[i] - mean) * rstd);
+    out[(long long)o * out_ld + tap * Cin + c] = __float2bfloat16((wr[i] - mean) * rstd);
   }
 }
 
@@ -66,8 +66,8 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ x, bf16* __restrict
 
 }  // namespace
 
-int pack_conv_launch(const float* w, bf16* out, int Cout, int Cin, int K, int standardize, cudaStream_t st) {
-  pack_conv_kernel<<<Cout, 128, 0, st>>>(w, out, Cin, K, standardize);
+int pack_conv_launch(const float* w, bf16* out, int Cout, int Cin, int K, int standardize, cudaStream_t st, int out_ld) {
+  pack_conv_kernel<<<Cout, 128, 0, st>>>(w, out, Cin, K, standardize, out_ld > 0 ? out_ld : Cin * K);
   LADIFF_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -19,6 +19,10 @@
 // Two TMEM accumulator stages, so the epilogue of tile i overlaps the main loop of tile i+1.
 // Short clips (L < 128) are packed several per tile (one TMA box per clip, per-clip zero padding kept).
 #include <cudaTypedefs.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
 
 #include "common.cuh"
 
@@ -26,7 +30,8 @@ namespace {
 
 constexpr int kThreads = 192;
 constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;  // 16 KB
-constexpr int kMaxSA = 8, kMaxSB = 4;
+constexpr int kMaxStages = 6;
+constexpr int kStageTaps = 3;    // weight tiles per pipeline stage
 constexpr size_t kSmemLimit = 232448 - 1024;     // 227 KB minus the static barriers
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -57,6 +62,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (spins == 64) t0 = clock64();
     if (spins > 64 && (spins & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();
   }
+}
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, long long& acc, bool on) {
+  if (!on) { mbar_wait(bar, parity); return; }
+  const long long t = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t;
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
   asm volatile(
@@ -119,32 +130,31 @@ __device__ __forceinline__ TileCoord decode_tile(const TcConvParams& p, int t) {
 
 __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_constant__ TcConvParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_a[kMaxSA];
-  __shared__ __align__(8) uint64_t empty_a[kMaxSA];
-  __shared__ __align__(8) uint64_t full_b[kMaxSB];
-  __shared__ __align__(8) uint64_t empty_b[kMaxSB];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tmem_full[2];
   __shared__ __align__(8) uint64_t tmem_empty[2];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_ring = smem_base;
-  const uint32_t b_ring = a_ring + (uint32_t)p.sa * A_BYTES;
-  const uint32_t stage0 = b_ring + (uint32_t)p.sb * (uint32_t)p.b_slot_bytes;
+  const uint32_t b_off = (uint32_t)p.a_cap * A_BYTES;                 // stage = [a_cap weight tiles][activation tile]
+  const uint32_t stage0 = smem_base + (uint32_t)p.S * (uint32_t)p.stage_bytes;   // epilogue staging
   uint32_t acc_stride = 32;
   while ((int)acc_stride < p.NMMA) acc_stride <<= 1;
   const uint32_t tmem_cols = 2 * acc_stride;
   const int total_tiles = p.MT * p.n_ntiles;
+  const bool prof = p.prof != nullptr;
+  const long long t_begin = prof ? clock64() : 0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.sa; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
-    for (int s = 0; s < p.sb; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+    for (int s = 0; s < p.S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmW) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmX) : "memory");
     if (!p.direct) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmY) : "memory");
+    if (p.split_m) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmY2) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(tmem_cols) : "memory");
@@ -157,33 +167,34 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
-      // ---------------- TMA producer
+      // ---------------- TMA producer: one pipeline stage per (group, 64-channel chunk) = activation tile + its taps' weight tiles
       const uint32_t b_bytes = (uint32_t)(p.NCLIP * p.BOXROWS) * 128u;
-      int ia = 0, ib = 0;
+      int st = 0; uint32_t ph = 0;
+      long long w_empty = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const TileCoord tc = decode_tile(p, t);
         for (int g = 0; g < p.ngrp; ++g) {
           const TcGroup& gr = p.grp[g];
+          uint32_t n_a = 0;
+          for (int tp = 0; tp < gr.ntaps; ++tp) n_a += (tc.m0 >= gr.tap[tp].m_lo && tc.m0 < gr.tap[tp].m_hi) ? 1u : 0u;
           for (int c = 0; c < gr.nchunk; ++c) {
-            const int sbi = ib % p.sb;
-            mbar_wait(&empty_b[sbi], ((ib / p.sb) & 1) ^ 1);
-            mbar_expect_tx(&full_b[sbi], b_bytes);
-            const uint32_t b_dst = b_ring + (uint32_t)sbi * (uint32_t)p.b_slot_bytes;
+            mbar_wait_t(&empty_bar[st], ph ^ 1, w_empty, prof);
+            mbar_expect_tx(&full_bar[st], b_bytes + n_a * A_BYTES);
+            const uint32_t a_dst = smem_base + (uint32_t)st * (uint32_t)p.stage_bytes;
             for (int j = 0; j < p.NCLIP; ++j)
-              tma_load_3d(b_dst + (uint32_t)(j * p.BOXROWS) * 128u, &p.tmX, &full_b[sbi], gr.ch0 + c * TC_BK, tc.l0 + gr.shift, tc.b0 + j);
-            ++ib;
+              tma_load_3d(a_dst + b_off + (uint32_t)(j * p.BOXROWS) * 128u, &p.tmX, &full_bar[st], gr.ch0 + c * TC_BK, tc.l0 + gr.shift, tc.b0 + j);
+            uint32_t idx = 0;
             for (int tp = 0; tp < gr.ntaps; ++tp) {
               const TcTap& tap = gr.tap[tp];
               if (tc.m0 < tap.m_lo || tc.m0 >= tap.m_hi) continue;
-              const int sai = ia % p.sa;
-              mbar_wait(&empty_a[sai], ((ia / p.sa) & 1) ^ 1);
-              mbar_expect_tx(&full_a[sai], A_BYTES);
-              tma_load_2d(a_ring + (uint32_t)sai * A_BYTES, &p.tmW, &full_a[sai], tap.kofs + c * TC_BK, tc.m0);
-              ++ia;
+              tma_load_2d(a_dst + idx * A_BYTES, &p.tmW, &full_bar[st], tap.kofs + c * TC_BK, tc.m0);
+              ++idx;
             }
+            if (++st == p.S) { st = 0; ph ^= 1; }
           }
         }
       }
+      if (prof) p.prof[blockIdx.x * 8 + 0] = (unsigned long long)w_empty;
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -191,56 +202,57 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
       // ---------------- MMA issuer.  Instruction descriptor (InstrDescriptor, mma_sm100_desc.hpp):
       // c_format F32 (1<<4) | a_format BF16 (1<<7) | b_format BF16 (1<<10) | K-major A,B | N>>3 <<17 | M>>4 <<24
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NMMA >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      int ia = 0, ib = 0, tl = 0;
+      int st = 0, tl = 0; uint32_t ph = 0;
+      long long w_full = 0, w_tmem = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
         const TileCoord tc = decode_tile(p, t);
         const int acc = tl & 1;
-        mbar_wait(&tmem_empty[acc], ((tl >> 1) & 1) ^ 1);     // the epilogue has drained this accumulator stage
+        mbar_wait_t(&tmem_empty[acc], ((tl >> 1) & 1) ^ 1, w_tmem, prof);     // the epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_stride;
         uint32_t accumulate = 0;
         for (int g = 0; g < p.ngrp; ++g) {
           const TcGroup& gr = p.grp[g];
           for (int c = 0; c < gr.nchunk; ++c) {
-            const int sbi = ib % p.sb;
-            mbar_wait(&full_b[sbi], (ib / p.sb) & 1);
-            const uint32_t b_addr = b_ring + (uint32_t)sbi * (uint32_t)p.b_slot_bytes;
+            mbar_wait_t(&full_bar[st], ph, w_full, prof);
+            tc_fence_after();
+            const uint32_t a_base = smem_base + (uint32_t)st * (uint32_t)p.stage_bytes;
+            uint64_t adesc = umma_desc(a_base);
+            const uint64_t bdesc0 = umma_desc(a_base + b_off);
             for (int tp = 0; tp < gr.ntaps; ++tp) {
               const TcTap& tap = gr.tap[tp];
               if (tc.m0 < tap.m_lo || tc.m0 >= tap.m_hi) continue;
-              const int sai = ia % p.sa;
-              mbar_wait(&full_a[sai], (ia / p.sa) & 1);
-              tc_fence_after();
-              const uint32_t a_addr = a_ring + (uint32_t)sai * A_BYTES;
-              const uint32_t bt_addr = b_addr + (uint32_t)tap.row_off * 128u;
+              const uint64_t bdesc = bdesc0 + (uint64_t)(tap.row_off * 8);    // +128 B per row, in 16-byte units
 #pragma unroll
               for (int k = 0; k < TC_BK / 16; ++k) {
-                umma_bf16(d_tmem, umma_desc(a_addr + k * 32), umma_desc(bt_addr + k * 32), idesc, accumulate);
+                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);   // +32 B per K=16 step
                 accumulate = 1;
               }
-              tc_commit(&empty_a[sai]);    // frees the weight slot once these MMAs have read it
-              ++ia;
+              adesc += A_BYTES >> 4;
             }
-            tc_commit(&empty_b[sbi]);      // frees the activation slot after its last tap
-            ++ib;
+            tc_commit(&empty_bar[st]);     // frees the stage once these MMAs have read it
+            if (++st == p.S) { st = 0; ph ^= 1; }
           }
         }
         tc_commit(&tmem_full[acc]);        // accumulator complete
       }
+      if (prof) { p.prof[blockIdx.x * 8 + 1] = (unsigned long long)w_full; p.prof[blockIdx.x * 8 + 2] = (unsigned long long)w_tmem; }
     }
     __syncwarp();
   } else {
     // ---------------- epilogue warps (warp w owns TMEM lanes 32*(w&3) .. +31)
     const int q = warp & 3;
     const bool issuer = threadIdx.x == 64;
-    const int Cc = p.up_cout ? p.up_cout : p.Cout;
+    const int Cc = p.up_cout ? p.up_cout : (p.split_m ? p.split_m : p.Cout);
     int tl = 0, cc = 0;
+    long long w_acc = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
       const TileCoord tc = decode_tile(p, t);
       const int acc = tl & 1;
       const int ch = tc.m0 + q * 32 + lane;
       const float bias = p.bias ? p.bias[ch] : 0.f;
-      mbar_wait(&tmem_full[acc], (tl >> 1) & 1);
+      const bool second = p.split_m && tc.m0 >= p.split_m;
+      mbar_wait_t(&tmem_full[acc], (tl >> 1) & 1, w_acc, prof);
       tc_fence_after();
       const uint32_t tlane = tmem_base + (uint32_t)acc * acc_stride + ((uint32_t)(q * 32) << 16);
       for (int j = 0; j < p.NCLIP; ++j) {
@@ -290,20 +302,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
             epi_bar();
             if (issuer) {
               const uint32_t src = stage0 + (uint32_t)(cc & 1) * (uint32_t)p.CR * 256u;
-              tma_store_4d(nrows == p.CR ? &p.tmY : &p.tmYr, src, tc.m0 % Cc, tc.m0 / Cc, tc.l0 + r0, b);
+              if (second) tma_store_4d(nrows == p.CR ? &p.tmY2 : &p.tmY2r, src, tc.m0 - p.split_m, 0, tc.l0 + r0, b);
+              else tma_store_4d(nrows == p.CR ? &p.tmY : &p.tmYr, src, tc.m0 % Cc, tc.m0 / Cc, tc.l0 + r0, b);
               bulk_commit();
             }
             ++cc;
           }
         }
-        if (p.stats && vr > 0) {
+        if (p.stats && vr > 0 && !second) {
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) {
             s1 += __shfl_xor_sync(0xffffffffu, s1, o);
             s2 += __shfl_xor_sync(0xffffffffu, s2, o);
           }
           if (lane == 0)
-            p.stats[((long long)b * p.n_ptiles + tc.pt) * (p.Cout / 32) + (tc.m0 / 32 + q)] = make_float2(s1, s2);
+            p.stats[((long long)b * p.n_ptiles + tc.pt) * p.stat_slots + (tc.m0 / 32 + q)] = make_float2(s1, s2);
         }
       }
       tc_fence_before();
@@ -311,6 +324,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);   // 4 warps -> accumulator stage free for the MMA issuer
     }
     if (issuer) bulk_wait_all();
+    if (prof && issuer) { p.prof[blockIdx.x * 8 + 3] = (unsigned long long)w_acc; p.prof[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - t_begin); }
   }
   tc_fence_before();
   __syncthreads();
@@ -326,7 +340,7 @@ __global__ void __launch_bounds__(128) tc_conv_ref_kernel(TcConvParams p, TcRefV
   const int pt = blockIdx.x, ch = blockIdx.y * 32 + lane, b = blockIdx.z;
   const int m0 = (ch / TC_BM) * TC_BM;
   const int l0 = pt * p.NT;
-  const int Cc = p.up_cout ? p.up_cout : p.Cout;
+  const int Cc = p.up_cout ? p.up_cout : (p.split_m ? p.split_m : p.Cout);
   const float bias = p.bias ? p.bias[ch] : 0.f;
   float s1 = 0.f, s2 = 0.f;
   for (int r = warp; r < p.NT; r += 4) {
@@ -351,12 +365,14 @@ __global__ void __launch_bounds__(128) tc_conv_ref_kernel(TcConvParams p, TcRefV
       const long long o = (long long)b * p.out_bstride + (long long)l * p.out_pitch + ch;
       if (p.out_f32) reinterpret_cast<float*>(p.out)[o] = val;
       else reinterpret_cast<bf16*>(p.out)[o] = __float2bfloat16(val);
+    } else if (p.split_m && ch >= p.split_m) {
+      v.out2[(long long)b * v.out2_bstride + (long long)l * v.out2_pitch + (ch - p.split_m)] = __float2bfloat16(val);
     } else {
       const int phase = ch / Cc, cc = ch % Cc, nph = p.up_cout ? 2 : 1;
       v.out[(long long)b * v.out_bstride + (long long)(l * nph + phase) * v.out_pitch + cc] = __float2bfloat16(val);
     }
   }
-  if (p.stats) {
+  if (p.stats && !(p.split_m && ch >= p.split_m)) {
     __shared__ float red[2][4][32];
     red[0][warp][lane] = s1; red[1][warp][lane] = s2;
     __syncthreads();
@@ -368,7 +384,7 @@ __global__ void __launch_bounds__(128) tc_conv_ref_kernel(TcConvParams p, TcRefV
         a += __shfl_xor_sync(0xffffffffu, a, o);
         c += __shfl_xor_sync(0xffffffffu, c, o);
       }
-      if (lane == 0) p.stats[((long long)b * p.n_ptiles + pt) * (p.Cout / 32) + blockIdx.y] = make_float2(a, c);
+      if (lane == 0) p.stats[((long long)b * p.n_ptiles + pt) * p.stat_slots + blockIdx.y] = make_float2(a, c);
     }
   }
 }
@@ -486,16 +502,35 @@ int tc_conv_plan(const TcConvDesc& d, TcConvParams* pp, TcRefView* rv) {
     LADIFF_REQUIRE((d.CoutV / 2) % TC_BM == 0, LADIFF_ERR_ARG, "tc_conv: upsample conv needs Cout %% 128 == 0");
   } else {
     LADIFF_REQUIRE(d.K >= 1 && d.K <= TC_MAX_TAPS && (d.K & 1), LADIFF_ERR_ARG, "tc_conv: K=%d", d.K);
-    for (int s = 0; s < d.K; ++s) taps[ntap++] = T{s - (d.K - 1) / 2, 0, s * d.Cin, 0, d.CoutV};
+    const int m_hi = d.split_m ? d.split_m : d.CoutV;
+    for (int s = 0; s < d.K; ++s) taps[ntap++] = T{s - (d.K - 1) / 2, 0, s * d.Cin, 0, m_hi};
     halo2 = d.K - 1;
   }
-  // groups: taps that read the same channel range share one shared-memory tile
+  if (d.split_m) {                      // fused 1x1 conv of the same input on rows [split_m, CoutV)
+    LADIFF_REQUIRE(d.kind == TC_KIND_PLAIN && d.split_m % TC_BM == 0 && d.split_m < d.CoutV && d.out2 && !d.out32 && !d.res && ntap < 8,
+                   LADIFF_ERR_ARG, "tc_conv: bad second-output configuration");
+    int at = ntap;                      // keep taps ordered by shift: insert after the last tap with shift <= 0
+    for (int i = 0; i < ntap; ++i) if (taps[i].shift > 0) { at = i; break; }
+    for (int i = ntap; i > at; --i) taps[i] = taps[i - 1];
+    taps[at] = T{0, 0, 0, d.split_m, d.CoutV};
+    ++ntap;
+  }
+  // groups: taps that read the same channel range share one shared-memory tile; a group is one pipeline stage per chunk, so it
+  // holds at most kStageTaps weight tiles for any output-channel tile (k=7 becomes 3+3+1)
   p.ngrp = 0;
+  int a_cap = 1, tile_halo = 0;
   for (int i = 0; i < ntap; ++i) {
     int g = -1;
     if (d.tap_share)
-      for (int k = 0; k < p.ngrp; ++k) if (p.grp[k].ch0 == taps[i].ch0) g = k;
+      for (int k = 0; k < p.ngrp; ++k) {
+        if (p.grp[k].ch0 != taps[i].ch0) continue;
+        int overlap = 0;
+        for (int t2 = 0; t2 < p.grp[k].ntaps; ++t2)
+          overlap += (p.grp[k].tap[t2].m_lo < taps[i].m_hi && taps[i].m_lo < p.grp[k].tap[t2].m_hi) ? 1 : 0;
+        if (overlap < kStageTaps && p.grp[k].ntaps < TC_MAX_TAPS) g = k;
+      }
     if (g < 0) {
+      LADIFF_REQUIRE(p.ngrp < TC_MAX_GRP, LADIFF_ERR_ARG, "tc_conv: too many tap groups");
       g = p.ngrp++;
       p.grp[g].ch0 = taps[i].ch0; p.grp[g].shift = taps[i].shift; p.grp[g].nchunk = nch; p.grp[g].ntaps = 0;
     }
@@ -504,11 +539,21 @@ int tc_conv_plan(const TcConvDesc& d, TcConvParams* pp, TcRefView* rv) {
     tp.row_off = taps[i].shift - gr.shift;      // taps are listed by increasing shift, so row_off >= 0
     tp.kofs = taps[i].kofs; tp.m_lo = taps[i].m_lo; tp.m_hi = taps[i].m_hi;
     LADIFF_REQUIRE(tp.row_off >= 0 && tp.row_off <= 7, LADIFF_ERR_ARG, "tc_conv: tap row offset %d", tp.row_off);
+    tile_halo = tp.row_off > tile_halo ? tp.row_off : tile_halo;
   }
-  const int tile_halo = d.tap_share ? halo2 : 0;   // extra rows a shared tile needs
+  for (int g = 0; g < p.ngrp; ++g)               // weight tiles a stage must hold = most taps any one m-tile uses
+    for (int m0 = 0; m0 < d.CoutV; m0 += TC_BM) {
+      int n = 0;
+      for (int t2 = 0; t2 < p.grp[g].ntaps; ++t2) n += (m0 >= p.grp[g].tap[t2].m_lo && m0 < p.grp[g].tap[t2].m_hi) ? 1 : 0;
+      a_cap = n > a_cap ? n : a_cap;
+    }
+  p.a_cap = a_cap;
+  (void)halo2;
   p.MT = d.CoutV / TC_BM;
   p.B = d.B; p.Lout = Lout; p.Cout = d.CoutV; p.bias = d.bias; p.stats = d.stats;
   p.up_cout = d.kind == TC_KIND_UP ? d.CoutV / 2 : 0;
+  p.split_m = d.split_m;
+  p.stat_slots = (d.split_m ? d.split_m : d.CoutV) / 32;
   pick_tiling(Lout, d.B, p.MT, tile_halo, &p.NT, &p.NCLIP, &p.n_ptiles);
   p.NMMA = p.NT * p.NCLIP;
   p.n_ntiles = p.NCLIP == 1 ? d.B * p.n_ptiles : cdiv(d.B, p.NCLIP);
@@ -517,21 +562,23 @@ int tc_conv_plan(const TcConvDesc& d, TcConvParams* pp, TcRefView* rv) {
                  p.BOXROWS);
   LADIFF_REQUIRE(p.NCLIP == 1 || Lout + tile_halo <= p.NT, LADIFF_ERR_ARG, "tc_conv: clip region too small");
   p.direct = (d.out32 != nullptr || d.res != nullptr) ? 1 : 0;
-  p.CR = p.NCLIP == 1 ? (p.NT < 64 ? p.NT : 64) : p.NT;
   p.b_slot_bytes = (int)align_up((size_t)p.NCLIP * p.BOXROWS * 128, 1024);
-  // shared-memory budget: [weights ring][activation ring][2 staging chunks] + 1 KB alignment + 1 KB tap over-read
-  const size_t stage_bytes = p.direct ? 0 : (size_t)2 * p.CR * 256;
-  int max_taps = 1;
-  for (int g = 0; g < p.ngrp; ++g) max_taps = p.grp[g].ntaps > max_taps ? p.grp[g].ntaps : max_taps;
-  p.sb = 3;
-  for (;;) {
-    const long rest = (long)kSmemLimit - 2048 - (long)stage_bytes - (long)p.sb * p.b_slot_bytes;
-    p.sa = (int)(rest / A_BYTES);
-    if (p.sa > kMaxSA) p.sa = kMaxSA;
-    if (p.sa >= max_taps + 1 || p.sb == 2) break;
-    p.sb = 2;
+  p.stage_bytes = p.a_cap * (int)A_BYTES + p.b_slot_bytes;
+  // shared-memory budget: S pipeline stages + 2 epilogue staging chunks + 1 KB alignment + 1 KB tap over-read.
+  // Smaller staging chunks (32 rows) are used when they buy another pipeline stage.
+  auto stages_for = [&](int cr) {
+    const long rest = (long)kSmemLimit - 2048 - (p.direct ? 0 : (long)2 * cr * 256);
+    const int s2 = (int)(rest / p.stage_bytes);
+    return s2 > kMaxStages ? kMaxStages : s2;
+  };
+  if (p.NCLIP == 1) {
+    p.CR = p.NT < 64 ? p.NT : 64;
+    if (p.NT > 32 && stages_for(32) > stages_for(p.CR)) p.CR = 32;
+  } else {
+    p.CR = p.NT;
   }
-  LADIFF_REQUIRE(p.sa >= 2, LADIFF_ERR_ARG, "tc_conv: no shared memory left for the weight ring (N=%d)", p.NMMA);
+  p.S = stages_for(p.CR);
+  LADIFF_REQUIRE(p.S >= 2, LADIFF_ERR_ARG, "tc_conv: tile N=%d with %d taps per stage does not fit two pipeline stages", p.NMMA, p.a_cap);
   p.tmW = *d.tmW;
   int rc = make_tmap_x(&p.tmX, d.x, d.B, Lv, Cv, pitch_v, d.x_bstride, p.BOXROWS);
   if (rc) return rc;
@@ -541,7 +588,7 @@ int tc_conv_plan(const TcConvDesc& d, TcConvParams* pp, TcRefView* rv) {
     p.res = d.res; p.res_bstride = d.res_bstride; p.res_pitch = d.res_pitch;
     LADIFF_REQUIRE(d.kind != TC_KIND_UP, LADIFF_ERR_ARG, "tc_conv: the upsample conv has no direct epilogue");
   } else {
-    const int phases = p.up_cout ? 2 : 1, Cc = p.up_cout ? p.up_cout : d.CoutV;
+    const int phases = p.up_cout ? 2 : 1, Cc = p.up_cout ? p.up_cout : (d.split_m ? d.split_m : d.CoutV);
     LADIFF_REQUIRE(((uintptr_t)d.out % 16) == 0 && d.out_pitch % 8 == 0 && d.out_bstride % 8 == 0, LADIFF_ERR_ARG,
                    "tc_conv: output view is not 16-byte aligned");
     rc = make_tmap_y(&p.tmY, d.out, Cc, phases, Lout, d.B, d.out_pitch, d.out_bstride, p.CR);
@@ -549,16 +596,25 @@ int tc_conv_plan(const TcConvDesc& d, TcConvParams* pp, TcRefView* rv) {
     const int rem = p.NT % p.CR;
     rc = make_tmap_y(&p.tmYr, d.out, Cc, phases, Lout, d.B, d.out_pitch, d.out_bstride, rem ? rem : p.CR);
     if (rc) return rc;
+    if (d.split_m) {
+      LADIFF_REQUIRE(((uintptr_t)d.out2 % 16) == 0 && d.out2_pitch % 8 == 0 && d.out2_bstride % 8 == 0, LADIFF_ERR_ARG,
+                     "tc_conv: second output view is not 16-byte aligned");
+      rc = make_tmap_y(&p.tmY2, d.out2, d.CoutV - d.split_m, 1, Lout, d.B, d.out2_pitch, d.out2_bstride, p.CR);
+      if (rc) return rc;
+      rc = make_tmap_y(&p.tmY2r, d.out2, d.CoutV - d.split_m, 1, Lout, d.B, d.out2_pitch, d.out2_bstride, rem ? rem : p.CR);
+      if (rc) return rc;
+    }
   }
   if (rv) {
     rv->x = d.x; rv->bstride = d.x_bstride; rv->pitch = pitch_v; rv->Lv = Lv; rv->Cv = Cv; rv->w = d.w; rv->Ktot = d.Ktot;
     rv->out = d.out; rv->out_bstride = d.out_bstride; rv->out_pitch = d.out_pitch;
+    rv->out2 = d.out2; rv->out2_bstride = d.out2_bstride; rv->out2_pitch = d.out2_pitch;
   }
   return 0;
 }
 
 static size_t tc_smem_bytes(const TcConvParams& p) {
-  return (size_t)p.sa * A_BYTES + (size_t)p.sb * p.b_slot_bytes + (p.direct ? 0 : (size_t)2 * p.CR * 256) + 2048;
+  return (size_t)p.S * p.stage_bytes + (p.direct ? 0 : (size_t)2 * p.CR * 256) + 2048;
 }
 
 int tc_conv_launch(const TcConvParams& p, cudaStream_t st) {
@@ -570,8 +626,28 @@ int tc_conv_launch(const TcConvParams& p, cudaStream_t st) {
     attr_set = true;
   }
   const int tiles = p.MT * p.n_ntiles, nsm = tc_num_sms();
-  tc_conv_kernel<<<tiles < nsm ? tiles : nsm, kThreads, smem, st>>>(p);
+  const int grid = tiles < nsm ? tiles : nsm;
+  static const bool want_prof = getenv("LADIFF_TC_PROF") != nullptr;   // debug aid: per-role mbarrier wait cycles, printed per launch
+  if (!want_prof) {
+    tc_conv_kernel<<<grid, kThreads, smem, st>>>(p);
+    LADIFF_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  TcConvParams q = p;
+  unsigned long long* dprof = nullptr;
+  LADIFF_CUDA_OK(cudaMalloc((void**)&dprof, sizeof(unsigned long long) * 8 * grid));
+  LADIFF_CUDA_OK(cudaMemset(dprof, 0, sizeof(unsigned long long) * 8 * grid));
+  q.prof = dprof;
+  tc_conv_kernel<<<grid, kThreads, smem, st>>>(q);
   LADIFF_CUDA_OK(cudaGetLastError());
+  LADIFF_CUDA_OK(cudaStreamSynchronize(st));
+  std::vector<unsigned long long> hp((size_t)8 * grid);
+  LADIFF_CUDA_OK(cudaMemcpy(hp.data(), dprof, sizeof(unsigned long long) * hp.size(), cudaMemcpyDeviceToHost));
+  cudaFree(dprof);
+  double a[5] = {0, 0, 0, 0, 0};
+  for (int i = 0; i < grid; ++i) for (int k = 0; k < 5; ++k) a[k] += (double)hp[(size_t)i * 8 + k] / grid;
+  fprintf(stderr, "[tc_prof] Cout=%d N=%d(NT=%d x%d) S=%d a_cap=%d grid=%d tiles=%d | cycles/CTA: total %.0f  producer-wait-empty %.0f  mma-wait-full %.0f  "
+                  "mma-wait-tmem %.0f  epi-wait-acc %.0f\n", p.Cout, p.NMMA, p.NT, p.NCLIP, p.S, p.a_cap, grid, tiles, a[4], a[0], a[1], a[2], a[3]);
   return 0;
 }
 

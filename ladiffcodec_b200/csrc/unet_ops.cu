@@ -24,54 +24,68 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // ------------------------------------------------------------------ GroupNorm apply
+// grid (ceil(L / rows_per_cta), B), 256 threads.  Prologue: warp g reduces the conv epilogue's partial sums of group g
+// (fixed lane assignment + xor-shuffle tree: deterministic); every thread then owns ONE 8-channel chunk for the whole
+// kernel, so its fused scale/shift (gamma * rstd * (film_scale + 1), ...) live in registers.
 __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a, int rows_per_cta) {
-  extern __shared__ float sm[];
-  const int C = a.y.C, Cg = C / 8, spg = Cg / 32, b = blockIdx.y;
-  float* sa = sm;
-  float* sb = sm + C;
+  const int C = a.y.C, Cg = C / 8, spg = Cg / 32, nslots = C / 32, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __shared__ float s_mean[8], s_rstd[8];
-  if (threadIdx.x < 8) {
-    const int g = threadIdx.x;
+  {
     float s1 = 0.f, s2 = 0.f;
-    for (int nt = 0; nt < a.n_ntiles; ++nt) {
-      const float2* row = a.stats + ((long long)b * a.n_ntiles + nt) * (C / 32) + g * spg;
-      for (int s = 0; s < spg; ++s) { s1 += row[s].x; s2 += row[s].y; }
+    const int n = a.n_ntiles * spg;
+    const float2* base = a.stats + (long long)b * a.n_ntiles * nslots + warp * spg;
+    for (int i = lane; i < n; i += 32) {
+      const int pt = i / spg, s = i - pt * spg;
+      const float2 v = base[pt * nslots + s];
+      s1 += v.x; s2 += v.y;
     }
-    const float n = (float)Cg * (float)a.L;
-    const float m = s1 / n;
-    float var = s2 / n - m * m;
-    var = var < 0.f ? 0.f : var;
-    s_mean[g] = m;
-    s_rstd[g] = rsqrtf(var + 1e-5f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) {
+      const float cnt = (float)Cg * (float)a.L;
+      const float m = s1 / cnt;
+      float var = s2 / cnt - m * m;
+      var = var < 0.f ? 0.f : var;
+      s_mean[warp] = m;
+      s_rstd[warp] = rsqrtf(var + 1e-5f);
+    }
   }
   __syncthreads();
-  const float* film = nullptr;
-  if (a.film) film = a.film + (long long)a.t_dev[b] * a.film_stride;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / Cg;
-    float ga = a.gamma[c] * s_rstd[g];
-    float be = a.beta[c] - s_mean[g] * ga;
-    if (film) {
-      const float sc = film[c] + 1.f, sh = film[C + c];
-      ga *= sc;
-      be = be * sc + sh;
+  const int cv = C / 8;                       // 8-channel chunks per row: 32, 64 or 128
+  const int c0 = (threadIdx.x % cv) * 8, rsub = threadIdx.x / cv, rstep = 256 / cv;
+  float sa[8], sb[8];
+  {
+    const float* film = a.film ? a.film + (long long)a.t_dev[b] * a.film_stride : nullptr;
+    const float mean = s_mean[c0 / Cg], rstd = s_rstd[c0 / Cg];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float ga = a.gamma[c0 + j] * rstd;
+      float be = a.beta[c0 + j] - mean * ga;
+      if (film) {
+        const float sc = film[c0 + j] + 1.f, sh = film[C + c0 + j];
+        ga *= sc;
+        be = be * sc + sh;
+      }
+      sa[j] = ga; sb[j] = be;
     }
-    sa[c] = ga; sb[c] = be;
   }
-  __syncthreads();
-  const int cv = C / 8;
   const int r0 = blockIdx.x * rows_per_cta;
   const int r1 = min(r0 + rows_per_cta, a.L);
-  const long long total = (long long)(r1 - r0) * cv;
-  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
-    const int row = r0 + (int)(i / cv), c0 = (int)(i % cv) * 8;
-    const uint4 u = *reinterpret_cast<const uint4*>(a.y.p + (long long)b * a.y.bstride + (long long)row * a.y.pitch + c0);
+  const bf16* yb = a.y.p + (long long)b * a.y.bstride + c0;
+  const bf16* rb = a.res.p ? a.res.p + (long long)b * a.res.bstride + c0 : nullptr;
+  bf16* ob = a.out.p + (long long)b * a.out.bstride + c0;
+  for (int row = r0 + rsub; row < r1; row += rstep) {
+    const uint4 u = *reinterpret_cast<const uint4*>(yb + (long long)row * a.y.pitch);
     float f[8];
     unpack8(u, f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j] * sa[c0 + j] + sb[c0 + j]);
-    if (a.res.p) {
-      const uint4 ur = *reinterpret_cast<const uint4*>(a.res.p + (long long)b * a.res.bstride + (long long)row * a.res.pitch + c0);
+    for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j] * sa[j] + sb[j]);
+    if (rb) {
+      const uint4 ur = *reinterpret_cast<const uint4*>(rb + (long long)row * a.res.pitch);
       float r[8];
       unpack8(ur, r);
 #pragma unroll
@@ -81,7 +95,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a, int rows_p
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = tanhf(f[j]);
     }
-    *reinterpret_cast<uint4*>(a.out.p + (long long)b * a.out.bstride + (long long)row * a.out.pitch + c0) = pack8(f);
+    *reinterpret_cast<uint4*>(ob + (long long)row * a.out.pitch) = pack8(f);
   }
 }
 
@@ -128,99 +142,154 @@ __global__ void __launch_bounds__(256) layernorm_cl_kernel(ClView x, const float
   }
 }
 
-// ------------------------------------------------------------------ linear attention
-// ctx[b][h][d][e] = 32^-1/2 * sum_n softmax_n(k)[d,n] v[e,n]      grid (4, B), 256 threads
-__global__ void __launch_bounds__(256) linattn_ctx_kernel(ClView qkv, float* __restrict__ ctx, int L) {
-  const int h = blockIdx.x, b = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bf16* base = qkv.p + (long long)b * qkv.bstride;
-  const int kc = 128 + h * 32 + lane, vc = 256 + h * 32 + lane;
-  __shared__ float red_m[8][32];
-  __shared__ float red_z[8][32];
-  __shared__ float tile_k[8][4][32];
-  __shared__ __align__(16) float tile_v[8][4][32];
-  __shared__ float ctx_s[32][33];
-  // pass 1: max over positions per d
-  float m = -INFINITY;
-  for (int n = warp; n < L; n += 8) m = fmaxf(m, __bfloat162float(base[(long long)n * qkv.pitch + kc]));
-  red_m[warp][lane] = m;
+// ------------------------------------------------------------------ linear attention (unet.py:208-221)
+// ctx[b][h][d][e] = 32^-1/2 * sum_n softmax_n(k)[d,n] v[e,n].
+// grid (nsplit, 4, B), 256 threads: each CTA reduces a segment of <= LA_S positions held in shared memory (exact
+// two-pass softmax inside the segment) and writes (max, sum, ctx) partials; the last CTA of a (clip, head) to arrive
+// (ticket counter) merges the partials in segment order, so the result does not depend on CTA scheduling.
+constexpr int LA_S = 160;
+constexpr int LA_PART = 64 + 1024;   // floats per partial: m[32], z[32], ctx[32][32]
+
+__global__ void __launch_bounds__(256) linattn_ctx_kernel(ClView qkv, float* __restrict__ ctx, float* part, int* counters, int L, int S,
+                                                          int nsplit) {
+  const int sp = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  __shared__ __align__(16) float ks[LA_S][32];
+  __shared__ __align__(16) float vs[LA_S][32];
+  __shared__ float red[8][32];
+  __shared__ float m_s[32], z_s[32];
+  __shared__ int is_last;
+  const int n_lo = sp * S, cnt = min(L, n_lo + S) - n_lo;
+  {
+    const int c = tid & 7;
+    const bf16* base = qkv.p + (long long)b * qkv.bstride + (c < 4 ? 128 : 256) + h * 32 + (c & 3) * 8;
+    float (*dst)[32] = c < 4 ? ks : vs;
+    for (int i = tid >> 3; i < cnt; i += 32) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(base + (long long)(n_lo + i) * qkv.pitch), f);
+      float4* d4 = reinterpret_cast<float4*>(&dst[i][(c & 3) * 8]);
+      d4[0] = make_float4(f[0], f[1], f[2], f[3]);
+      d4[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+  }
   __syncthreads();
+  float m = -INFINITY;
+  for (int i = warp; i < cnt; i += 8) m = fmaxf(m, ks[i][lane]);
+  red[warp][lane] = m;
+  __syncthreads();
+  if (warp == 0) {
 #pragma unroll
-  for (int w = 0; w < 8; ++w) m = fmaxf(m, red_m[w][lane]);
-  // pass 2: exp-sum and context
-  float z = 0.f, acc[32];
-#pragma unroll
-  for (int e = 0; e < 32; ++e) acc[e] = 0.f;
-  for (int n0 = warp * 4; n0 < L; n0 += 32) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + j;
-      float kk = 0.f, vv = 0.f;
-      if (n < L) {
-        kk = __bfloat162float(base[(long long)n * qkv.pitch + kc]);
-        vv = __bfloat162float(base[(long long)n * qkv.pitch + vc]);
-      }
-      tile_k[warp][j][lane] = kk;
-      tile_v[warp][j][lane] = vv;
-    }
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (n0 + j < L) {
-        const float p = expf(tile_k[warp][j][lane] - m);
-        z += p;
-        const float4* v4 = reinterpret_cast<const float4*>(tile_v[warp][j]);
-#pragma unroll
-        for (int e4 = 0; e4 < 8; ++e4) {
-          const float4 t = v4[e4];
-          acc[4 * e4 + 0] += p * t.x; acc[4 * e4 + 1] += p * t.y;
-          acc[4 * e4 + 2] += p * t.z; acc[4 * e4 + 3] += p * t.w;
-        }
-      }
-    }
-    __syncwarp();
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w][lane]);
+    m_s[lane] = m;
   }
-  red_z[warp][lane] = z;
-  for (int w = 0; w < 8; ++w) {       // deterministic warp-ordered reduction
-    if (warp == w) {
-#pragma unroll
-      for (int e = 0; e < 32; ++e) ctx_s[lane][e] = (w == 0 ? 0.f : ctx_s[lane][e]) + acc[e];
-    }
-    __syncthreads();
+  __syncthreads();
+  m = m_s[lane];
+  float z = 0.f;
+  for (int i = warp; i < cnt; i += 8) {
+    const float pe = expf(ks[i][lane] - m);
+    ks[i][lane] = pe;
+    z += pe;
   }
-  const float scale = 0.17677669529663687f;  // 32^-0.5 (q * scale, unet.py:216)
-  for (int i = threadIdx.x; i < 1024; i += 256) {
-    const int d = i >> 5, e = i & 31;
+  __syncthreads();          // all of red[] has been read by warp 0 and every p is in place
+  red[warp][lane] = z;
+  __syncthreads();
+  if (warp == 0) {
     float zz = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) zz += red_z[w][d];
-    ctx[(((long long)b * 4 + h) * 32 + d) * 32 + e] = ctx_s[d][e] / zz * scale;
+    for (int w = 0; w < 8; ++w) zz += red[w][lane];
+    z_s[lane] = zz;
   }
+  const int d = tid >> 3, e4 = (tid & 7) * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < cnt; ++i) {
+    const float pe = ks[i][d];
+    const float4 v = *reinterpret_cast<const float4*>(&vs[i][e4]);
+    acc.x += pe * v.x; acc.y += pe * v.y; acc.z += pe * v.z; acc.w += pe * v.w;
+  }
+  __syncthreads();
+  const float scale = 0.17677669529663687f;  // 32^-0.5 (q * scale, unet.py:216)
+  float* cout = ctx + (((long long)b * 4 + h) * 32 + d) * 32 + e4;
+  if (nsplit == 1) {
+    const float inv = scale / z_s[d];
+    *reinterpret_cast<float4*>(cout) = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+    return;
+  }
+  float* pp = part + (((long long)b * 4 + h) * nsplit + sp) * LA_PART;
+  if (tid < 32) { pp[tid] = m_s[tid]; pp[32 + tid] = z_s[tid]; }
+  *reinterpret_cast<float4*>(pp + 64 + d * 32 + e4) = acc;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) is_last = atomicAdd(&counters[b * 4 + h], 1) == nsplit - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const float* p0 = part + ((long long)b * 4 + h) * nsplit * LA_PART;
+  float M = -INFINITY;
+  for (int s = 0; s < nsplit; ++s) M = fmaxf(M, __ldcg(p0 + (long long)s * LA_PART + d));
+  float Z = 0.f;
+  acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < nsplit; ++s) {
+    const float* ps = p0 + (long long)s * LA_PART;
+    const float w = expf(__ldcg(ps + d) - M);
+    Z += w * __ldcg(ps + 32 + d);
+    const float4 c = __ldcg(reinterpret_cast<const float4*>(ps + 64 + d * 32 + e4));
+    acc.x += w * c.x; acc.y += w * c.y; acc.z += w * c.z; acc.w += w * c.w;
+  }
+  const float inv = scale / Z;
+  *reinterpret_cast<float4*>(cout) = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+  if (tid == 0) counters[b * 4 + h] = 0;     // ready for the next launch on this stream
 }
 
-// out[b][n][h*32+e] = sum_d ctx[d][e] softmax_d(q[:,n])[d]          grid (ceil(L/64), B), 256 threads
+// out[b][n][h*32+e] = sum_d ctx[h][d][e] softmax_d(q[n,h,:])[d]      grid (ceil(L/64), B), 256 threads
+// warp w: head w&3, rows 32*(w>>2) + lane; one (row, head) per thread: q row in registers, ctx broadcast from smem
 __global__ void __launch_bounds__(256) linattn_out_kernel(ClView qkv, const float* __restrict__ ctx, ClView out, int L) {
   const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __shared__ float cs[4][32][32];
-  for (int i = threadIdx.x; i < 4096; i += 256) (&cs[0][0][0])[i] = ctx[(long long)b * 4096 + i];
+  __shared__ __align__(16) float cs[4][32][32];
+  {
+    const float4* src = reinterpret_cast<const float4*>(ctx + (long long)b * 4096);
+    float4* dst = reinterpret_cast<float4*>(&cs[0][0][0]);
+    for (int i = threadIdx.x; i < 1024; i += 256) dst[i] = src[i];
+  }
   __syncthreads();
-  const int n0 = blockIdx.x * 64;
-  for (int task = warp; task < 256; task += 8) {
-    const int n = n0 + (task >> 2), h = task & 3;
-    if (n >= L) break;
-    const float q = __bfloat162float(qkv.p[(long long)b * qkv.bstride + (long long)n * qkv.pitch + h * 32 + lane]);
-    float mx = q;
+  const int h = warp & 3, n = blockIdx.x * 64 + (warp >> 2) * 32 + lane;
+  if (n >= L) return;
+  const bf16* qr = qkv.p + (long long)b * qkv.bstride + (long long)n * qkv.pitch + h * 32;
+  float q[32];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    const float ex = expf(q - mx);
-    float sum = ex;
+  for (int i = 0; i < 4; ++i) {
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(qr + 8 * i), f);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float qs = ex / sum;
-    float acc = 0.f;
+    for (int j = 0; j < 8; ++j) q[8 * i + j] = f[j];
+  }
+  float mx = q[0];
 #pragma unroll
-    for (int d = 0; d < 32; ++d) acc += cs[h][d][lane] * __shfl_sync(0xffffffffu, qs, d);
-    out.p[(long long)b * out.bstride + (long long)n * out.pitch + h * 32 + lane] = __float2bfloat16(acc);
+  for (int i = 1; i < 32; ++i) mx = fmaxf(mx, q[i]);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { q[i] = expf(q[i] - mx); sum += q[i]; }
+  const float inv = 1.f / sum;
+  float acc[32];
+#pragma unroll
+  for (int e = 0; e < 32; ++e) acc[e] = 0.f;
+#pragma unroll 4
+  for (int d = 0; d < 32; ++d) {
+    const float pd = q[d] * inv;
+    const float4* c4 = reinterpret_cast<const float4*>(&cs[h][d][0]);
+#pragma unroll
+    for (int e4 = 0; e4 < 8; ++e4) {
+      const float4 c = c4[e4];
+      acc[4 * e4 + 0] += pd * c.x; acc[4 * e4 + 1] += pd * c.y;
+      acc[4 * e4 + 2] += pd * c.z; acc[4 * e4 + 3] += pd * c.w;
+    }
+  }
+  bf16* orow = out.p + (long long)b * out.bstride + (long long)n * out.pitch + h * 32;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = acc[8 * i + j];
+    *reinterpret_cast<uint4*>(orow + 8 * i) = pack8(f);
   }
 }
 
@@ -438,10 +507,12 @@ __global__ void sinusoid_kernel(float* emb, int T, int dim) {
 
 int gn_apply_launch(const GnApplyArgs& a, int B, cudaStream_t st) {
   const int C = a.y.C;
-  LADIFF_REQUIRE(C % 256 == 0 && C <= 4096, LADIFF_ERR_ARG, "gn_apply: C=%d", C);
-  const int rows = 32;
+  LADIFF_REQUIRE(C == 256 || C == 512 || C == 1024, LADIFF_ERR_ARG, "gn_apply: C=%d", C);
+  const int rstep = 256 / (C / 8);
+  int rows = cdiv(a.L * B, 4 * 148);                     // ~4 CTAs per SM
+  rows = cdiv(rows < rstep ? rstep : rows, rstep) * rstep;
   dim3 grid(cdiv(a.L, rows), B);
-  gn_apply_kernel<<<grid, 256, 2 * C * sizeof(float), st>>>(a, rows);
+  gn_apply_kernel<<<grid, 256, 0, st>>>(a, rows);
   LADIFF_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -459,8 +530,23 @@ int layernorm_cl_launch(ClView x, const float* g, ClView res, ClView out, int B,
   return 0;
 }
 
-int linattn_launch(ClView qkv, float* ctx, ClView out, int B, int L, cudaStream_t st) {
-  linattn_ctx_kernel<<<dim3(4, B), 256, 0, st>>>(qkv, ctx, L);
+void linattn_split(int B, int L, int* S, int* nsplit) {
+  const int target = cdiv(600, 4 * B);                  // ~4 CTAs per SM over (split, head, clip)
+  int s = cdiv(L, target < 1 ? 1 : target);
+  s = s < 32 ? 32 : (s > LA_S ? LA_S : s);
+  *S = s;
+  *nsplit = cdiv(L, s);
+}
+size_t linattn_part_floats(int B, int L) {
+  int S, ns;
+  linattn_split(B, L, &S, &ns);
+  return (size_t)B * 4 * ns * LA_PART;
+}
+
+int linattn_launch(ClView qkv, float* ctx, float* part, int* counters, ClView out, int B, int L, cudaStream_t st) {
+  int S, ns;
+  linattn_split(B, L, &S, &ns);
+  linattn_ctx_kernel<<<dim3(ns, 4, B), 256, 0, st>>>(qkv, ctx, part, counters, L, S, ns);
   LADIFF_CUDA_OK(cudaGetLastError());
   linattn_out_kernel<<<dim3(cdiv(L, 64), B), 256, 0, st>>>(qkv, ctx, out, L);
   LADIFF_CUDA_OK(cudaGetLastError());

@@ -31,8 +31,10 @@ int gn_apply_launch(const GnApplyArgs& a, int B, cudaStream_t st);
 int layernorm_cl_launch(ClView x, const float* g, ClView res, ClView out, int B, int L, cudaStream_t st);
 
 // LinearAttention core (between to_qkv and to_out)              unet.py:208-221
-// qkv [B][L][384] bf16 (q | k | v, each 4 heads x 32) -> out [B][L][128] bf16; ctx scratch [B][4][32][32] f32
-int linattn_launch(ClView qkv, float* ctx, ClView out, int B, int L, cudaStream_t st);
+// qkv [B][L][384] bf16 (q | k | v, each 4 heads x 32) -> out [B][L][128] bf16; ctx scratch [B][4][32][32] f32;
+// part scratch linattn_part_floats(B, L) f32; counters [4B] int32, zero before the first launch (the kernel re-zeroes them)
+int linattn_launch(ClView qkv, float* ctx, float* part, int* counters, ClView out, int B, int L, cudaStream_t st);
+size_t linattn_part_floats(int B, int L);
 // Attention core (mid block)                                    unet.py:234-245
 int fullattn_launch(ClView qkv, ClView out, int B, int L, cudaStream_t st);
 
