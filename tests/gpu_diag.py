@@ -18,7 +18,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 OUT = os.path.join(ROOT, "gpurun_out")
 
-STAGES = ["conv_op", "codec", "unet_simt", "unet_tc", "ddpm", "synth", "synth_B"]
+STAGES = ["conv_op", "codec", "unet_simt", "unet_tc", "ddpm", "synth", "synth_B"]   # + "conv_prof" on request
 
 
 def stage_conv_op(res):
@@ -58,6 +58,28 @@ def stage_conv_op(res):
                                 stats_err=round((st[:, :, 0].cpu() - s_ref).abs().max().item(), 5))
         res[f"B{B}_L{L}_Cin{Cin}_Cout{Cout}_k{k}"] = dict(out=out, ref_absmax=ref.abs().max().item())
         print(f"conv B{B} L{L} Cin{Cin} Cout{Cout} k{k}: " + " ".join(f"{k2}={v}" for k2, v in out.items()), flush=True)
+
+
+def stage_conv_prof(res):
+    """Config-2-sized conv shapes through the operator entry point (run with LADIFF_TC_PROF=1 for per-role wait cycles)."""
+    import ctypes
+    import torch
+    from ladiffcodec_b200 import _lib
+    lib = _lib.get_lib()
+    P = ctypes.c_void_p
+    shapes = [(32, 1200, 256, 256, 3), (32, 1200, 512, 256, 3), (32, 600, 768, 512, 3), (32, 300, 512, 512, 3), (32, 150, 1024, 1024, 3),
+              (32, 75, 1024, 1024, 3), (32, 75, 2048, 1024, 3), (32, 1200, 256, 384, 1), (32, 75, 1024, 384, 1), (32, 1200, 256, 256, 7)]
+    for (B, L, Cin, Cout, k) in shapes:
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn(B, L, Cin, generator=g).to(torch.bfloat16).cuda()
+        w = (torch.randn(Cout, Cin, k, generator=g) * (Cin * k) ** -0.5).cuda()
+        bias = torch.zeros(Cout).cuda()
+        y = torch.empty(B, L, Cout, device="cuda", dtype=torch.bfloat16)
+        for impl in (0, 2):
+            rc = lib.ladiff_op_conv1d_cl(P(x.data_ptr()), P(w.data_ptr()), P(bias.data_ptr()), B, L, Cin, Cout, k, P(y.data_ptr()), 0, impl, None)
+            torch.cuda.synchronize()
+            print(f"conv_prof B{B} L{L} Cin{Cin} Cout{Cout} k{k} impl{impl} rc={rc} gflop={2e-9 * B * L * Cin * Cout * k:.2f}", flush=True)
+            res[f"L{L}_Cin{Cin}_Cout{Cout}_k{k}_impl{impl}"] = rc
 
 
 def _setup(name="A_3kbps"):
