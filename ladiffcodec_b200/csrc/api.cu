@@ -1,5 +1,6 @@
 // C-ABI of ladiff_b200 (include/ladiff_b200.h): handle, strict loader, load-time folds, stage plans.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -101,7 +102,15 @@ struct Plan {
   std::vector<std::string> op_label;
   std::vector<cudaEvent_t> ev;           // profiling: [2*i], [2*i+1] around conv op i; last two around the whole evaluation
   long long launches_per_run = 0;
-  ~Plan() { for (auto e : ev) cudaEventDestroy(e); }
+  long long runs = 0;
+  cudaGraphExec_t gexec = nullptr;       // captured evaluation (see run_plan)
+  int graph_impl = 0;
+  cudaStream_t cap_stream = nullptr;
+  ~Plan() {
+    for (auto e : ev) cudaEventDestroy(e);
+    if (gexec) cudaGraphExecDestroy(gexec);
+    if (cap_stream) cudaStreamDestroy(cap_stream);
+  }
 };
 
 }  // namespace
@@ -703,6 +712,12 @@ ClView view(bf16* p, int L, int pitch, int C, int ch0 = 0) {
 
 struct PlanBuilder {
   H* h; Plan* pl; int B;
+  void label(const char* fmt, int a, int b, int c, int d) {
+    char buf[120];
+    snprintf(buf, sizeof(buf), fmt, a, b, c, d);
+    pl->op_label.resize(pl->ops.size());
+    pl->op_label.back() = buf;
+  }
   // conv: `in` has Lin rows; writes Lout rows into `out` (bf16) or out32 (fp32, contiguous [B][Lout][CoutV])
   int conv(const PackedConv& pc, ClView in, int Lin, ClView out, float* out32, bool want_stats, int* n_ntiles, ClView res,
            ClView out2 = ClView{nullptr, 0, 0, 0}) {
@@ -754,6 +769,7 @@ struct PlanBuilder {
     a.film_stride = h->un.film_stride; a.t_dev = pl->bufs.t_dev; a.res = res; a.out = out; a.L = L; a.do_tanh = do_tanh ? 1 : 0;
     const int BB = B;
     pl->ops.push_back([a, BB](cudaStream_t st) { return gn_apply_launch(a, BB, st); });
+    label("gn_apply C=%d L=%d film=%d res=%d", y.C, L, film ? 1 : 0, res.p ? 1 : 0);
     pl->launches_per_run++;
     return 0;
   }
@@ -778,6 +794,7 @@ struct PlanBuilder {
   int layernorm(ClView x, const float* g, ClView res, ClView out, int L) {
     const int BB = B;
     pl->ops.push_back([x, g, res, out, BB, L](cudaStream_t st) { return layernorm_cl_launch(x, g, res, out, BB, L, st); });
+    label("layernorm C=%d L=%d res=%d", x.C, L, res.p ? 1 : 0, 0);
     pl->launches_per_run++;
     return 0;
   }
@@ -791,12 +808,14 @@ struct PlanBuilder {
     const int BB = B; float* ctx = u.ctx; float* lap = u.la_part; int* lac = u.la_cnt;
     if (linear) {
       pl->ops.push_back([qkv, ctx, lap, lac, ao, BB, L](cudaStream_t st) { return linattn_launch(qkv, ctx, lap, lac, ao, BB, L, st); });
+      label("linattn(ctx+out) L=%d", L, 0, 0, 0);
       pl->launches_per_run += 2;
       ClView yo = view(u.tY, L, a.C, a.C);
       TRY(conv(a.out, ao, L, yo, nullptr, false, nullptr, none));
       TRY(layernorm(yo, a.out_g, x, out, L));
     } else {
       pl->ops.push_back([qkv, ao, BB, L](cudaStream_t st) { return fullattn_launch(qkv, ao, BB, L, st); });
+      label("fullattn L=%d", L, 0, 0, 0);
       pl->launches_per_run++;
       TRY(conv(a.out, ao, L, out, nullptr, false, nullptr, x));
     }
@@ -879,7 +898,32 @@ int build_plan(H* h, void* ws_unet, int B, int L, Plan** out) {
 int run_plan(H* h, Plan* pl, cudaStream_t st) {
   pl->op_flops.resize(pl->ops.size(), 0.0);
   if (!h->profiling) {
-    for (auto& op : pl->ops) TRY(op(st));
+    // The evaluation is a fixed launch sequence over fixed buffers (the step index lives in t_dev), so after one eager
+    // run (which also performs the one-time cudaFuncSetAttribute calls) it is captured into a CUDA graph and replayed:
+    // ~170 kernel launches per DDPM step become one graph launch.
+    static const bool no_graph = getenv("LADIFF_NO_GRAPH") != nullptr || getenv("LADIFF_TC_PROF") != nullptr;
+    if (no_graph || pl->runs == 0) {
+      for (auto& op : pl->ops) TRY(op(st));
+    } else {
+      if (pl->gexec && pl->graph_impl != h->conv_impl) { cudaGraphExecDestroy(pl->gexec); pl->gexec = nullptr; }
+      if (!pl->gexec) {
+        cudaGraph_t g = nullptr;
+        // capture on a private stream: the caller's stream may be the legacy default stream, which cannot capture
+        if (!pl->cap_stream) LADIFF_CUDA_OK(cudaStreamCreateWithFlags(&pl->cap_stream, cudaStreamNonBlocking));
+        LADIFF_CUDA_OK(cudaStreamBeginCapture(pl->cap_stream, cudaStreamCaptureModeThreadLocal));
+        int rc = 0;
+        for (auto& op : pl->ops) { rc = op(pl->cap_stream); if (rc) break; }
+        cudaError_t e = cudaStreamEndCapture(pl->cap_stream, &g);
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        LADIFF_CUDA_OK(e);
+        e = cudaGraphInstantiate(&pl->gexec, g, 0);
+        cudaGraphDestroy(g);
+        LADIFF_CUDA_OK(e);
+        pl->graph_impl = h->conv_impl;
+      }
+      LADIFF_CUDA_OK(cudaGraphLaunch(pl->gexec, st));
+    }
+    pl->runs++;
   } else {   // CUDA events on the launching stream around every conv launch (bench.py roofline)
     if (pl->ev.empty()) {
       pl->ev.resize(2 * pl->ops.size() + 2);
@@ -887,10 +931,10 @@ int run_plan(H* h, Plan* pl, cudaStream_t st) {
     }
     LADIFF_CUDA_OK(cudaEventRecord(pl->ev[2 * pl->ops.size()], st));
     for (size_t i = 0; i < pl->ops.size(); ++i) {
-      const bool is_conv = pl->op_flops[i] > 0.0;
-      if (is_conv) LADIFF_CUDA_OK(cudaEventRecord(pl->ev[2 * i], st));
+      const bool timed = pl->op_flops[i] > 0.0 || h->profiling == 2;
+      if (timed) LADIFF_CUDA_OK(cudaEventRecord(pl->ev[2 * i], st));
       TRY(pl->ops[i](st));
-      if (is_conv) LADIFF_CUDA_OK(cudaEventRecord(pl->ev[2 * i + 1], st));
+      if (timed) LADIFF_CUDA_OK(cudaEventRecord(pl->ev[2 * i + 1], st));
     }
     LADIFF_CUDA_OK(cudaEventRecord(pl->ev[2 * pl->ops.size() + 1], st));
     h->last_plan = pl;
@@ -1193,7 +1237,7 @@ extern "C" int32_t ladiff_set_conv_impl(LadiffHandle* h, int32_t impl) {
 }
 extern "C" int32_t ladiff_set_profiling(LadiffHandle* h, int32_t on) {
   LADIFF_REQUIRE(h, LADIFF_ERR_ARG, "null handle");
-  h->profiling = on ? 1 : 0;
+  h->profiling = on < 0 ? 0 : (on > 2 ? 2 : on);   // 1: events around conv launches; 2: around every op of the evaluation
   if (!on) h->last_plan = nullptr;
   return 0;
 }
@@ -1223,12 +1267,13 @@ extern "C" int32_t ladiff_profile_dump(LadiffHandle* h, char* buf, int64_t cap) 
   LADIFF_CUDA_OK(cudaDeviceSynchronize());
   Plan* pl = h->last_plan;
   std::string out;
+  pl->op_label.resize(pl->ops.size());
   for (size_t i = 0; i < pl->ops.size(); ++i) {
-    if (pl->op_flops[i] <= 0.0) continue;
+    if (pl->op_flops[i] <= 0.0 && h->profiling != 2) continue;
     float t = 0.f;
-    LADIFF_CUDA_OK(cudaEventElapsedTime(&t, pl->ev[2 * i], pl->ev[2 * i + 1]));
+    if (cudaEventElapsedTime(&t, pl->ev[2 * i], pl->ev[2 * i + 1]) != cudaSuccess) { cudaGetLastError(); continue; }
     char line[256];
-    snprintf(line, sizeof(line), "%.4f %.3f %s\n", t, pl->op_flops[i] * 1e-9, i < pl->op_label.size() ? pl->op_label[i].c_str() : "");
+    snprintf(line, sizeof(line), "%.4f %.3f %s\n", t, pl->op_flops[i] * 1e-9, pl->op_label[i].c_str());
     out += line;
   }
   snprintf(buf, (size_t)cap, "%s", out.c_str());

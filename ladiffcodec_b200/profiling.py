@@ -5,7 +5,8 @@ from . import _lib
 
 
 def enable(model, on=True):
-    _lib.check(model._lib.ladiff_set_profiling(model._h, 1 if on else 0), "set_profiling")
+    """on: False/0 off, True/1 events around the tcgen05 conv launches, 2 events around every op of a UNet evaluation."""
+    _lib.check(model._lib.ladiff_set_profiling(model._h, int(on)), "set_profiling")
 
 
 def report(model):
@@ -19,7 +20,7 @@ def report(model):
 
 def dump(model):
     """Per-launch table [(ms, gflop, label)] of the most recent profiled UNet evaluation."""
-    buf = ctypes.create_string_buffer(1 << 16)
+    buf = ctypes.create_string_buffer(1 << 17)
     if model._lib.ladiff_profile_dump(model._h, buf, len(buf)) != 0:
         return []
     rows = []
