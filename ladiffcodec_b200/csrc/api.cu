@@ -23,6 +23,10 @@ void ladiff_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 extern "C" const char* ladiff_last_error(void) { return g_err; }
+bool ladiff_pdl_enabled() {
+  static const bool on = getenv("LADIFF_NO_PDL") == nullptr;
+  return on;
+}
 extern "C" int32_t ladiff_abi_version(void) { return 1; }
 
 #define TRY(expr)              \

@@ -5,6 +5,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
+
+#include <utility>
 
 #include "../../include/ladiff_b200.h"
 
@@ -31,6 +34,29 @@ void ladiff_set_error(const char* fmt, ...);
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// Kernels of the UNet step are launched with programmatic stream serialization: kernel N+1 may start (block scheduling,
+// barrier init, TMEM allocation, descriptor prefetch) while kernel N drains.  Every such kernel executes pdl_wait()
+// before it touches global memory another kernel may have written or may still read, and pdl_trigger() as soon as its
+// dependents may begin launching.  LADIFF_NO_PDL=1 falls back to plain stream order.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+bool ladiff_pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ladiff_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ------------------------------------------------------------------ tcgen05 implicit-GEMM conv (tc_conv.cu)
 // out[b, l, m] = bias[m] + sum over groups g, taps t of g, channels c < 64*nchunk_g:
@@ -118,6 +144,7 @@ struct TcConvParams {
   long long res_bstride;
   int res_pitch;
   unsigned long long* prof;   // debug (LADIFF_TC_PROF): per-CTA wait-cycle counters [grid][8]
+  int dbg;                    // debug (LADIFF_TC_DBG, only with LADIFF_TC_PROF): ablation bits, see tc_conv_launch
 };
 
 // X view description used by the SIMT check kernel (same math, no tensor maps, no tensor cores)

@@ -164,33 +164,48 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel's tail
+  pdl_wait();
+  pdl_trigger();
 
+  // The producer and the MMA issuer are single threads: every instruction of their loops is latency-exposed, so the
+  // taps a tile uses are resolved into registers once per (tile, group) and the per-chunk loops touch no parameter memory.
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer: one pipeline stage per (group, 64-channel chunk) = activation tile + its taps' weight tiles
       const uint32_t b_bytes = (uint32_t)(p.NCLIP * p.BOXROWS) * 128u;
-      int st = 0; uint32_t ph = 0;
+      const uint32_t box_bytes = (uint32_t)p.BOXROWS * 128u;
+      const int nclip = p.NCLIP, S = p.S;
+      const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
+      int st = 0, issued = 0; uint32_t ph = 0;
       long long w_empty = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const TileCoord tc = decode_tile(p, t);
         for (int g = 0; g < p.ngrp; ++g) {
           const TcGroup& gr = p.grp[g];
-          uint32_t n_a = 0;
-          for (int tp = 0; tp < gr.ntaps; ++tp) n_a += (tc.m0 >= gr.tap[tp].m_lo && tc.m0 < gr.tap[tp].m_hi) ? 1u : 0u;
-          for (int c = 0; c < gr.nchunk; ++c) {
+          int n_a = 0, k0 = 0, k1 = 0, k2 = 0;
+          for (int tp = 0; tp < gr.ntaps; ++tp) {
+            const TcTap tap = gr.tap[tp];
+            if (tc.m0 < tap.m_lo || tc.m0 >= tap.m_hi) continue;
+            if (n_a == 0) k0 = tap.kofs; else if (n_a == 1) k1 = tap.kofs; else k2 = tap.kofs;
+            ++n_a;
+          }
+          const int nchunk = gr.nchunk, ch0 = gr.ch0, row = tc.l0 + gr.shift;
+          const uint32_t tx_bytes = b_bytes + (uint32_t)n_a * A_BYTES;
+          for (int c = 0; c < nchunk; ++c) {
             mbar_wait_t(&empty_bar[st], ph ^ 1, w_empty, prof);
-            mbar_expect_tx(&full_bar[st], b_bytes + n_a * A_BYTES);
-            const uint32_t a_dst = smem_base + (uint32_t)st * (uint32_t)p.stage_bytes;
-            for (int j = 0; j < p.NCLIP; ++j)
-              tma_load_3d(a_dst + b_off + (uint32_t)(j * p.BOXROWS) * 128u, &p.tmX, &full_bar[st], gr.ch0 + c * TC_BK, tc.l0 + gr.shift, tc.b0 + j);
-            uint32_t idx = 0;
-            for (int tp = 0; tp < gr.ntaps; ++tp) {
-              const TcTap& tap = gr.tap[tp];
-              if (tc.m0 < tap.m_lo || tc.m0 >= tap.m_hi) continue;
-              tma_load_2d(a_dst + idx * A_BYTES, &p.tmW, &full_bar[st], tap.kofs + c * TC_BK, tc.m0);
-              ++idx;
-            }
-            if (++st == p.S) { st = 0; ph ^= 1; }
+            if ((p.dbg & 1) && issued >= S) { mbar_arrive(&full_bar[st]); if (++st == S) { st = 0; ph ^= 1; } continue; }
+            ++issued;
+            uint64_t* fb = &full_bar[st];
+            mbar_expect_tx(fb, tx_bytes);
+            const uint32_t a_dst = smem_base + (uint32_t)st * stage_bytes;
+            const int kc = c * TC_BK;
+            tma_load_3d(a_dst + b_off, &p.tmX, fb, ch0 + kc, row, tc.b0);
+            for (int j = 1; j < nclip; ++j) tma_load_3d(a_dst + b_off + (uint32_t)j * box_bytes, &p.tmX, fb, ch0 + kc, row, tc.b0 + j);
+            if (n_a > 0) tma_load_2d(a_dst, &p.tmW, fb, k0 + kc, tc.m0);
+            if (n_a > 1) tma_load_2d(a_dst + A_BYTES, &p.tmW, fb, k1 + kc, tc.m0);
+            if (n_a > 2) tma_load_2d(a_dst + 2 * A_BYTES, &p.tmW, fb, k2 + kc, tc.m0);
+            if (++st == S) { st = 0; ph ^= 1; }
           }
         }
       }
@@ -202,6 +217,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
       // ---------------- MMA issuer.  Instruction descriptor (InstrDescriptor, mma_sm100_desc.hpp):
       // c_format F32 (1<<4) | a_format BF16 (1<<7) | b_format BF16 (1<<10) | K-major A,B | N>>3 <<17 | M>>4 <<24
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NMMA >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const int S = p.S;
+      const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
+      const bool no_mma = (p.dbg & 4) != 0;
       int st = 0, tl = 0; uint32_t ph = 0;
       long long w_full = 0, w_tmem = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
@@ -213,25 +231,38 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
         uint32_t accumulate = 0;
         for (int g = 0; g < p.ngrp; ++g) {
           const TcGroup& gr = p.grp[g];
-          for (int c = 0; c < gr.nchunk; ++c) {
+          int n_a = 0;
+          uint32_t r0 = 0, r1 = 0, r2 = 0;       // per tap: row offset in 16-byte descriptor units (128 B per row)
+          for (int tp = 0; tp < gr.ntaps; ++tp) {
+            const TcTap tap = gr.tap[tp];
+            if (tc.m0 < tap.m_lo || tc.m0 >= tap.m_hi) continue;
+            const uint32_t ro = (uint32_t)tap.row_off * 8u;
+            if (n_a == 0) r0 = ro; else if (n_a == 1) r1 = ro; else r2 = ro;
+            ++n_a;
+          }
+          const int nchunk = gr.nchunk;
+          for (int c = 0; c < nchunk; ++c) {
             mbar_wait_t(&full_bar[st], ph, w_full, prof);
             tc_fence_after();
-            const uint32_t a_base = smem_base + (uint32_t)st * (uint32_t)p.stage_bytes;
-            uint64_t adesc = umma_desc(a_base);
-            const uint64_t bdesc0 = umma_desc(a_base + b_off);
-            for (int tp = 0; tp < gr.ntaps; ++tp) {
-              const TcTap& tap = gr.tap[tp];
-              if (tc.m0 < tap.m_lo || tc.m0 >= tap.m_hi) continue;
-              const uint64_t bdesc = bdesc0 + (uint64_t)(tap.row_off * 8);    // +128 B per row, in 16-byte units
+            const uint32_t a_base = smem_base + (uint32_t)st * stage_bytes;
+            const uint64_t adesc = umma_desc(a_base);
+            const uint64_t bdesc = umma_desc(a_base + b_off);
+            if (!no_mma) {
+              if (n_a > 0) {
 #pragma unroll
-              for (int k = 0; k < TC_BK / 16; ++k) {
-                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);   // +32 B per K=16 step
-                accumulate = 1;
+                for (int k = 0; k < TC_BK / 16; ++k) { umma_bf16(d_tmem, adesc + 2 * k, bdesc + r0 + 2 * k, idesc, accumulate); accumulate = 1; }
               }
-              adesc += A_BYTES >> 4;
+              if (n_a > 1) {
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k) umma_bf16(d_tmem, adesc + (A_BYTES >> 4) + 2 * k, bdesc + r1 + 2 * k, idesc, 1u);
+              }
+              if (n_a > 2) {
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k) umma_bf16(d_tmem, adesc + 2 * (A_BYTES >> 4) + 2 * k, bdesc + r2 + 2 * k, idesc, 1u);
+              }
             }
             tc_commit(&empty_bar[st]);     // frees the stage once these MMAs have read it
-            if (++st == p.S) { st = 0; ph ^= 1; }
+            if (++st == S) { st = 0; ph ^= 1; }
           }
         }
         tc_commit(&tmem_full[acc]);        // accumulator complete
@@ -262,7 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
         if (b >= p.B) vr = 0;
         float s1 = 0.f, s2 = 0.f;
         for (int r0 = 0; r0 < p.NT; r0 += p.CR) {
-          if (vr <= r0) break;                   // uniform over the 128 epilogue threads
+          if (vr <= r0 || (p.dbg & 2)) break;    // uniform over the 128 epilogue threads
           const int nrows = (p.NT - r0) < p.CR ? (p.NT - r0) : p.CR;
           uint32_t stg = 0;
           if (!p.direct) {
@@ -470,6 +501,11 @@ static void pick_tiling(int Lout, int B, int MT, int halo2, int* NT, int* NCLIP,
     }
     return;
   }
+  static const int force_nt = getenv("LADIFF_TC_NT") ? atoi(getenv("LADIFF_TC_NT")) : 0;   // experiment knob
+  if (force_nt >= 64 && force_nt <= maxn && force_nt % 16 == 0) {
+    *NT = force_nt; *NCLIP = 1; *n_ptiles = cdiv(Lout, force_nt);
+    return;
+  }
   for (int nt = maxn; nt >= 64; nt -= 16) {
     const int np = cdiv(Lout, nt);
     const long tiles = (long)MT * B * np;
@@ -629,11 +665,11 @@ int tc_conv_launch(const TcConvParams& p, cudaStream_t st) {
   const int grid = tiles < nsm ? tiles : nsm;
   static const bool want_prof = getenv("LADIFF_TC_PROF") != nullptr;   // debug aid: per-role mbarrier wait cycles, printed per launch
   if (!want_prof) {
-    tc_conv_kernel<<<grid, kThreads, smem, st>>>(p);
-    LADIFF_CUDA_OK(cudaGetLastError());
+    LADIFF_CUDA_OK(launch_pdl(tc_conv_kernel, dim3(grid), dim3(kThreads), smem, st, p));
     return 0;
   }
   TcConvParams q = p;
+  q.dbg = getenv("LADIFF_TC_DBG") ? atoi(getenv("LADIFF_TC_DBG")) : 0;   // 1: no TMA after ring fill, 2: no epilogue, 4: no MMA
   unsigned long long* dprof = nullptr;
   LADIFF_CUDA_OK(cudaMalloc((void**)&dprof, sizeof(unsigned long long) * 8 * grid));
   LADIFF_CUDA_OK(cudaMemset(dprof, 0, sizeof(unsigned long long) * 8 * grid));
@@ -646,8 +682,8 @@ int tc_conv_launch(const TcConvParams& p, cudaStream_t st) {
   cudaFree(dprof);
   double a[5] = {0, 0, 0, 0, 0};
   for (int i = 0; i < grid; ++i) for (int k = 0; k < 5; ++k) a[k] += (double)hp[(size_t)i * 8 + k] / grid;
-  fprintf(stderr, "[tc_prof] Cout=%d N=%d(NT=%d x%d) S=%d a_cap=%d grid=%d tiles=%d | cycles/CTA: total %.0f  producer-wait-empty %.0f  mma-wait-full %.0f  "
-                  "mma-wait-tmem %.0f  epi-wait-acc %.0f\n", p.Cout, p.NMMA, p.NT, p.NCLIP, p.S, p.a_cap, grid, tiles, a[4], a[0], a[1], a[2], a[3]);
+  fprintf(stderr, "[tc_prof] dbg=%d Cout=%d N=%d(NT=%d x%d) S=%d a_cap=%d grid=%d tiles=%d | cycles/CTA: total %.0f  producer-wait-empty %.0f  mma-wait-full %.0f  "
+                  "mma-wait-tmem %.0f  epi-wait-acc %.0f\n", q.dbg, p.Cout, p.NMMA, p.NT, p.NCLIP, p.S, p.a_cap, grid, tiles, a[4], a[0], a[1], a[2], a[3]);
   return 0;
 }
 

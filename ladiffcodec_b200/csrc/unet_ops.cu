@@ -28,6 +28,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // (fixed lane assignment + xor-shuffle tree: deterministic); every thread then owns ONE 8-channel chunk for the whole
 // kernel, so its fused scale/shift (gamma * rstd * (film_scale + 1), ...) live in registers.
 __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a, int rows_per_cta) {
+  pdl_wait();
+  pdl_trigger();
   const int C = a.y.C, Cg = C / 8, spg = Cg / 32, nslots = C / 32, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __shared__ float s_mean[8], s_rstd[8];
@@ -102,6 +104,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a, int rows_p
 // ------------------------------------------------------------------ channel LayerNorm: one warp per row
 template <int NVEC>
 __global__ void __launch_bounds__(256) layernorm_cl_kernel(ClView x, const float* __restrict__ g, ClView res, ClView out, int L) {
+  pdl_wait();
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp, b = blockIdx.y;
   if (row >= L) return;
@@ -152,6 +156,8 @@ constexpr int LA_PART = 64 + 1024;   // floats per partial: m[32], z[32], ctx[32
 
 __global__ void __launch_bounds__(256) linattn_ctx_kernel(ClView qkv, float* __restrict__ ctx, float* part, int* counters, int L, int S,
                                                           int nsplit) {
+  pdl_wait();
+  pdl_trigger();
   const int sp = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   __shared__ __align__(16) float ks[LA_S][32];
@@ -243,6 +249,8 @@ __global__ void __launch_bounds__(256) linattn_ctx_kernel(ClView qkv, float* __r
 // out[b][n][h*32+e] = sum_d ctx[h][d][e] softmax_d(q[n,h,:])[d]      grid (ceil(L/64), B), 256 threads
 // warp w: head w&3, rows 32*(w>>2) + lane; one (row, head) per thread: q row in registers, ctx broadcast from smem
 __global__ void __launch_bounds__(256) linattn_out_kernel(ClView qkv, const float* __restrict__ ctx, ClView out, int L) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __shared__ __align__(16) float cs[4][32][32];
   {
@@ -296,6 +304,8 @@ __global__ void __launch_bounds__(256) linattn_out_kernel(ClView qkv, const floa
 // ------------------------------------------------------------------ full attention (mid block), online softmax
 // grid (ceil(n/32), 4, B), 256 threads: each warp owns 4 queries; keys/values staged in smem tiles of 128
 __global__ void __launch_bounds__(256) fullattn_kernel(ClView qkv, ClView out, int L) {
+  pdl_wait();
+  pdl_trigger();
   const int h = blockIdx.y, b = blockIdx.z, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int KT = 128;
   __shared__ float ks[KT][33];
@@ -512,18 +522,17 @@ int gn_apply_launch(const GnApplyArgs& a, int B, cudaStream_t st) {
   int rows = cdiv(a.L * B, 4 * 148);                     // ~4 CTAs per SM
   rows = cdiv(rows < rstep ? rstep : rows, rstep) * rstep;
   dim3 grid(cdiv(a.L, rows), B);
-  gn_apply_kernel<<<grid, 256, 0, st>>>(a, rows);
-  LADIFF_CUDA_OK(cudaGetLastError());
+  LADIFF_CUDA_OK(launch_pdl(gn_apply_kernel, grid, dim3(256), 0, st, a, rows));
   return 0;
 }
 
 int layernorm_cl_launch(ClView x, const float* g, ClView res, ClView out, int B, int L, cudaStream_t st) {
   dim3 grid(cdiv(L, 8), B);
   switch (x.C) {
-    case 256: layernorm_cl_kernel<1><<<grid, 256, 0, st>>>(x, g, res, out, L); break;
-    case 512: layernorm_cl_kernel<2><<<grid, 256, 0, st>>>(x, g, res, out, L); break;
-    case 768: layernorm_cl_kernel<3><<<grid, 256, 0, st>>>(x, g, res, out, L); break;
-    case 1024: layernorm_cl_kernel<4><<<grid, 256, 0, st>>>(x, g, res, out, L); break;
+    case 256: LADIFF_CUDA_OK(launch_pdl(layernorm_cl_kernel<1>, grid, dim3(256), 0, st, x, g, res, out, L)); break;
+    case 512: LADIFF_CUDA_OK(launch_pdl(layernorm_cl_kernel<2>, grid, dim3(256), 0, st, x, g, res, out, L)); break;
+    case 768: LADIFF_CUDA_OK(launch_pdl(layernorm_cl_kernel<3>, grid, dim3(256), 0, st, x, g, res, out, L)); break;
+    case 1024: LADIFF_CUDA_OK(launch_pdl(layernorm_cl_kernel<4>, grid, dim3(256), 0, st, x, g, res, out, L)); break;
     default: LADIFF_REQUIRE(false, LADIFF_ERR_ARG, "layernorm_cl: unsupported C=%d", x.C);
   }
   LADIFF_CUDA_OK(cudaGetLastError());
@@ -546,16 +555,13 @@ size_t linattn_part_floats(int B, int L) {
 int linattn_launch(ClView qkv, float* ctx, float* part, int* counters, ClView out, int B, int L, cudaStream_t st) {
   int S, ns;
   linattn_split(B, L, &S, &ns);
-  linattn_ctx_kernel<<<dim3(ns, 4, B), 256, 0, st>>>(qkv, ctx, part, counters, L, S, ns);
-  LADIFF_CUDA_OK(cudaGetLastError());
-  linattn_out_kernel<<<dim3(cdiv(L, 64), B), 256, 0, st>>>(qkv, ctx, out, L);
-  LADIFF_CUDA_OK(cudaGetLastError());
+  LADIFF_CUDA_OK(launch_pdl(linattn_ctx_kernel, dim3(ns, 4, B), dim3(256), 0, st, qkv, ctx, part, counters, L, S, ns));
+  LADIFF_CUDA_OK(launch_pdl(linattn_out_kernel, dim3(cdiv(L, 64), B), dim3(256), 0, st, qkv, (const float*)ctx, out, L));
   return 0;
 }
 
 int fullattn_launch(ClView qkv, ClView out, int B, int L, cudaStream_t st) {
-  fullattn_kernel<<<dim3(cdiv(L, 32), 4, B), 256, 0, st>>>(qkv, out, L);
-  LADIFF_CUDA_OK(cudaGetLastError());
+  LADIFF_CUDA_OK(launch_pdl(fullattn_kernel, dim3(cdiv(L, 32), 4, B), dim3(256), 0, st, qkv, out, L));
   return 0;
 }
 

@@ -67,15 +67,17 @@ def stage_conv_prof(res):
     from ladiffcodec_b200 import _lib
     lib = _lib.get_lib()
     P = ctypes.c_void_p
-    shapes = [(32, 1200, 256, 256, 3), (32, 1200, 512, 256, 3), (32, 600, 768, 512, 3), (32, 300, 512, 512, 3), (32, 150, 1024, 1024, 3),
-              (32, 75, 1024, 1024, 3), (32, 75, 2048, 1024, 3), (32, 1200, 256, 384, 1), (32, 75, 1024, 384, 1), (32, 1200, 256, 256, 7)]
+    shapes = [(32, 1200, 256, 256, 3), (32, 600, 768, 512, 3), (32, 75, 1024, 1024, 3), (32, 1200, 256, 384, 1)]
+    if os.environ.get("LADIFF_PROF_ALL"):
+        shapes += [(32, 1200, 512, 256, 3), (32, 300, 512, 512, 3), (32, 150, 1024, 1024, 3), (32, 75, 2048, 1024, 3), (32, 75, 1024, 384, 1),
+                   (32, 1200, 256, 256, 7)]
     for (B, L, Cin, Cout, k) in shapes:
         g = torch.Generator().manual_seed(1)
         x = torch.randn(B, L, Cin, generator=g).to(torch.bfloat16).cuda()
         w = (torch.randn(Cout, Cin, k, generator=g) * (Cin * k) ** -0.5).cuda()
         bias = torch.zeros(Cout).cuda()
         y = torch.empty(B, L, Cout, device="cuda", dtype=torch.bfloat16)
-        for impl in (0, 2):
+        for impl in (0,):
             rc = lib.ladiff_op_conv1d_cl(P(x.data_ptr()), P(w.data_ptr()), P(bias.data_ptr()), B, L, Cin, Cout, k, P(y.data_ptr()), 0, impl, None)
             torch.cuda.synchronize()
             print(f"conv_prof B{B} L{L} Cin{Cin} Cout{Cout} k{k} impl{impl} rc={rc} gflop={2e-9 * B * L * Cin * Cout * k:.2f}", flush=True)
