@@ -45,6 +45,18 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
 bool ladiff_pdl_enabled();
+// Every kernel of the step keeps the SM's shared-memory carve-out at its maximum, the configuration the conv kernel needs:
+// a kernel that prefers a different L1/shared split cannot become resident next to a running conv CTA and forces an SM
+// reconfiguration at every kernel boundary of the ~170-kernel step.
+template <typename... KArgs>
+static inline void prefer_max_smem_carveout(void (*kernel)(KArgs...)) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+#define LADIFF_CARVEOUT_ONCE(kernel)                                             \
+  do {                                                                           \
+    static bool _done = false;                                                   \
+    if (!_done) { prefer_max_smem_carveout(kernel); _done = true; }              \
+  } while (0)
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg;

@@ -36,6 +36,14 @@ constexpr size_t kSmemLimit = 232448 - 1024;     // 227 KB minus the static barr
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a converged warp.  The compiler knows an elect.sync region is single-threaded and emits the uniform-datapath
+// instructions (UTCHMMA / UTMALDG / UTMASTG) directly; under `lane == 0` it wraps each of them in an ELECT + BRA.U.ANY
+// waterfall loop that costs ~50 cycles per instruction on the latency-exposed single issuing thread.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -171,7 +179,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
   // The producer and the MMA issuer are single threads: every instruction of their loops is latency-exposed, so the
   // taps a tile uses are resolved into registers once per (tile, group) and the per-chunk loops touch no parameter memory.
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---------------- TMA producer: one pipeline stage per (group, 64-channel chunk) = activation tile + its taps' weight tiles
       const uint32_t b_bytes = (uint32_t)(p.NCLIP * p.BOXROWS) * 128u;
       const uint32_t box_bytes = (uint32_t)p.BOXROWS * 128u;
@@ -213,7 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---------------- MMA issuer.  Instruction descriptor (InstrDescriptor, mma_sm100_desc.hpp):
       // c_format F32 (1<<4) | a_format BF16 (1<<7) | b_format BF16 (1<<10) | K-major A,B | N>>3 <<17 | M>>4 <<24
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NMMA >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
@@ -273,7 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
   } else {
     // ---------------- epilogue warps (warp w owns TMEM lanes 32*(w&3) .. +31)
     const int q = warp & 3;
-    const bool issuer = threadIdx.x == 64;
+    const bool store_warp = warp == 2;   // its elected lane issues the TMA stores; bulk-group waits are executed warp-wide
     const int Cc = p.up_cout ? p.up_cout : (p.split_m ? p.split_m : p.Cout);
     int tl = 0, cc = 0;
     long long w_acc = 0;
@@ -297,7 +305,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
           const int nrows = (p.NT - r0) < p.CR ? (p.NT - r0) : p.CR;
           uint32_t stg = 0;
           if (!p.direct) {
-            if (issuer) bulk_wait_read_1();      // the store issued two chunks ago has finished reading its buffer
+            if (store_warp) bulk_wait_read_1();  // the store issued two chunks ago has finished reading its buffer
             epi_bar();
             stg = stage0 + (uint32_t)(cc & 1) * (uint32_t)p.CR * 256u + (uint32_t)(q * 32 + lane) * 2u;
           }
@@ -331,7 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
           if (!p.direct) {
             fence_async_smem();
             epi_bar();
-            if (issuer) {
+            if (store_warp && elect_one()) {
               const uint32_t src = stage0 + (uint32_t)(cc & 1) * (uint32_t)p.CR * 256u;
               if (second) tma_store_4d(nrows == p.CR ? &p.tmY2 : &p.tmY2r, src, tc.m0 - p.split_m, 0, tc.l0 + r0, b);
               else tma_store_4d(nrows == p.CR ? &p.tmY : &p.tmYr, src, tc.m0 % Cc, tc.m0 / Cc, tc.l0 + r0, b);
@@ -354,8 +362,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);   // 4 warps -> accumulator stage free for the MMA issuer
     }
-    if (issuer) bulk_wait_all();
-    if (prof && issuer) { p.prof[blockIdx.x * 8 + 3] = (unsigned long long)w_acc; p.prof[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - t_begin); }
+    if (store_warp) bulk_wait_all();
+    if (prof && threadIdx.x == 64) { p.prof[blockIdx.x * 8 + 3] = (unsigned long long)w_acc; p.prof[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - t_begin); }
   }
   tc_fence_before();
   __syncthreads();

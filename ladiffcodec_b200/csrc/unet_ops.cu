@@ -5,7 +5,7 @@
 
 namespace {
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -24,22 +24,62 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // ------------------------------------------------------------------ GroupNorm apply
-// grid (ceil(L / rows_per_cta), B), 256 threads.  Prologue: warp g reduces the conv epilogue's partial sums of group g
-// (fixed lane assignment + xor-shuffle tree: deterministic); every thread then owns ONE 8-channel chunk for the whole
-// kernel, so its fused scale/shift (gamma * rstd * (film_scale + 1), ...) live in registers.
+// grid (ceil(L / rows_per_cta), B), 256 threads; every thread owns ONE 8-channel chunk for the whole kernel, so its fused
+// scale/shift (gamma * rstd * (film_scale + 1), ...) live in registers.  The kernel is latency-bound, so its dependent load
+// chains are flattened: the parameters (gamma, beta, FiLM row of step t: written long before the previous kernel) are
+// fetched BEFORE the programmatic-dependency wait, i.e. while the producing conv is still draining; after the wait the
+// first batch of rows and the GroupNorm partials are requested together.  Warp g reduces the conv epilogue's partial sums
+// of group g (fixed lane assignment + xor-shuffle tree: deterministic).
+constexpr int GN_U = 4;   // rows per thread per batch (all loads of a batch in flight at once)
+
 __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a, int rows_per_cta) {
-  pdl_wait();
-  pdl_trigger();
   const int C = a.y.C, Cg = C / 8, spg = Cg / 32, nslots = C / 32, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cv = C / 8;                       // 8-channel chunks per row: 32, 64 or 128
+  const int c0 = (threadIdx.x % cv) * 8, rsub = threadIdx.x / cv, rstep = 256 / cv;
   __shared__ float s_mean[8], s_rstd[8];
+  float ga[8], be[8], fsc[8], fsh[8];
+  {
+    const float4* g4 = reinterpret_cast<const float4*>(a.gamma + c0);
+    const float4* b4 = reinterpret_cast<const float4*>(a.beta + c0);
+    const float4 g0 = __ldg(g4), g1 = __ldg(g4 + 1), b0 = __ldg(b4), b1 = __ldg(b4 + 1);
+    ga[0] = g0.x; ga[1] = g0.y; ga[2] = g0.z; ga[3] = g0.w; ga[4] = g1.x; ga[5] = g1.y; ga[6] = g1.z; ga[7] = g1.w;
+    be[0] = b0.x; be[1] = b0.y; be[2] = b0.z; be[3] = b0.w; be[4] = b1.x; be[5] = b1.y; be[6] = b1.z; be[7] = b1.w;
+    if (a.film) {
+      const float* film = a.film + (long long)a.t_dev[b] * a.film_stride + c0;
+      const float4 s0 = __ldg(reinterpret_cast<const float4*>(film)), s1 = __ldg(reinterpret_cast<const float4*>(film) + 1);
+      const float4 h0 = __ldg(reinterpret_cast<const float4*>(film + C)), h1 = __ldg(reinterpret_cast<const float4*>(film + C) + 1);
+      fsc[0] = s0.x; fsc[1] = s0.y; fsc[2] = s0.z; fsc[3] = s0.w; fsc[4] = s1.x; fsc[5] = s1.y; fsc[6] = s1.z; fsc[7] = s1.w;
+      fsh[0] = h0.x; fsh[1] = h0.y; fsh[2] = h0.z; fsh[3] = h0.w; fsh[4] = h1.x; fsh[5] = h1.y; fsh[6] = h1.z; fsh[7] = h1.w;
+    }
+  }
+  const int r0 = blockIdx.x * rows_per_cta;
+  const int r1 = min(r0 + rows_per_cta, a.L);
+  const bf16* yb = a.y.p + (long long)b * a.y.bstride + c0;
+  const bf16* rb = a.res.p ? a.res.p + (long long)b * a.res.bstride + c0 : nullptr;
+  bf16* ob = a.out.p + (long long)b * a.out.bstride + c0;
+  pdl_wait();
+  pdl_trigger();
+  uint4 u[GN_U], ur[GN_U];
+  int row = r0 + rsub;
+  auto load_batch = [&](int rw) {
+#pragma unroll
+    for (int k = 0; k < GN_U; ++k) {
+      const int r = rw + k * rstep;
+      if (r < r1) {
+        u[k] = __ldcg(reinterpret_cast<const uint4*>(yb + (long long)r * a.y.pitch));
+        if (rb) ur[k] = __ldcg(reinterpret_cast<const uint4*>(rb + (long long)r * a.res.pitch));
+      }
+    }
+  };
+  load_batch(row);
   {
     float s1 = 0.f, s2 = 0.f;
     const int n = a.n_ntiles * spg;
     const float2* base = a.stats + (long long)b * a.n_ntiles * nslots + warp * spg;
     for (int i = lane; i < n; i += 32) {
       const int pt = i / spg, s = i - pt * spg;
-      const float2 v = base[pt * nslots + s];
+      const float2 v = __ldcg(base + pt * nslots + s);
       s1 += v.x; s2 += v.y;
     }
 #pragma unroll
@@ -57,92 +97,116 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a, int rows_p
     }
   }
   __syncthreads();
-  const int cv = C / 8;                       // 8-channel chunks per row: 32, 64 or 128
-  const int c0 = (threadIdx.x % cv) * 8, rsub = threadIdx.x / cv, rstep = 256 / cv;
   float sa[8], sb[8];
   {
-    const float* film = a.film ? a.film + (long long)a.t_dev[b] * a.film_stride : nullptr;
     const float mean = s_mean[c0 / Cg], rstd = s_rstd[c0 / Cg];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float ga = a.gamma[c0 + j] * rstd;
-      float be = a.beta[c0 + j] - mean * ga;
-      if (film) {
-        const float sc = film[c0 + j] + 1.f, sh = film[C + c0 + j];
-        ga *= sc;
-        be = be * sc + sh;
+      float g = ga[j] * rstd;
+      float bb = be[j] - mean * g;
+      if (a.film) {
+        const float sc = fsc[j] + 1.f;
+        g *= sc;
+        bb = bb * sc + fsh[j];
       }
-      sa[j] = ga; sb[j] = be;
+      sa[j] = g; sb[j] = bb;
     }
   }
-  const int r0 = blockIdx.x * rows_per_cta;
-  const int r1 = min(r0 + rows_per_cta, a.L);
-  const bf16* yb = a.y.p + (long long)b * a.y.bstride + c0;
-  const bf16* rb = a.res.p ? a.res.p + (long long)b * a.res.bstride + c0 : nullptr;
-  bf16* ob = a.out.p + (long long)b * a.out.bstride + c0;
-  for (int row = r0 + rsub; row < r1; row += rstep) {
-    const uint4 u = *reinterpret_cast<const uint4*>(yb + (long long)row * a.y.pitch);
-    float f[8];
-    unpack8(u, f);
+  for (;;) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j] * sa[j] + sb[j]);
-    if (rb) {
-      const uint4 ur = *reinterpret_cast<const uint4*>(rb + (long long)row * a.res.pitch);
-      float r[8];
-      unpack8(ur, r);
+    for (int k = 0; k < GN_U; ++k) {
+      const int r = row + k * rstep;
+      if (r >= r1) break;
+      float f[8];
+      unpack8(u[k], f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] += r[j];
+      for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j] * sa[j] + sb[j]);
+      if (rb) {
+        float rr[8];
+        unpack8(ur[k], rr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += rr[j];
+      }
+      if (a.do_tanh) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = tanhf(f[j]);
+      }
+      *reinterpret_cast<uint4*>(ob + (long long)r * a.out.pitch) = pack8(f);
     }
-    if (a.do_tanh) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = tanhf(f[j]);
-    }
-    *reinterpret_cast<uint4*>(ob + (long long)row * a.out.pitch) = pack8(f);
+    row += GN_U * rstep;
+    if (row >= r1) break;
+    load_batch(row);
   }
 }
 
-// ------------------------------------------------------------------ channel LayerNorm: one warp per row
+// ------------------------------------------------------------------ channel LayerNorm: each warp normalises LN_R rows at once
+// (all of their loads are issued before the first reduction: the kernel is latency-bound, not bandwidth-bound)
 template <int NVEC>
 __global__ void __launch_bounds__(256) layernorm_cl_kernel(ClView x, const float* __restrict__ g, ClView res, ClView out, int L) {
-  pdl_wait();
-  pdl_trigger();
+  constexpr int LN_R = NVEC >= 4 ? 1 : (NVEC >= 2 ? 2 : 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + warp, b = blockIdx.y;
-  if (row >= L) return;
-  const int C = NVEC * 256;
-  const bf16* xr = x.p + (long long)b * x.bstride + (long long)row * x.pitch;
-  float v[NVEC][8];
-  float s = 0.f;
+  const int row0 = (blockIdx.x * 8 + warp) * LN_R, b = blockIdx.y;
+  constexpr int C = NVEC * 256;
+  float gg[NVEC][8];
 #pragma unroll
   for (int i = 0; i < NVEC; ++i) {
-    unpack8(*reinterpret_cast<const uint4*>(xr + (lane + 32 * i) * 8), v[i]);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + (lane + 32 * i) * 8));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(g + (lane + 32 * i) * 8 + 4));
+    gg[i][0] = g0.x; gg[i][1] = g0.y; gg[i][2] = g0.z; gg[i][3] = g0.w;
+    gg[i][4] = g1.x; gg[i][5] = g1.y; gg[i][6] = g1.z; gg[i][7] = g1.w;
+  }
+  pdl_wait();       // the gains above are parameters: fetched while the producing kernel drains
+  pdl_trigger();
+  if (row0 >= L) return;
+  uint4 raw[LN_R][NVEC], rres[LN_R][NVEC];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s += v[i][j];
+  for (int r = 0; r < LN_R; ++r) {
+    if (row0 + r >= L) break;
+    const bf16* xr = x.p + (long long)b * x.bstride + (long long)(row0 + r) * x.pitch;
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) raw[r][i] = __ldcg(reinterpret_cast<const uint4*>(xr + (lane + 32 * i) * 8));
+    if (res.p) {
+      const bf16* rr = res.p + (long long)b * res.bstride + (long long)(row0 + r) * res.pitch;
+#pragma unroll
+      for (int i = 0; i < NVEC; ++i) rres[r][i] = __ldcg(reinterpret_cast<const uint4*>(rr + (lane + 32 * i) * 8));
+    }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / (float)C;
-  float q = 0.f;
+  for (int r = 0; r < LN_R; ++r) {
+    if (row0 + r >= L) break;
+    float v[NVEC][8];
+    float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < NVEC; ++i)
+    for (int i = 0; i < NVEC; ++i) {
+      unpack8(raw[r][i], v[i]);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; q += d * d; }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q / (float)C + 1e-5f);
-#pragma unroll
-  for (int i = 0; i < NVEC; ++i) {
-    const int c0 = (lane + 32 * i) * 8;
-    float f[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = (v[i][j] - mean) * rstd * g[c0 + j];
-    if (res.p) {
-      float r[8];
-      unpack8(*reinterpret_cast<const uint4*>(res.p + (long long)b * res.bstride + (long long)row * res.pitch + c0), r);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] += r[j];
+      for (int j = 0; j < 8; ++j) s += v[i][j];
     }
-    *reinterpret_cast<uint4*>(out.p + (long long)b * out.bstride + (long long)row * out.pitch + c0) = pack8(f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; q += d * d; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / (float)C + 1e-5f);
+    bf16* orow = out.p + (long long)b * out.bstride + (long long)(row0 + r) * out.pitch;
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = (v[i][j] - mean) * rstd * gg[i][j];
+      if (res.p) {
+        float rr[8];
+        unpack8(rres[r][i], rr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += rr[j];
+      }
+      *reinterpret_cast<uint4*>(orow + (lane + 32 * i) * 8) = pack8(f);
+    }
   }
 }
 
@@ -519,20 +583,22 @@ int gn_apply_launch(const GnApplyArgs& a, int B, cudaStream_t st) {
   const int C = a.y.C;
   LADIFF_REQUIRE(C == 256 || C == 512 || C == 1024, LADIFF_ERR_ARG, "gn_apply: C=%d", C);
   const int rstep = 256 / (C / 8);
-  int rows = cdiv(a.L * B, 4 * 148);                     // ~4 CTAs per SM
+  int rows = cdiv(a.L * B, 3 * 148);                     // one wave of ~3 CTAs per SM, resident before the producer ends (PDL)
   rows = cdiv(rows < rstep ? rstep : rows, rstep) * rstep;
   dim3 grid(cdiv(a.L, rows), B);
+  LADIFF_CARVEOUT_ONCE(gn_apply_kernel);
   LADIFF_CUDA_OK(launch_pdl(gn_apply_kernel, grid, dim3(256), 0, st, a, rows));
   return 0;
 }
 
 int layernorm_cl_launch(ClView x, const float* g, ClView res, ClView out, int B, int L, cudaStream_t st) {
-  dim3 grid(cdiv(L, 8), B);
+  const int nvec = x.C / 256, ln_r = nvec >= 4 ? 1 : (nvec >= 2 ? 2 : 4);   // rows per warp, as in the kernel
+  dim3 grid(cdiv(L, 8 * ln_r), B);
   switch (x.C) {
-    case 256: LADIFF_CUDA_OK(launch_pdl(layernorm_cl_kernel<1>, grid, dim3(256), 0, st, x, g, res, out, L)); break;
-    case 512: LADIFF_CUDA_OK(launch_pdl(layernorm_cl_kernel<2>, grid, dim3(256), 0, st, x, g, res, out, L)); break;
-    case 768: LADIFF_CUDA_OK(launch_pdl(layernorm_cl_kernel<3>, grid, dim3(256), 0, st, x, g, res, out, L)); break;
-    case 1024: LADIFF_CUDA_OK(launch_pdl(layernorm_cl_kernel<4>, grid, dim3(256), 0, st, x, g, res, out, L)); break;
+    case 256: LADIFF_CARVEOUT_ONCE(layernorm_cl_kernel<1>); LADIFF_CUDA_OK(launch_pdl(layernorm_cl_kernel<1>, grid, dim3(256), 0, st, x, g, res, out, L)); break;
+    case 512: LADIFF_CARVEOUT_ONCE(layernorm_cl_kernel<2>); LADIFF_CUDA_OK(launch_pdl(layernorm_cl_kernel<2>, grid, dim3(256), 0, st, x, g, res, out, L)); break;
+    case 768: LADIFF_CARVEOUT_ONCE(layernorm_cl_kernel<3>); LADIFF_CUDA_OK(launch_pdl(layernorm_cl_kernel<3>, grid, dim3(256), 0, st, x, g, res, out, L)); break;
+    case 1024: LADIFF_CARVEOUT_ONCE(layernorm_cl_kernel<4>); LADIFF_CUDA_OK(launch_pdl(layernorm_cl_kernel<4>, grid, dim3(256), 0, st, x, g, res, out, L)); break;
     default: LADIFF_REQUIRE(false, LADIFF_ERR_ARG, "layernorm_cl: unsupported C=%d", x.C);
   }
   LADIFF_CUDA_OK(cudaGetLastError());
@@ -555,12 +621,15 @@ size_t linattn_part_floats(int B, int L) {
 int linattn_launch(ClView qkv, float* ctx, float* part, int* counters, ClView out, int B, int L, cudaStream_t st) {
   int S, ns;
   linattn_split(B, L, &S, &ns);
+  LADIFF_CARVEOUT_ONCE(linattn_ctx_kernel);
+  LADIFF_CARVEOUT_ONCE(linattn_out_kernel);
   LADIFF_CUDA_OK(launch_pdl(linattn_ctx_kernel, dim3(ns, 4, B), dim3(256), 0, st, qkv, ctx, part, counters, L, S, ns));
   LADIFF_CUDA_OK(launch_pdl(linattn_out_kernel, dim3(cdiv(L, 64), B), dim3(256), 0, st, qkv, (const float*)ctx, out, L));
   return 0;
 }
 
 int fullattn_launch(ClView qkv, ClView out, int B, int L, cudaStream_t st) {
+  LADIFF_CARVEOUT_ONCE(fullattn_kernel);
   LADIFF_CUDA_OK(launch_pdl(fullattn_kernel, dim3(cdiv(L, 32), 4, B), dim3(256), 0, st, qkv, out, L));
   return 0;
 }
@@ -588,12 +657,14 @@ int absmax_inv_launch(const float* x, float* inv, int B, long long n, float eps,
 int ddpm_step_launch(const float* eps, float* x, const float* noise, unsigned long long seed, int step_index, const int* t_dev,
                      DdpmTables tb, ClView xin, int B, int C, int L, cudaStream_t st) {
   LADIFF_REQUIRE(C % 32 == 0, LADIFF_ERR_ARG, "ddpm_step: C=%d", C);
+  LADIFF_CARVEOUT_ONCE(ddpm_step_kernel);
   ddpm_step_kernel<<<dim3(cdiv(L, 32), C / 32, B), dim3(32, 8), 0, st>>>(eps, x, noise, seed, step_index, t_dev, tb, xin, C, L);
   LADIFF_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 int fill_t_launch(int* t_dev, int t, int B, cudaStream_t st) {
+  LADIFF_CARVEOUT_ONCE(fill_t_kernel);
   fill_t_kernel<<<cdiv(B, 128), 128, 0, st>>>(t_dev, t, B);
   LADIFF_CUDA_OK(cudaGetLastError());
   return 0;
