@@ -598,6 +598,9 @@ int run_lstm(H* h, const LstmW& lw, float*& x, int T, Pool& pool, float* hbuf, f
     if (lw.H == 64 || lw.H == 128) {
       TRY(lstm_seq_launch(pre, lw.whh[l], skip, y, B, lw.H, T, st));
       h->launches++;
+    } else if (lw.H % 32 == 0 && lw.H / 4 <= tc_num_sms() && lw.H <= 1024) {
+      TRY(lstm_persist_launch(pre, lw.whh[l], skip, y, hbuf, reinterpret_cast<unsigned int*>(cbuf), B, lw.H, T, st));
+      h->launches++;
     } else {
       TRY(lstm_steps_launch(pre, lw.whh[l], skip, y, hbuf, cbuf, B, lw.H, T, st, &h->launches));
     }
@@ -624,8 +627,8 @@ int setup_pool(H* h, Bump& bp, int B, int T, Pool& pool, float** hbuf, float** c
   const size_t n = codec_buf_elems(h, B, T);
   for (int i = 0; i < kPoolBufs; ++i) pool.put(bp.get<float>(n));
   const int Hmax = h->cfg.n_filters * (1 << h->cfg.n_enc_ratios);
-  *hbuf = bp.get<float>((size_t)2 * B * Hmax);
-  *cbuf = bp.get<float>((size_t)B * Hmax);
+  *hbuf = bp.get<float>(lstm_persist_scratch_floats(B, Hmax));   // >= 2*B*Hmax, the per-step fallback's need
+  *cbuf = bp.get<float>((size_t)B * Hmax + 64);
   return 0;
 }
 
@@ -702,7 +705,7 @@ void carve_unet(const H* h, Bump& bp, int B, int L, UnetBufs* u) {
   u->ctx = bp.get<float>((size_t)B * 4096);
   u->la_part = bp.get<float>(linattn_part_floats(B, L));
   u->la_cnt = bp.get<int>((size_t)4 * B);
-  u->stats_slots = (L / 16 + 2) * 32;
+  u->stats_slots = (L / 16 + 4) * 32 * TC_STAT_PARTS;
   u->stats = bp.get<float2>((size_t)B * u->stats_slots);
   u->t_dev = bp.get<int>(B);
   u->inv_scale = bp.get<float>(B);
@@ -716,6 +719,7 @@ ClView view(bf16* p, int L, int pitch, int C, int ch0 = 0) {
 
 struct PlanBuilder {
   H* h; Plan* pl; int B;
+  bool tune_stream_ok; cudaStream_t tune_stream; cudaEvent_t tune_ev[2];
   void label(const char* fmt, int a, int b, int c, int d) {
     char buf[120];
     snprintf(buf, sizeof(buf), fmt, a, b, c, d);
@@ -742,12 +746,48 @@ struct PlanBuilder {
     TcRefView rv;
     d.tap_share = 1;
     TRY(tc_conv_plan(d, &ps, &rv));
+    if (tune_stream_ok && h->conv_impl == 0) {
+      // Autotune the tile shape on the real buffers: wave quantisation over 148 SMs, operand traffic and epilogue cost all
+      // depend on it and none is monotonic in the tile width.  A candidate replaces the cost model's pick only if it is >3 %
+      // faster (keeps the choice stable against timing noise).  The conv's inputs hold arbitrary data here; its outputs are
+      // scratch that the real evaluation overwrites.
+      auto time_one = [&](const TcConvParams& cand, float* ms) -> int {
+        TRY(tc_conv_launch(cand, tune_stream));
+        LADIFF_CUDA_OK(cudaEventRecord(tune_ev[0], tune_stream));
+        for (int r = 0; r < 3; ++r) TRY(tc_conv_launch(cand, tune_stream));
+        LADIFF_CUDA_OK(cudaEventRecord(tune_ev[1], tune_stream));
+        LADIFF_CUDA_OK(cudaEventSynchronize(tune_ev[1]));
+        LADIFF_CUDA_OK(cudaEventElapsedTime(ms, tune_ev[0], tune_ev[1]));
+        return 0;
+      };
+      float best_ms = 0.f;
+      TRY(time_one(ps, &best_ms));
+      const float base_ms = best_ms;
+      TcConvParams best = ps;
+      TcRefView best_rv = rv;
+      const bool multi = ps.NCLIP > 1 || ps.Lout + 8 <= 120;
+      for (int c = 0; c < 12; ++c) {
+        TcConvDesc dc = d;
+        if (multi) { dc.want_nclip = c + 1; if (c >= 3) break; }
+        else { dc.want_nt = 256 - 16 * c; if (dc.want_nt < 96) break; }
+        TcConvParams pc2;
+        TcRefView rv2;
+        if (tc_conv_plan(dc, &pc2, &rv2) != 0) continue;                     // shape does not fit (smem, halo): skip
+        if (pc2.NT == ps.NT && pc2.NCLIP == ps.NCLIP) continue;
+        if (want_stats && pc2.n_ptiles * TC_STAT_PARTS * pc2.stat_slots > pl->bufs.stats_slots) continue;
+        float ms = 0.f;
+        TRY(time_one(pc2, &ms));
+        if (ms < best_ms && ms < 0.97f * base_ms) { best_ms = ms; best = pc2; best_rv = rv2; }
+      }
+      ps = best; rv = best_rv;
+    }
     d.tap_share = 0;
-    TRY(tc_conv_plan(d, &pu, nullptr));
+    d.want_nt = ps.NCLIP == 1 ? ps.NT : 0; d.want_nclip = ps.NCLIP > 1 ? ps.NCLIP : 0;
+    if (tc_conv_plan(d, &pu, nullptr) != 0) { d.want_nt = 0; d.want_nclip = 0; TRY(tc_conv_plan(d, &pu, nullptr)); }
     LADIFF_REQUIRE(ps.n_ptiles == pu.n_ptiles || !want_stats, LADIFF_ERR_ARG, "plan: tap-shared and per-tap tilings disagree");
     if (want_stats)
-      LADIFF_REQUIRE(ps.n_ptiles * ps.stat_slots <= pl->bufs.stats_slots, LADIFF_ERR_WORKSPACE, "plan: stats buffer too small");
-    if (n_ntiles) *n_ntiles = ps.n_ptiles;
+      LADIFF_REQUIRE(ps.n_ptiles * TC_STAT_PARTS * ps.stat_slots <= pl->bufs.stats_slots, LADIFF_ERR_WORKSPACE, "plan: stats buffer too small");
+    if (n_ntiles) *n_ntiles = ps.n_ptiles * TC_STAT_PARTS;
     H* hh = h;
     pl->ops.push_back([hh, ps, pu, rv](cudaStream_t st) {
       if (hh->conv_impl == 1) return tc_conv_ref_launch(ps, rv, st);
@@ -827,7 +867,7 @@ struct PlanBuilder {
   }
 };
 
-int build_plan(H* h, void* ws_unet, int B, int L, Plan** out) {
+int build_plan(H* h, void* ws_unet, int B, int L, cudaStream_t st, Plan** out) {
   for (Plan* p : h->plans)
     if (p->ws == ws_unet && p->B == B && p->L == L) { *out = p; return 0; }
   LADIFF_REQUIRE(L % 16 == 0 && L >= 16, LADIFF_ERR_ARG, "UNet needs a latent length that is a multiple of 16 (got %d)", L);
@@ -838,7 +878,14 @@ int build_plan(H* h, void* ws_unet, int B, int L, Plan** out) {
   UnetBufs& u = pl->bufs;
   const UNetW& w = h->un;
   const int* d = w.dims;
-  PlanBuilder pb{h, pl, B};
+  PlanBuilder pb{h, pl, B, false, st, {nullptr, nullptr}};
+  {
+    static const bool no_tune = getenv("LADIFF_NO_AUTOTUNE") != nullptr;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (!no_tune && cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone &&
+        cudaEventCreate(&pb.tune_ev[0]) == cudaSuccess && cudaEventCreate(&pb.tune_ev[1]) == cudaSuccess)
+      pb.tune_stream_ok = true;
+  }
   ClView none; memset(&none, 0, sizeof(none));
   int rc = 0;
   auto CHECK = [&](int r) { if (r && !rc) rc = r; };
@@ -892,6 +939,8 @@ int build_plan(H* h, void* ws_unet, int B, int L, Plan** out) {
     CHECK(pb.resnet(w.fin, fc, L, fo, true));                        // + tanh (unet.py:467)
     CHECK(pb.conv(w.finalc, fo, L, none, u.eps, false, nullptr, none));
   }
+  if (pb.tune_ev[0]) cudaEventDestroy(pb.tune_ev[0]);
+  if (pb.tune_ev[1]) cudaEventDestroy(pb.tune_ev[1]);
   if (rc) { delete pl; return rc; }
   if (h->plans.size() >= 4) { delete h->plans.front(); h->plans.erase(h->plans.begin()); }
   h->plans.push_back(pl);
@@ -975,7 +1024,7 @@ size_t codec_ws_bytes(const H* h, int B, int T) {
   const size_t n = codec_buf_elems(h, B, T);
   const int Hmax = h->cfg.n_filters * (1 << h->cfg.n_enc_ratios);
   const size_t z = align_up(sizeof(float) * (size_t)B * h->cfg.rep_dims * (T / h->enc_hop + 1), 1024);   // get_cond's encoder output
-  return (n * kPoolBufs + (size_t)3 * B * Hmax) * sizeof(float) + z + 16 * 1024;
+  return (n * kPoolBufs + lstm_persist_scratch_floats(B, Hmax) + (size_t)B * Hmax + 64) * sizeof(float) + z + 32 * 1024;
 }
 // persistent region used by ladiff_synthesize: cond [B][128][F], x [B][128][L], two upsample temporaries
 size_t persist_bytes(int B, int T, int L) {
@@ -1167,7 +1216,7 @@ extern "C" int32_t ladiff_unet_forward(LadiffHandle* h, const float* x, const in
   LADIFF_REQUIRE(x && time && cond && eps && B > 0, LADIFF_ERR_ARG, "ladiff_unet_forward: null argument");
   TRY(check_ws(ws, ws_bytes, unet_ws_bytes(h, B, L)));
   Plan* pl = nullptr;
-  TRY(build_plan(h, ws, B, L, &pl));
+  TRY(build_plan(h, ws, B, L, st, &pl));
   UnetBufs& u = pl->bufs;
   TRY(prepare_cond(h, pl, cond, B, L, F, st));
   TRY(ncl_to_cl_launch(x, nullptr, view(u.xin, L, 256, 128, 128), B, 128, L, st));
@@ -1186,7 +1235,7 @@ extern "C" int32_t ladiff_ddpm_steps(LadiffHandle* h, float* x, const float* con
   LADIFF_REQUIRE(x && cond && B > 0, LADIFF_ERR_ARG, "ladiff_ddpm_steps: null argument");
   TRY(check_ws(ws, ws_bytes, unet_ws_bytes(h, B, L)));
   Plan* pl = nullptr;
-  TRY(build_plan(h, ws, B, L, &pl));
+  TRY(build_plan(h, ws, B, L, st, &pl));
   return ddpm_run(h, pl, x, cond, noise, n_noise, seed, t_start, n_steps, B, L, F, st);
 }
 
@@ -1226,7 +1275,7 @@ extern "C" int32_t ladiff_synthesize(LadiffHandle* m, LadiffHandle* cm, const fl
   TRY(run_cond_upsample(m, cond, B, F, x, ta, tb, st));                                                 // :125-128
   TRY(normalize_clips_launch(x, B, (long long)128 * L, 0, st));                                         // :129
   Plan* pl = nullptr;
-  TRY(build_plan(m, scratch, B, L, &pl));
+  TRY(build_plan(m, scratch, B, L, st, &pl));
   TRY(ddpm_run(m, pl, x, cond, noise, n_noise, seed, n_steps, n_steps, B, L, F, st));                   // :130
   TRY(run_decoder(m, x, B, L, wav_out, Bump(scratch), st));                                             // :131
   TRY(normalize_clips_launch(wav_out, B, T, 1, st));                                                    // :133-134
@@ -1311,14 +1360,15 @@ extern "C" int32_t ladiff_op_conv1d_cl(const void* x_bf16, const float* w, const
   TcRefView rv;
   if (!rc) rc = tc_conv_plan(d, &p, &rv);
   if (!rc && gn_stats) {
-    if (cudaMalloc((void**)&stats, sizeof(float2) * (size_t)B * p.n_ptiles * (Cout / 32)) != cudaSuccess) rc = LADIFF_ERR_CUDA;
+    if (cudaMalloc((void**)&stats, sizeof(float2) * (size_t)B * p.n_ptiles * TC_STAT_PARTS * (Cout / 32)) != cudaSuccess) rc = LADIFF_ERR_CUDA;
+    else cudaMemset(stats, 0, sizeof(float2) * (size_t)B * p.n_ptiles * TC_STAT_PARTS * (Cout / 32));
     p.stats = stats;
   }
   if (!rc) rc = impl == 1 ? tc_conv_ref_launch(p, rv, 0) : tc_conv_launch(p, 0);
   cudaError_t e = cudaDeviceSynchronize();
   if (!rc && e != cudaSuccess) { ladiff_set_error("ladiff_op_conv1d_cl: %s", cudaGetErrorString(e)); rc = LADIFF_ERR_CUDA; }
   if (!rc && gn_stats) {   // reduce the per-tile partials on the host: [B][Cout/32][2]
-    const int npt = p.n_ptiles;
+    const int npt = p.n_ptiles * TC_STAT_PARTS;
     std::vector<float2> hst((size_t)B * npt * (Cout / 32));
     cudaMemcpy(hst.data(), stats, sizeof(float2) * hst.size(), cudaMemcpyDeviceToHost);
     std::vector<float> red((size_t)B * (Cout / 32) * 2, 0.f);

@@ -199,6 +199,109 @@ __global__ void __launch_bounds__(128) lstm_step_kernel(const float* __restrict_
   }
 }
 
+// ------------------------------------------------------------------ LSTM, large H: ONE persistent cooperative kernel per layer
+// grid H/4 CTAs x 256 threads, all co-resident (cooperative launch).  CTA c owns hidden units 4c..4c+3 = 16 gate rows, whose
+// recurrent weights stay in shared memory ([k][16], 32 B per k) for the whole sequence.  Clips are processed in groups of 32.
+// Per time step: every CTA pulls h_{t-1} of the group ([H][32] fp32, k-major, written by all CTAs) from L2 into shared memory,
+// warp w multiplies its K-slice (thread tile 4 rows x 4 clips, operands as broadcast LDS.128), the 8 partial tiles are summed
+// in a fixed order, 128 threads apply the gates (cell state lives in their registers) and publish h_t; a global arrive/spin
+// barrier (monotonic counter) separates the steps.  Replaces T launches of lstm_step_kernel.
+constexpr int LP_B = 32;      // clips per group
+constexpr int LP_WARPS = 8;
+
+__device__ __forceinline__ void lp_grid_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256, 1) lstm_persist_kernel(const float* __restrict__ pre, const float* __restrict__ whh,
+                                                               const float* __restrict__ skip, float* __restrict__ y,
+                                                               float* __restrict__ hglob, unsigned int* counter, int B, int H, int T) {
+  extern __shared__ __align__(16) float lp_sm[];
+  float* Wt = lp_sm;                              // [H][16]  (k-major; column lr = gate*4 + unit)
+  float* hs = lp_sm + (size_t)H * 16;             // [H][32]  h_{t-1} of the clip group, k-major
+  float* part = hs + (size_t)H * LP_B;            // [8][16][32] partial tiles
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int j0 = blockIdx.x * 4;
+  for (int i = tid; i < 16 * H; i += 256) {
+    const int lr = i / H, k = i - lr * H;
+    Wt[k * 16 + lr] = whh[(long long)((lr >> 2) * H + j0 + (lr & 3)) * H + k];
+  }
+  const int kslice = H / LP_WARPS, k_lo = warp * kslice;
+  const int ri = lane >> 3, ci = lane & 7;        // thread tile: rows 4ri..4ri+3, clips 4ci..4ci+3
+  const int gu = tid >> 5, gb = tid & 31;         // gate threads (tid < 128): unit gu, clip gb of the group
+  const int ngroups = (B + LP_B - 1) / LP_B;
+  unsigned int epoch = 0;
+  for (int g = 0; g < ngroups; ++g) {
+    const int bg = g * LP_B + gb;
+    float c = 0.f;
+    float* hbuf0 = hglob + (size_t)g * 2 * H * LP_B;
+    for (int t = 0; t < T; ++t) {
+      // gate pre-activations of this step: independent of h, requested before the barrier wait
+      float p4[4] = {0.f, 0.f, 0.f, 0.f};
+      float sk = 0.f;
+      if (tid < 128 && bg < B) {
+        const long long pbase = (long long)bg * 4 * H * T + t;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) p4[q] = __ldg(pre + pbase + (long long)(q * H + j0 + gu) * T);
+        if (skip) sk = __ldg(skip + ((long long)bg * H + j0 + gu) * T + t);
+      }
+      float acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      if (t > 0) {
+        lp_grid_barrier(counter, (++epoch) * gridDim.x);     // h_{t-1} of every unit is published
+        const float4* src = reinterpret_cast<const float4*>(hbuf0 + (size_t)((t - 1) & 1) * H * LP_B);
+        float4* dst = reinterpret_cast<float4*>(hs);
+#pragma unroll 8
+        for (int i = tid; i < H * LP_B / 4; i += 256) dst[i] = __ldcg(src + i);
+        __syncthreads();
+        const float4* w4 = reinterpret_cast<const float4*>(Wt) + ri;
+        const float4* h4 = reinterpret_cast<const float4*>(hs) + ci;
+#pragma unroll 4
+        for (int k = k_lo; k < k_lo + kslice; ++k) {
+          const float4 w = w4[k * 4], hv = h4[k * 8];
+          acc[0][0] += w.x * hv.x; acc[0][1] += w.x * hv.y; acc[0][2] += w.x * hv.z; acc[0][3] += w.x * hv.w;
+          acc[1][0] += w.y * hv.x; acc[1][1] += w.y * hv.y; acc[1][2] += w.y * hv.z; acc[1][3] += w.y * hv.w;
+          acc[2][0] += w.z * hv.x; acc[2][1] += w.z * hv.y; acc[2][2] += w.z * hv.z; acc[2][3] += w.z * hv.w;
+          acc[3][0] += w.w * hv.x; acc[3][1] += w.w * hv.y; acc[3][2] += w.w * hv.z; acc[3][3] += w.w * hv.w;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<float4*>(part + ((size_t)warp * 16 + 4 * ri + i) * LP_B + 4 * ci) =
+            make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      __syncthreads();
+      if (tid < 128) {
+        float gsum[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float a = 0.f;
+#pragma unroll
+          for (int w = 0; w < LP_WARPS; ++w) a += part[((size_t)w * 16 + q * 4 + gu) * LP_B + gb];
+          gsum[q] = a + p4[q];
+        }
+        c = sigmoid_f(gsum[1]) * c + sigmoid_f(gsum[0]) * tanhf(gsum[2]);
+        const float hv = sigmoid_f(gsum[3]) * tanhf(c);
+        hbuf0[(size_t)(t & 1) * H * LP_B + (size_t)(j0 + gu) * LP_B + gb] = hv;
+        if (bg < B) y[((long long)bg * H + j0 + gu) * T + t] = skip ? hv + sk : hv;
+      }
+      // `part` and `hs` are rewritten only after the next step's barrier (which begins with __syncthreads)
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------ RVQ
 // 8 frames per CTA, 256 threads; residual kept in smem across the n_q stages
 constexpr int RVQ_FR = 8;
@@ -432,6 +535,23 @@ int lstm_seq_launch(const float* pre, const float* whh, const float* skip, float
   LADIFF_CUDA_OK(cudaGetLastError());
   return 0;
 }
+
+int lstm_persist_launch(const float* pre, const float* whh, const float* skip, float* y, float* hglob, unsigned int* counter, int B, int H,
+                        int T, cudaStream_t st) {
+  LADIFF_REQUIRE(H % 32 == 0 && H >= 32, LADIFF_ERR_ARG, "lstm_persist: H=%d", H);
+  const size_t smem = ((size_t)H * 16 + (size_t)H * LP_B + (size_t)LP_WARPS * 16 * LP_B) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    LADIFF_CUDA_OK(cudaFuncSetAttribute(lstm_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  LADIFF_REQUIRE(smem <= 200 * 1024 && H / 4 <= tc_num_sms(), LADIFF_ERR_ARG, "lstm_persist: H=%d does not fit one co-resident grid", H);
+  LADIFF_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+  void* args[] = {(void*)&pre, (void*)&whh, (void*)&skip, (void*)&y, (void*)&hglob, (void*)&counter, (void*)&B, (void*)&H, (void*)&T};
+  LADIFF_CUDA_OK(cudaLaunchCooperativeKernel((const void*)lstm_persist_kernel, dim3(H / 4), dim3(256), args, smem, st));
+  return 0;
+}
+size_t lstm_persist_scratch_floats(int B, int H) { return (size_t)((B + LP_B - 1) / LP_B) * 2 * H * LP_B + 64; }
 
 int lstm_steps_launch(const float* pre, const float* whh, const float* skip, float* y, float* hbuf, float* cbuf, int B, int H, int T,
                       cudaStream_t st, long long* launches) {

@@ -28,6 +28,12 @@ int lstm_seq_launch(const float* pre, const float* whh, const float* skip, float
 int lstm_steps_launch(const float* pre, const float* whh, const float* skip, float* y, float* hbuf, float* cbuf, int B, int H, int T,
                       cudaStream_t st, long long* launches);
 
+// large H (encoder, H = 512): one persistent cooperative kernel per layer; hglob: lstm_persist_scratch_floats(B, H) floats
+// (h ping-pong per 32-clip group, k-major), counter: one zero-initialised-here unsigned int
+int lstm_persist_launch(const float* pre, const float* whh, const float* skip, float* y, float* hglob, unsigned int* counter, int B, int H,
+                        int T, cudaStream_t st);
+size_t lstm_persist_scratch_floats(int B, int H);
+
 // Residual VQ (core_vq.py:174-189, 324-362).  z [B][D][F] -> quantized [B][D][F] (nullable), codes [n_q][B][F] int64 (nullable)
 // embed [n_q][bins][D], embed_sq [n_q][bins] = sum_d e^2
 int rvq_encode_launch(const float* z, const float* embed, const float* embed_sq, int n_q, int bins, int D, int B, int F,

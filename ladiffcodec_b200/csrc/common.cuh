@@ -80,6 +80,7 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
 #define TC_MAX_TAPS 7
 #define TC_BM 128
 #define TC_BK 64
+#define TC_STAT_PARTS 2   // GroupNorm partials per (clip, position tile): one per epilogue warpgroup
 
 struct TcTap {
   int row_off;  // row offset of this tap inside the group's shared-memory tile (0..7)
@@ -109,7 +110,7 @@ struct TcConvDesc {
   const bf16* x; long long x_bstride; int x_pitch; int Lin;   // input view (Lin rows of Cin channels per clip)
   bf16* out; long long out_bstride; int out_pitch;            // bf16 output view (Lout rows; 2*Lout rows for UP)
   float* out32;             // if set: fp32 output, contiguous [B][Lout][CoutV] (direct epilogue)
-  float2* stats;            // optional GroupNorm partials [B][n_ptiles][CoutV/32]
+  float2* stats;            // optional GroupNorm partials [B][n_ptiles][TC_STAT_PARTS][CoutV/32]
   const bf16* res; long long res_bstride; int res_pitch;      // optional residual (direct epilogue)
   // optional second output (ResnetBlock: res_conv fused into block1's conv): output channels m >= split_m are a 1x1 conv of the
   // same input (weights at K offset 0 of rows [split_m, CoutV)) written to out2; GroupNorm partials cover m < split_m only
@@ -117,6 +118,7 @@ struct TcConvDesc {
   bf16* out2; long long out2_bstride; int out2_pitch;
   int B;
   int tap_share;            // 1: all taps of a chunk read one shared activation tile; 0: one tile load per tap
+  int want_nt, want_nclip;  // > 0: force the tile shape (rows per clip region / clip regions per tile); 0: cost model
 };
 
 struct TcConvParams {
@@ -146,7 +148,7 @@ struct TcConvParams {
   int stat_slots;    // GroupNorm slots per tile row block: (split_m ? split_m : Cout) / 32
   int B, Lout, Cout;
   const float* bias; // [Cout] or null
-  float2* stats;     // optional GroupNorm partials [B][n_ptiles][Cout/32] (sum, sumsq) of the fp32 result
+  float2* stats;     // optional GroupNorm partials [B][n_ptiles][TC_STAT_PARTS][Cout/32] (sum, sumsq) of the fp32 result
   // direct epilogue only
   void* out;
   long long out_bstride;

@@ -15,7 +15,8 @@
 // Persistent, warp-specialised CTAs (one per SM):
 //   warp 0    TMA producer (two rings: weights 16 KB slots, activations)
 //   warp 1    TMEM allocator + MMA issuer (tcgen05.mma cta_group::1 kind::f16, M=128, N<=256, K=16)
-//   warps 2-5 epilogue: tcgen05.ld -> +bias -> GroupNorm partial sums -> bf16 -> smem staging -> TMA store
+//   warps 2-9 epilogue: two warpgroups (each covers the four TMEM lane quadrants) that take alternate store chunks of a tile:
+//             tcgen05.ld -> +bias -> GroupNorm partial sums -> bf16 -> smem staging -> TMA store
 // Two TMEM accumulator stages, so the epilogue of tile i overlaps the main loop of tile i+1.
 // Short clips (L < 128) are packed several per tile (one TMA box per clip, per-clip zero padding kept).
 #include <cudaTypedefs.h>
@@ -28,7 +29,8 @@
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;
+constexpr int kEpiGroups = 2;     // epilogue warpgroups; GroupNorm partials carry one slot set per group
 constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;  // 16 KB
 constexpr int kMaxStages = 6;
 constexpr int kStageTaps = 3;    // weight tiles per pipeline stage
@@ -98,7 +100,7 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -117,14 +119,15 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+// asynchronous: the registers are valid only after tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct TileCoord { int m0, b0, l0, pt; };
 __device__ __forceinline__ TileCoord decode_tile(const TcConvParams& p, int t) {
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4 * kEpiGroups); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmW) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmX) : "memory");
@@ -279,18 +282,39 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
     }
     __syncwarp();
   } else {
-    // ---------------- epilogue warps (warp w owns TMEM lanes 32*(w&3) .. +31)
+    // ---------------- epilogue: warp w owns TMEM lanes 32*(w&3) .. +31; warpgroup wg (warps 2-5 / 6-9) takes the store chunks
+    // whose running index cc has (cc & 1) == wg, with its own pair of staging buffers, named barrier and TMA-store issuer
     const int q = warp & 3;
-    const bool store_warp = warp == 2;   // its elected lane issues the TMA stores; bulk-group waits are executed warp-wide
+    const int wg = (warp - 2) >> 2;
+    const bool store_warp = ((warp - 2) & 3) == 0;   // its elected lane issues this group's TMA stores; bulk-group waits are warp-wide
     const int Cc = p.up_cout ? p.up_cout : (p.split_m ? p.split_m : p.Cout);
-    int tl = 0, cc = 0;
-    long long w_acc = 0;
+    const uint32_t stage_wg = stage0 + (uint32_t)(wg * 2) * (uint32_t)p.CR * 256u;
+    int tl = 0, cc = 0, kk = 0;
+    // bias of the NEXT tile is requested one tile ahead (an exposed L2 round trip per tile otherwise)
+    float bias_next = (p.bias && (int)blockIdx.x < total_tiles) ? __ldg(p.bias + decode_tile(p, blockIdx.x).m0 + q * 32 + lane) : 0.f;
+    long long w_acc = 0, w_e1 = 0, w_e2 = 0, w_e3 = 0;   // profiling: chunk entry (store drain + barrier), body, fence + barrier + store issue
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
       const TileCoord tc = decode_tile(p, t);
       const int acc = tl & 1;
       const int ch = tc.m0 + q * 32 + lane;
-      const float bias = p.bias ? p.bias[ch] : 0.f;
+      const float bias = bias_next;
+      if (p.bias && t + (int)gridDim.x < total_tiles) bias_next = __ldg(p.bias + decode_tile(p, t + gridDim.x).m0 + q * 32 + lane);
       const bool second = p.split_m && tc.m0 >= p.split_m;
+      if (p.res) {
+        // direct epilogue with a residual: its tile ([clip region][row][128 channels] bf16) is staged in shared memory by all
+        // epilogue threads while the main loop of this tile is still running
+        asm volatile("bar.sync 3, 256;" ::: "memory");          // the previous tile's residual has been consumed
+        const int et = threadIdx.x - 64;                         // 0..255
+        for (int i = et; i < p.NMMA * 16; i += 256) {
+          const int rr = i >> 4, seg = i & 15, j = rr / p.NT, r = rr - j * p.NT;
+          const int b = tc.b0 + j, l = tc.l0 + r;
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (b < p.B && l < p.Lout)
+            v = __ldg(reinterpret_cast<const uint4*>(p.res + (long long)b * p.res_bstride + (long long)l * p.res_pitch + tc.m0) + seg);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage0 + (uint32_t)i * 16u), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        }
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+      }
       mbar_wait_t(&tmem_full[acc], (tl >> 1) & 1, w_acc, prof);
       tc_fence_after();
       const uint32_t tlane = tmem_base + (uint32_t)acc * acc_stride + ((uint32_t)(q * 32) << 16);
@@ -300,25 +324,40 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
         vr = vr > p.NT ? p.NT : vr;
         if (b >= p.B) vr = 0;
         float s1 = 0.f, s2 = 0.f;
-        for (int r0 = 0; r0 < p.NT; r0 += p.CR) {
-          if (vr <= r0 || (p.dbg & 2)) break;    // uniform over the 128 epilogue threads
+        for (int r0 = 0; r0 < p.NT; r0 += p.CR, ++cc) {
+          if ((cc & 1) != wg || vr <= r0 || (p.dbg & 2)) continue;    // uniform over the warpgroup
           const int nrows = (p.NT - r0) < p.CR ? (p.NT - r0) : p.CR;
           uint32_t stg = 0;
+          const long long te0 = prof ? clock64() : 0;
           if (!p.direct) {
-            if (store_warp) bulk_wait_read_1();  // the store issued two chunks ago has finished reading its buffer
-            epi_bar();
-            stg = stage0 + (uint32_t)(cc & 1) * (uint32_t)p.CR * 256u + (uint32_t)(q * 32 + lane) * 2u;
+            if (store_warp) bulk_wait_read_1();  // the store this group issued two chunks ago has finished reading its buffer
+            epi_bar(wg);
+            stg = stage_wg + (uint32_t)(kk & 1) * (uint32_t)p.CR * 256u + (uint32_t)(q * 32 + lane) * 2u;
           }
-          for (int c0 = 0; c0 < nrows; c0 += 16) {
-            uint32_t r[16];
-            tmem_ld16(tlane + (uint32_t)(j * p.NT + r0 + c0), r);
-            if (!p.direct) {
+          const long long te1 = prof ? clock64() : 0;
+          const uint32_t tcol = tlane + (uint32_t)(j * p.NT + r0);
+          const bool no_ld = (p.dbg & 8) != 0, no_st = (p.dbg & 16) != 0;   // ablations (LADIFF_TC_DBG)
+          auto consume = [&](const uint32_t (&r)[16], int c0) {
+            if (no_st) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float v = __uint_as_float(r[i]) + bias;
-                if (r0 + c0 + i < vr) { s1 += v; s2 += v * v; }
-                const unsigned short hv = __bfloat16_as_ushort(__float2bfloat16(v));
-                asm volatile("st.shared.u16 [%0], %1;" ::"r"(stg + (uint32_t)(c0 + i) * 256u), "h"(hv) : "memory");
+              for (int i = 0; i < 16; ++i) s1 += __uint_as_float(r[i]);
+            } else if (!p.direct) {
+              if (r0 + c0 + 16 <= vr) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const float v = __uint_as_float(r[i]) + bias;
+                  s1 += v; s2 += v * v;
+                  const unsigned short hv = __bfloat16_as_ushort(__float2bfloat16(v));
+                  asm volatile("st.shared.u16 [%0], %1;" ::"r"(stg + (uint32_t)(c0 + i) * 256u), "h"(hv) : "memory");
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const float v = __uint_as_float(r[i]) + bias;
+                  if (r0 + c0 + i < vr) { s1 += v; s2 += v * v; }
+                  const unsigned short hv = __bfloat16_as_ushort(__float2bfloat16(v));
+                  asm volatile("st.shared.u16 [%0], %1;" ::"r"(stg + (uint32_t)(c0 + i) * 256u), "h"(hv) : "memory");
+                }
               }
             } else {
 #pragma unroll
@@ -328,42 +367,63 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
                   const int l = tc.l0 + row;
                   float v = __uint_as_float(r[i]) + bias;
                   s1 += v; s2 += v * v;
-                  if (p.res) v += __bfloat162float(p.res[(long long)b * p.res_bstride + (long long)l * p.res_pitch + ch]);
+                  if (p.res) {
+                    unsigned short rv16;
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(rv16) : "r"(stage0 + (uint32_t)(j * p.NT + row) * 256u + (uint32_t)(q * 32 + lane) * 2u));
+                    v += __bfloat162float(__ushort_as_bfloat16(rv16));
+                  }
                   const long long o = (long long)b * p.out_bstride + (long long)l * p.out_pitch + ch;
                   if (p.out_f32) reinterpret_cast<float*>(p.out)[o] = v;
                   else reinterpret_cast<bf16*>(p.out)[o] = __float2bfloat16(v);
                 }
               }
             }
+          };
+          // two register sets: the TMEM load of the next 16 columns is in flight while the current ones are consumed
+          uint32_t ra[16], rb[16];
+          if (!no_ld) tmem_ld16_async(tcol, ra);
+          for (int c0 = 0; c0 < nrows; c0 += 32) {
+            tmem_ld_wait();
+            const bool has_b = c0 + 16 < nrows;
+            if (has_b && !no_ld) tmem_ld16_async(tcol + (uint32_t)(c0 + 16), rb);
+            consume(ra, c0);
+            if (has_b) {
+              tmem_ld_wait();
+              if (c0 + 32 < nrows && !no_ld) tmem_ld16_async(tcol + (uint32_t)(c0 + 32), ra);
+              consume(rb, c0 + 16);
+            }
           }
+          const long long te2 = prof ? clock64() : 0;
           if (!p.direct) {
             fence_async_smem();
-            epi_bar();
-            if (store_warp && elect_one()) {
-              const uint32_t src = stage0 + (uint32_t)(cc & 1) * (uint32_t)p.CR * 256u;
+            epi_bar(wg);
+            if (store_warp && !no_st && elect_one()) {
+              const uint32_t src = stage_wg + (uint32_t)(kk & 1) * (uint32_t)p.CR * 256u;
               if (second) tma_store_4d(nrows == p.CR ? &p.tmY2 : &p.tmY2r, src, tc.m0 - p.split_m, 0, tc.l0 + r0, b);
               else tma_store_4d(nrows == p.CR ? &p.tmY : &p.tmYr, src, tc.m0 % Cc, tc.m0 / Cc, tc.l0 + r0, b);
               bulk_commit();
             }
-            ++cc;
+            ++kk;
           }
+          if (prof) { const long long te3 = clock64(); w_e1 += te1 - te0; w_e2 += te2 - te1; w_e3 += te3 - te2; }
         }
-        if (p.stats && vr > 0 && !second) {
+        if (p.stats && vr > 0 && !second) {      // one partial per (clip, position tile, warpgroup); zero if this group had no chunk
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) {
             s1 += __shfl_xor_sync(0xffffffffu, s1, o);
             s2 += __shfl_xor_sync(0xffffffffu, s2, o);
           }
           if (lane == 0)
-            p.stats[((long long)b * p.n_ptiles + tc.pt) * p.stat_slots + (tc.m0 / 32 + q)] = make_float2(s1, s2);
+            p.stats[(((long long)b * p.n_ptiles + tc.pt) * kEpiGroups + wg) * p.stat_slots + (tc.m0 / 32 + q)] = make_float2(s1, s2);
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);   // 4 warps -> accumulator stage free for the MMA issuer
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);   // 8 warps -> accumulator stage free for the MMA issuer
     }
     if (store_warp) bulk_wait_all();
-    if (prof && threadIdx.x == 64) { p.prof[blockIdx.x * 8 + 3] = (unsigned long long)w_acc; p.prof[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - t_begin); }
+    if (prof && threadIdx.x == 64) { p.prof[blockIdx.x * 8 + 3] = (unsigned long long)w_acc; p.prof[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - t_begin);
+      p.prof[blockIdx.x * 8 + 5] = (unsigned long long)w_e1; p.prof[blockIdx.x * 8 + 6] = (unsigned long long)w_e2; p.prof[blockIdx.x * 8 + 7] = (unsigned long long)w_e3; }
   }
   tc_fence_before();
   __syncthreads();
@@ -423,7 +483,11 @@ __global__ void __launch_bounds__(128) tc_conv_ref_kernel(TcConvParams p, TcRefV
         a += __shfl_xor_sync(0xffffffffu, a, o);
         c += __shfl_xor_sync(0xffffffffu, c, o);
       }
-      if (lane == 0) p.stats[((long long)b * p.n_ptiles + pt) * p.stat_slots + blockIdx.y] = make_float2(a, c);
+      if (lane == 0) {
+        float2* sp = p.stats + (((long long)b * p.n_ptiles + pt) * kEpiGroups) * p.stat_slots + blockIdx.y;
+        sp[0] = make_float2(a, c);
+        for (int gi = 1; gi < kEpiGroups; ++gi) sp[(long long)gi * p.stat_slots] = make_float2(0.f, 0.f);
+      }
     }
   }
 }
@@ -495,7 +559,9 @@ int tc_make_tmap_w(CUtensorMap* tm, const bf16* w, int Cout, int Ktot) {
 }
 
 // Tile shape for clips of Lout rows: minimise rounds-over-the-SMs x per-tile cost; ties go to the wider tile (less operand traffic).
-static void pick_tiling(int Lout, int B, int MT, int halo2, int* NT, int* NCLIP, int* n_ptiles) {
+// Tile shape for clips of Lout rows.  want_nt/want_nclip > 0 force a shape (the plan builder's autotuner tries several);
+// otherwise: minimise rounds-over-the-SMs x per-tile cost; ties go to the wider tile (less operand traffic).
+static void pick_tiling(int Lout, int B, int MT, int halo2, int want_nt, int want_nclip, int* NT, int* NCLIP, int* n_ptiles) {
   const int nsm = tc_num_sms();
   long best = -1;
   const int maxn = halo2 ? 240 : 256;
@@ -503,13 +569,17 @@ static void pick_tiling(int Lout, int B, int MT, int halo2, int* NT, int* NCLIP,
     const int rp = cdiv(Lout + halo2, 16) * 16;
     for (int nc = 256 / rp; nc >= 1; --nc) {
       if (nc > B && nc > 1) continue;
+      if (want_nclip > 0 && nc != want_nclip) continue;
       const long tiles = (long)MT * cdiv(B, nc);
       const long cost = (long)cdiv((int)tiles, nsm) * (nc * rp + 32);
       if (best < 0 || cost < best) { best = cost; *NT = rp; *NCLIP = nc; *n_ptiles = 1; }
     }
+    if (best >= 0) return;
+    *NT = rp; *NCLIP = 1; *n_ptiles = 1;
     return;
   }
-  static const int force_nt = getenv("LADIFF_TC_NT") ? atoi(getenv("LADIFF_TC_NT")) : 0;   // experiment knob
+  static const int env_nt = getenv("LADIFF_TC_NT") ? atoi(getenv("LADIFF_TC_NT")) : 0;   // experiment knob
+  const int force_nt = want_nt > 0 ? want_nt : env_nt;
   if (force_nt >= 64 && force_nt <= maxn && force_nt % 16 == 0) {
     *NT = force_nt; *NCLIP = 1; *n_ptiles = cdiv(Lout, force_nt);
     return;
@@ -598,7 +668,7 @@ int tc_conv_plan(const TcConvDesc& d, TcConvParams* pp, TcRefView* rv) {
   p.up_cout = d.kind == TC_KIND_UP ? d.CoutV / 2 : 0;
   p.split_m = d.split_m;
   p.stat_slots = (d.split_m ? d.split_m : d.CoutV) / 32;
-  pick_tiling(Lout, d.B, p.MT, tile_halo, &p.NT, &p.NCLIP, &p.n_ptiles);
+  pick_tiling(Lout, d.B, p.MT, tile_halo, d.want_nt, d.want_nclip, &p.NT, &p.NCLIP, &p.n_ptiles);
   p.NMMA = p.NT * p.NCLIP;
   p.n_ntiles = p.NCLIP == 1 ? d.B * p.n_ptiles : cdiv(d.B, p.NCLIP);
   p.BOXROWS = p.NCLIP == 1 ? p.NT + (tile_halo ? 8 : 0) : p.NT;
@@ -608,19 +678,15 @@ int tc_conv_plan(const TcConvDesc& d, TcConvParams* pp, TcRefView* rv) {
   p.direct = (d.out32 != nullptr || d.res != nullptr) ? 1 : 0;
   p.b_slot_bytes = (int)align_up((size_t)p.NCLIP * p.BOXROWS * 128, 1024);
   p.stage_bytes = p.a_cap * (int)A_BYTES + p.b_slot_bytes;
-  // shared-memory budget: S pipeline stages + 2 epilogue staging chunks + 1 KB alignment + 1 KB tap over-read.
+  // shared-memory budget: S pipeline stages + 2 epilogue staging chunks per epilogue warpgroup + 1 KB alignment + 1 KB tap over-read.
   // Smaller staging chunks (32 rows) are used when they buy another pipeline stage.
   auto stages_for = [&](int cr) {
-    const long rest = (long)kSmemLimit - 2048 - (p.direct ? 0 : (long)2 * cr * 256);
+    const long rest = (long)kSmemLimit - 2048 - (p.direct ? (d.res ? (long)p.NMMA * 256 : 0) : (long)2 * kEpiGroups * cr * 256);
     const int s2 = (int)(rest / p.stage_bytes);
     return s2 > kMaxStages ? kMaxStages : s2;
   };
-  if (p.NCLIP == 1) {
-    p.CR = p.NT < 64 ? p.NT : 64;
-    if (p.NT > 32 && stages_for(32) > stages_for(p.CR)) p.CR = 32;
-  } else {
-    p.CR = p.NT;
-  }
+  p.CR = p.NT < 32 ? p.NT : 32;
+  if (p.NT > 16 && stages_for(16) > stages_for(p.CR)) p.CR = 16;
   p.S = stages_for(p.CR);
   LADIFF_REQUIRE(p.S >= 2, LADIFF_ERR_ARG, "tc_conv: tile N=%d with %d taps per stage does not fit two pipeline stages", p.NMMA, p.a_cap);
   p.tmW = *d.tmW;
@@ -658,7 +724,7 @@ int tc_conv_plan(const TcConvDesc& d, TcConvParams* pp, TcRefView* rv) {
 }
 
 static size_t tc_smem_bytes(const TcConvParams& p) {
-  return (size_t)p.S * p.stage_bytes + (p.direct ? 0 : (size_t)2 * p.CR * 256) + 2048;
+  return (size_t)p.S * p.stage_bytes + (p.direct ? (p.res ? (size_t)p.NMMA * 256 : 0) : (size_t)2 * kEpiGroups * p.CR * 256) + 2048;
 }
 
 int tc_conv_launch(const TcConvParams& p, cudaStream_t st) {
@@ -677,7 +743,7 @@ int tc_conv_launch(const TcConvParams& p, cudaStream_t st) {
     return 0;
   }
   TcConvParams q = p;
-  q.dbg = getenv("LADIFF_TC_DBG") ? atoi(getenv("LADIFF_TC_DBG")) : 0;   // 1: no TMA after ring fill, 2: no epilogue, 4: no MMA
+  q.dbg = getenv("LADIFF_TC_DBG") ? atoi(getenv("LADIFF_TC_DBG")) : 0;   // 1: no TMA after ring fill, 2: no epilogue, 4: no MMA, 8: epilogue without tcgen05.ld, 16: epilogue without smem/TMA stores
   unsigned long long* dprof = nullptr;
   LADIFF_CUDA_OK(cudaMalloc((void**)&dprof, sizeof(unsigned long long) * 8 * grid));
   LADIFF_CUDA_OK(cudaMemset(dprof, 0, sizeof(unsigned long long) * 8 * grid));
@@ -688,10 +754,10 @@ int tc_conv_launch(const TcConvParams& p, cudaStream_t st) {
   std::vector<unsigned long long> hp((size_t)8 * grid);
   LADIFF_CUDA_OK(cudaMemcpy(hp.data(), dprof, sizeof(unsigned long long) * hp.size(), cudaMemcpyDeviceToHost));
   cudaFree(dprof);
-  double a[5] = {0, 0, 0, 0, 0};
-  for (int i = 0; i < grid; ++i) for (int k = 0; k < 5; ++k) a[k] += (double)hp[(size_t)i * 8 + k] / grid;
+  double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < grid; ++i) for (int k = 0; k < 8; ++k) a[k] += (double)hp[(size_t)i * 8 + k] / grid;
   fprintf(stderr, "[tc_prof] dbg=%d Cout=%d N=%d(NT=%d x%d) S=%d a_cap=%d grid=%d tiles=%d | cycles/CTA: total %.0f  producer-wait-empty %.0f  mma-wait-full %.0f  "
-                  "mma-wait-tmem %.0f  epi-wait-acc %.0f\n", q.dbg, p.Cout, p.NMMA, p.NT, p.NCLIP, p.S, p.a_cap, grid, tiles, a[4], a[0], a[1], a[2], a[3]);
+                  "mma-wait-tmem %.0f  epi-wait-acc %.0f  epi(wg0): entry %.0f body %.0f exit %.0f\n", q.dbg, p.Cout, p.NMMA, p.NT, p.NCLIP, p.S, p.a_cap, grid, tiles, a[4], a[0], a[1], a[2], a[3], a[5], a[6], a[7]);
   return 0;
 }
 
