@@ -49,10 +49,10 @@ struct KeySpec {
 };
 
 // ---- folded codec parameters
-struct ConvW { const float* w = nullptr; const float* bias = nullptr; int Cout = 0, Cin = 0, K = 0, stride = 1; };
-struct ConvTrW { const float* w2 = nullptr; const float* bias = nullptr; int Cin = 0, Cout = 0, s = 1; };
+struct ConvW { const float* w = nullptr; const float* wt = nullptr; const float* bias = nullptr; int Cout = 0, Cin = 0, K = 0, stride = 1; };
+struct ConvTrW { const float* w2 = nullptr; const float* wt = nullptr; const float* bias = nullptr; int Cin = 0, Cout = 0, s = 1; };
 struct ResBlockW { ConvW c1, c2, sc; };
-struct LstmW { int H = 0, layers = 0; const float* wih[4]; const float* whh[4]; const float* bias[4]; };
+struct LstmW { int H = 0, layers = 0; const float* wih[4]; const float* wih_t[4]; const float* whh[4]; const float* bias[4]; };
 struct EncoderW { ConvW first, last; std::vector<ResBlockW> rb; std::vector<ConvW> down; LstmW lstm; };
 struct DecoderW { ConvW first, last; std::vector<ConvTrW> up; std::vector<ResBlockW> rb; LstmW lstm; };
 
@@ -314,6 +314,12 @@ int fold_wn_conv(H* h, const std::string& p, int cout, int cin, int k, int strid
   TRY(weight_norm_fold_launch(Wp(h, p + ".conv.conv.weight_g"), Wp(h, p + ".conv.conv.weight_v"), w, cout, cin * k, 0));
   out->w = w; out->bias = Wp(h, p + ".conv.conv.bias");
   out->Cout = cout; out->Cin = cin; out->K = k; out->stride = stride;
+  if (k % stride == 0) {          // K-major copy for the register-tiled kernel
+    float* wt = nullptr;
+    TRY(dalloc(h, &wt, (size_t)cout * cin * k));
+    TRY(conv_w_transpose_launch(w, wt, cout, cin, k, stride, 0, 0, 0));
+    out->wt = wt;
+  }
   return 0;
 }
 int fold_wn_convtr(H* h, const std::string& p, int cin, int cout, int s, ConvTrW* out) {
@@ -323,6 +329,12 @@ int fold_wn_convtr(H* h, const std::string& p, int cin, int cout, int s, ConvTrW
   TRY(weight_norm_fold_launch(Wp(h, p + ".convtr.convtr.weight_g"), Wp(h, p + ".convtr.convtr.weight_v"), w, cin, cout * 2 * s, 0));
   TRY(convtr_pack_launch(w, w2, cin, cout, s, 0));
   out->w2 = w2; out->bias = Wp(h, p + ".convtr.convtr.bias"); out->Cin = cin; out->Cout = cout; out->s = s;
+  {
+    float* wt = nullptr;
+    TRY(dalloc(h, &wt, (size_t)cin * cout * 2 * s));
+    TRY(conv_w_transpose_launch(w2, wt, s * cout, cin, 2, 1, s, cout, 0));
+    out->wt = wt;
+  }
   return 0;
 }
 int fold_resblock(H* h, const std::string& p, int dim, ResBlockW* rb) {
@@ -337,6 +349,12 @@ int fold_lstm(H* h, const std::string& p, int dim, int layers, LstmW* lw) {
     const std::string s = std::to_string(l);
     lw->wih[l] = Wp(h, p + ".lstm.weight_ih_l" + s);
     lw->whh[l] = Wp(h, p + ".lstm.weight_hh_l" + s);
+    {
+      float* wt = nullptr;
+      TRY(dalloc(h, &wt, (size_t)4 * dim * dim));
+      TRY(conv_w_transpose_launch(lw->wih[l], wt, 4 * dim, dim, 1, 1, 0, 0, 0));
+      lw->wih_t[l] = wt;
+    }
     float* b = nullptr;
     TRY(dalloc(h, &b, (size_t)4 * dim));
     TRY(add_vec_launch(Wp(h, p + ".lstm.bias_ih_l" + s), Wp(h, p + ".lstm.bias_hh_l" + s), b, 4 * dim, 0));
@@ -538,6 +556,12 @@ int fold_unet(H* h) {
     TRY(dalloc(h, &w2, (size_t)cc * cc * 2 * s));
     TRY(convtr_pack_launch(Wp(h, p + ".weight"), w2, cc, cc, s, 0));
     t.w2 = w2; t.bias = Wp(h, p + ".bias"); t.Cin = cc; t.Cout = cc; t.s = s;
+    {
+      float* wt = nullptr;
+      TRY(dalloc(h, &wt, (size_t)cc * cc * 2 * s));
+      TRY(conv_w_transpose_launch(w2, wt, s * cc, cc, 2, 1, s, cc, 0));
+      t.wt = wt;
+    }
     u.cond_up.push_back(t);
   }
   return 0;
@@ -558,7 +582,7 @@ int conv_out_len(int Lin, int K, int stride) {   // conv.py:56-63 with padding_t
 int run_conv(H* h, const ConvW& cw, const float* x, int Lin, float* y, int act_in, const float* res, int B, cudaStream_t st) {
   ConvF32Args a;
   memset(&a, 0, sizeof(a));
-  a.x = x; a.Cin = cw.Cin; a.Lin = Lin; a.w = cw.w; a.bias = cw.bias; a.y = y; a.CoutV = cw.Cout;
+  a.x = x; a.Cin = cw.Cin; a.Lin = Lin; a.w = cw.w; a.wt = cw.wt; a.bias = cw.bias; a.y = y; a.CoutV = cw.Cout;
   a.LoutV = conv_out_len(Lin, cw.K, cw.stride);
   a.K = cw.K; a.stride = cw.stride; a.padL = (cw.K - 1) - (cw.stride - 1); a.pad_reflect = 1; a.act_in = act_in; a.res = res;
   h->launches++;
@@ -568,7 +592,7 @@ int run_conv(H* h, const ConvW& cw, const float* x, int Lin, float* y, int act_i
 int run_convtr(H* h, const ConvTrW& cw, const float* x, int Lin, float* y, int act_in, bool causal, int B, cudaStream_t st) {
   ConvF32Args a;
   memset(&a, 0, sizeof(a));
-  a.x = x; a.Cin = cw.Cin; a.Lin = Lin; a.w = cw.w2; a.bias = cw.bias; a.y = y; a.CoutV = cw.s * cw.Cout; a.LoutV = Lin + 1;
+  a.x = x; a.Cin = cw.Cin; a.Lin = Lin; a.w = cw.w2; a.wt = cw.wt; a.bias = cw.bias; a.y = y; a.CoutV = cw.s * cw.Cout; a.LoutV = Lin + 1;
   a.K = 2; a.stride = 1; a.padL = 1; a.pad_reflect = 0; a.act_in = act_in; a.res = nullptr;
   a.il_s = cw.s; a.il_cout = cw.Cout; a.il_lout = Lin * cw.s;
   const int total = cw.s;                    // k - s
@@ -591,7 +615,7 @@ int run_lstm(H* h, const LstmW& lw, float*& x, int T, Pool& pool, float* hbuf, f
   float* pre = pool.get();
   float* y = nullptr;
   for (int l = 0; l < lw.layers; ++l) {
-    ConvW ip; ip.w = lw.wih[l]; ip.bias = lw.bias[l]; ip.Cout = 4 * lw.H; ip.Cin = lw.H; ip.K = 1; ip.stride = 1;
+    ConvW ip; ip.w = lw.wih[l]; ip.wt = lw.wih_t[l]; ip.bias = lw.bias[l]; ip.Cout = 4 * lw.H; ip.Cin = lw.H; ip.K = 1; ip.stride = 1;
     TRY(run_conv(h, ip, in, T, pre, 0, nullptr, B, st));
     y = pool.get();
     const float* skip = (l == lw.layers - 1) ? x : nullptr;

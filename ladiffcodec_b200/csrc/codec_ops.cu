@@ -1,5 +1,7 @@
 // fp32 NCL kernels of the SEANet codec path (HBM/latency-bound side of the pipeline; plain SIMT fp32 so that the
 // encoder output feeding the RVQ argmax keeps fp32 fidelity).
+#include <stdlib.h>
+
 #include "codec_ops.cuh"
 
 namespace {
@@ -87,6 +89,196 @@ __global__ void __launch_bounds__(256) conv1d_f32_kernel(ConvF32Args a, int CI_T
       }
     }
   }
+}
+
+// ------------------------------------------------------------------ Conv1d, register-tiled (the fast path)
+// A strided conv (K = 2*stride in SEANet) is a stride-1 conv over S = stride "phase channels" with KT = K/S taps:
+//   y[co][t] = sum_{cv = ci*S + p} sum_{kt < KT} wt[cv*KT + kt][co] * xv[cv][t + kt],   xv[ci*S + p][u] = xpad[ci][u*S + p - padL]
+// so one kernel serves plain, strided and (phase-interleaved) transposed convs.  Block 256 = 16 (t) x 16 (co) threads; thread tile
+// RC channels x 8 consecutive positions: per phase channel the thread reads its 8+KT-1 inputs once (LDS.128) and reuses them for
+// every tap, weights come as broadcast LDS.128 -> ~0.05 shared-memory instructions per FMA.  The output tile goes through
+// shared memory so that global stores (and residual loads) are coalesced along time also for the interleaved layout.
+template <int RC, int KT>
+__global__ void __launch_bounds__(256, RC >= 8 ? 2 : 3) conv1d_f32_v2_kernel(ConvF32Args a, int CI_T, int S) {
+  extern __shared__ __align__(16) float sm2[];
+  constexpr int CO_T = 16 * RC, T_T = 128, XW = T_T + KT - 1, XWP = (XW + 3) & ~3, NX = 8 + KT - 1;
+  float* xs = sm2;                       // [CI_T][XWP]
+  float* ws = sm2 + CI_T * XWP;          // [CI_T*KT][CO_T]
+  const int b = blockIdx.z, co0 = blockIdx.y * CO_T, t0 = blockIdx.x * T_T;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float acc[RC][8];
+#pragma unroll
+  for (int i = 0; i < RC; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  const int CinV = a.Cin * S;
+  const float* xb = a.x + (long long)b * a.Cin * a.Lin;
+  const long long g_base = (long long)t0 * S - a.padL;
+  const int span = XW * S;
+  for (int cv0 = 0; cv0 < CinV; cv0 += CI_T) {
+    const int nci = min(CI_T, CinV - cv0), nreal = nci / S;
+    __syncthreads();
+    // fills: batches of independent loads (all in flight before the first shared-memory store): the layers with long time
+    // axes are latency-bound on exactly these loads
+    constexpr int FB = 8;
+    const int xtotal = nreal * span;
+    for (int i0 = tid; i0 < xtotal; i0 += 256 * FB) {
+      float v[FB];
+      int dst[FB];
+#pragma unroll
+      for (int qq = 0; qq < FB; ++qq) {
+        const int i = i0 + qq * 256;
+        v[qq] = 0.f; dst[qq] = -1;
+        if (i < xtotal) {
+          const int ci = i / span, g = i - ci * span;
+          long long gi = g_base + g;
+          if (gi < 0) gi = a.pad_reflect ? -gi : -1;
+          else if (gi >= a.Lin) gi = a.pad_reflect ? 2LL * (a.Lin - 1) - gi : -1;
+          if (gi >= 0 && gi < a.Lin) v[qq] = __ldg(xb + (long long)(cv0 / S + ci) * a.Lin + gi);
+          const int u = S == 1 ? g : g / S, ph = g - u * S;
+          dst[qq] = (ci * S + ph) * XWP + u;
+        }
+      }
+#pragma unroll
+      for (int qq = 0; qq < FB; ++qq) {
+        if (dst[qq] >= 0) {
+          float vv = v[qq];
+          if (a.act_in == 1) vv = vv > 0.f ? vv : expm1f(vv);
+          xs[dst[qq]] = vv;
+        }
+      }
+    }
+    if ((a.CoutV & 3) == 0) {
+      constexpr int WB = 4;
+      const int wtotal = nci * KT * (CO_T / 4);
+      for (int i0 = tid; i0 < wtotal; i0 += 256 * WB) {
+        float4 v[WB];
+#pragma unroll
+        for (int qq = 0; qq < WB; ++qq) {
+          const int i = i0 + qq * 256;
+          v[qq] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < wtotal) {
+            const int r = i / (CO_T / 4), c4 = i - r * (CO_T / 4), co = co0 + 4 * c4;
+            if (co < a.CoutV) v[qq] = __ldg(reinterpret_cast<const float4*>(a.wt + (long long)(cv0 * KT + r) * a.CoutV + co));
+          }
+        }
+#pragma unroll
+        for (int qq = 0; qq < WB; ++qq) {
+          const int i = i0 + qq * 256;
+          if (i < wtotal) {
+            const int r = i / (CO_T / 4), c4 = i - r * (CO_T / 4);
+            *reinterpret_cast<float4*>(ws + r * CO_T + 4 * c4) = v[qq];
+          }
+        }
+      }
+    } else {
+      for (int i = tid; i < nci * KT * CO_T; i += 256) {
+        const int r = i / CO_T, c = i - r * CO_T;
+        ws[i] = (co0 + c < a.CoutV) ? __ldg(a.wt + (long long)(cv0 * KT + r) * a.CoutV + co0 + c) : 0.f;
+      }
+    }
+    __syncthreads();
+    for (int cv = 0; cv < nci; ++cv) {
+      const float* xr = xs + cv * XWP + tx * 8;
+      float xv[NX];
+      {
+        const float4 x0 = *reinterpret_cast<const float4*>(xr), x1 = *reinterpret_cast<const float4*>(xr + 4);
+        xv[0] = x0.x; xv[1] = x0.y; xv[2] = x0.z; xv[3] = x0.w; xv[4] = x1.x; xv[5] = x1.y; xv[6] = x1.z; xv[7] = x1.w;
+#pragma unroll
+        for (int j = 8; j < NX; ++j) xv[j] = xr[j];
+      }
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
+        const float* wr = ws + (cv * KT + k) * CO_T + ty * RC;
+        float wv[RC];
+        if (RC >= 4) {
+#pragma unroll
+          for (int i4 = 0; i4 < RC / 4; ++i4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wr + 4 * i4);
+            wv[4 * i4] = w4.x; wv[4 * i4 + 1] = w4.y; wv[4 * i4 + 2] = w4.z; wv[4 * i4 + 3] = w4.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < RC; ++i) wv[i] = wr[i];
+        }
+#pragma unroll
+        for (int i = 0; i < RC; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] += wv[i] * xv[j + k];
+      }
+    }
+  }
+  // ---- epilogue: two passes of 8*RC channels through shared memory ([channel][EPW]), coalesced copy-out
+  constexpr int EPW = T_T + 4, ECH = 8 * RC;
+  float* es = sm2;
+  const int s_il = a.il_s ? a.il_s : 1;
+  const int nreal_ch = ECH / s_il;               // real channels per pass (interleave: s_il virtual channels each)
+  const int ow = T_T * s_il;                     // output positions per real channel per tile
+  for (int h = 0; h < 2; ++h) {
+    __syncthreads();
+    if ((ty >> 3) == h) {
+#pragma unroll
+      for (int i = 0; i < RC; ++i) {
+        float* er = es + ((ty & 7) * RC + i) * EPW + tx * 8;
+        *reinterpret_cast<float4*>(er) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        *reinterpret_cast<float4*>(er + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+      }
+    }
+    __syncthreads();
+    const int v0 = co0 + h * ECH;                // first virtual channel of this pass
+    const int etotal = nreal_ch * ow;
+    if (a.il_s == 0) {
+      constexpr int EB = 4;
+      for (int e0 = tid; e0 < etotal; e0 += 256 * EB) {
+        float rv[EB], bv[EB];
+        long long oo[EB];
+#pragma unroll
+        for (int qq = 0; qq < EB; ++qq) {
+          const int e = e0 + qq * 256;
+          oo[qq] = -1; rv[qq] = 0.f; bv[qq] = 0.f;
+          if (e < etotal) {
+            const int crl = e / ow, pos = e - crl * ow, vch = v0 + crl;
+            if (vch < a.CoutV && t0 + pos < a.LoutV) {
+              oo[qq] = ((long long)b * a.CoutV + vch) * a.LoutV + t0 + pos;
+              if (a.res) rv[qq] = __ldg(a.res + oo[qq]);
+              if (a.bias) bv[qq] = __ldg(a.bias + vch);
+            }
+          }
+        }
+#pragma unroll
+        for (int qq = 0; qq < EB; ++qq) {
+          const int e = e0 + qq * 256;
+          if (oo[qq] >= 0) { const int crl = e / ow, pos = e - crl * ow; a.y[oo[qq]] = es[crl * EPW + pos] + bv[qq] + rv[qq]; }
+        }
+      }
+    } else {
+      for (int e = tid; e < etotal; e += 256) {
+        const int crl = e / ow, op = e - crl * ow;
+        const int pos = op / s_il, ph = op - pos * s_il;
+        const int vch = v0 + crl * s_il + ph;
+        if (vch >= a.CoutV || t0 + pos >= a.LoutV) continue;
+        const int cr = vch / s_il;
+        const long long opos = (long long)(t0 + pos) * s_il + ph - a.il_trim;
+        if (opos >= 0 && opos < a.il_lout)
+          a.y[((long long)b * a.il_cout + cr) * a.il_lout + opos] = es[(crl * s_il + ph) * EPW + pos] + (a.bias ? __ldg(a.bias + cr) : 0.f);
+      }
+    }
+  }
+}
+
+__global__ void conv_w_transpose_kernel(const float* __restrict__ w, float* __restrict__ wt, int CoutV, int Cin, int K, int S, int perm_s,
+                                        int perm_cout) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)CoutV * Cin * K;
+  if (i >= total) return;
+  const int KT = K / S;
+  const int col = (int)(i % CoutV);
+  const long long r = i / CoutV;                 // (ci*S + p)*KT + kt
+  const int kt = (int)(r % KT);
+  const int cv = (int)(r / KT), ci = cv / S, p = cv - ci * S;
+  int co = col;
+  if (perm_s > 0) { const int cr = col / perm_s, ph = col - cr * perm_s; co = ph * perm_cout + cr; }
+  wt[i] = w[((long long)co * Cin + ci) * K + kt * S + p];
 }
 
 // ------------------------------------------------------------------ LSTM, small H: one persistent CTA per clip
@@ -497,8 +689,54 @@ __global__ void add_vec_kernel(const float* a, const float* b, float* c, int n) 
 
 }  // namespace
 
+template <int RC>
+static int conv1d_v2_dispatch(const ConvF32Args& a, int KT, int S, int B, cudaStream_t st) {
+  constexpr int CO_T = 16 * RC;
+  const int XWP = (128 + KT - 1 + 3) & ~3;
+  int CI_T = KT == 1 ? 32 : (KT == 2 ? 24 : (KT == 3 ? 16 : 8));
+  CI_T = (CI_T / S) * S;
+  if (CI_T < S) CI_T = S;
+  if (CI_T > a.Cin * S) CI_T = a.Cin * S;
+  size_t smem = (size_t)(CI_T * XWP + CI_T * KT * CO_T) * sizeof(float);
+  const size_t epi = (size_t)8 * RC * 132 * sizeof(float);
+  if (epi > smem) smem = epi;
+  LADIFF_REQUIRE(smem <= 100 * 1024, LADIFF_ERR_ARG, "conv1d_f32_v2: smem %zu", smem);
+  dim3 grid(cdiv(a.LoutV, 128), cdiv(a.CoutV, CO_T), B);
+#define LADIFF_V2_CASE(KTV)                                                                                                   \
+  case KTV: {                                                                                                                 \
+    static bool attr = false;                                                                                                 \
+    if (!attr) {                                                                                                              \
+      LADIFF_CUDA_OK(cudaFuncSetAttribute(conv1d_f32_v2_kernel<RC, KTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); \
+      attr = true;                                                                                                            \
+    }                                                                                                                         \
+    conv1d_f32_v2_kernel<RC, KTV><<<grid, 256, smem, st>>>(a, CI_T, S);                                                       \
+    break;                                                                                                                    \
+  }
+  switch (KT) {
+    LADIFF_V2_CASE(1)
+    LADIFF_V2_CASE(2)
+    LADIFF_V2_CASE(3)
+    LADIFF_V2_CASE(7)
+    default: LADIFF_REQUIRE(false, LADIFF_ERR_ARG, "conv1d_f32_v2: KT=%d", KT);
+  }
+#undef LADIFF_V2_CASE
+  LADIFF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int conv1d_f32_launch(const ConvF32Args& a, int B, cudaStream_t st) {
   LADIFF_REQUIRE(a.K >= 1 && a.K <= 64 && a.stride >= 1, LADIFF_ERR_ARG, "conv1d_f32: K=%d stride=%d", a.K, a.stride);
+  static const bool no_v2 = getenv("LADIFF_CODEC_V1") != nullptr;
+  if (a.wt && !no_v2 && a.K % a.stride == 0) {
+    const int S = a.stride, KT = a.K / S;
+    const bool il_ok = a.il_s == 0 || (a.il_s <= 8 && (8 % a.il_s) == 0);     // phases of one channel live in one thread tile / pass
+    if ((KT == 1 || KT == 2 || KT == 3 || KT == 7) && S <= 8 && il_ok) {
+      if (a.CoutV >= 128) return conv1d_v2_dispatch<8>(a, KT, S, B, st);
+      if (a.CoutV >= 64) return conv1d_v2_dispatch<4>(a, KT, S, B, st);
+      if (a.CoutV >= 32 && a.il_s <= 4) return conv1d_v2_dispatch<2>(a, KT, S, B, st);
+      if (a.il_s <= 1) return conv1d_v2_dispatch<1>(a, KT, S, B, st);
+    }
+  }
   int CI_T = 64 / a.K;
   if (CI_T > 32) CI_T = 32;
   if (CI_T < 1) CI_T = 1;
@@ -601,6 +839,14 @@ int normalize_clips_launch(float* x, int B, long long n, int mode, cudaStream_t 
 
 int weight_norm_fold_launch(const float* g, const float* v, float* w, int rows, int inner, cudaStream_t st) {
   weight_norm_fold_kernel<<<rows, 128, 0, st>>>(g, v, w, inner);
+  LADIFF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int conv_w_transpose_launch(const float* w, float* wt, int CoutV, int Cin, int K, int S, int perm_s, int perm_cout, cudaStream_t st) {
+  LADIFF_REQUIRE(S >= 1 && K % S == 0, LADIFF_ERR_ARG, "conv_w_transpose: K=%d S=%d", K, S);
+  const long long total = (long long)CoutV * Cin * K;
+  conv_w_transpose_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, wt, CoutV, Cin, K, S, perm_s, perm_cout);
   LADIFF_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -7,6 +7,7 @@
 struct ConvF32Args {
   const float* x; int Cin; int Lin;
   const float* w;          // [CoutV][Cin][K]
+  const float* wt;         // optional K-major copy for the register-tiled kernel (conv_w_transpose_launch); null: generic kernel
   const float* bias;       // [Cout real] or null
   float* y;
   int CoutV;               // (virtual) output channels computed
@@ -20,6 +21,9 @@ struct ConvF32Args {
   int il_s, il_cout, il_trim, il_lout;
 };
 int conv1d_f32_launch(const ConvF32Args& a, int B, cudaStream_t st);
+// wt[((ci*S + p)*KT + kt)][col(co)] = w[co][ci][kt*S + p], S = stride phases (K = KT*S), for the register-tiled kernel.
+// perm_s > 0 (transposed-conv virtual channels co = ph*perm_cout + cr): col = cr*perm_s + ph (phase fastest), else col = co.
+int conv_w_transpose_launch(const float* w, float* wt, int CoutV, int Cin, int K, int S, int perm_s, int perm_cout, cudaStream_t st);
 
 // nn.LSTM layer recurrence given pre[b][4H][T] = W_ih x_t + b_ih + b_hh (PyTorch gate order i,f,g,o; lstm.py:20)
 //   y[b][j][t] = h_t[j] (+ skip[b][j][t]).  small H (64/128): one persistent CTA per clip.

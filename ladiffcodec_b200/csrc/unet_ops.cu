@@ -226,20 +226,32 @@ __global__ void __launch_bounds__(256) linattn_ctx_kernel(ClView qkv, float* __r
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   __shared__ __align__(16) float ks[LA_S][32];
   __shared__ __align__(16) float vs[LA_S][32];
-  __shared__ float red[8][32];
+  __shared__ __align__(16) float red[8][32];
   __shared__ float m_s[32], z_s[32];
   __shared__ int is_last;
   const int n_lo = sp * S, cnt = min(L, n_lo + S) - n_lo;
   {
+    // 8 threads per row: 4 x 16 B of k, 4 x 16 B of v; all (<= LA_S/32) row loads of a thread are issued before the first use
     const int c = tid & 7;
     const bf16* base = qkv.p + (long long)b * qkv.bstride + (c < 4 ? 128 : 256) + h * 32 + (c & 3) * 8;
     float (*dst)[32] = c < 4 ? ks : vs;
-    for (int i = tid >> 3; i < cnt; i += 32) {
-      float f[8];
-      unpack8(*reinterpret_cast<const uint4*>(base + (long long)(n_lo + i) * qkv.pitch), f);
-      float4* d4 = reinterpret_cast<float4*>(&dst[i][(c & 3) * 8]);
-      d4[0] = make_float4(f[0], f[1], f[2], f[3]);
-      d4[1] = make_float4(f[4], f[5], f[6], f[7]);
+    constexpr int NB = LA_S / 32;
+    uint4 raw[NB];
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      const int i = (tid >> 3) + 32 * k;
+      if (i < cnt) raw[k] = __ldcg(reinterpret_cast<const uint4*>(base + (long long)(n_lo + i) * qkv.pitch));
+    }
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      const int i = (tid >> 3) + 32 * k;
+      if (i < cnt) {
+        float f[8];
+        unpack8(raw[k], f);
+        float4* d4 = reinterpret_cast<float4*>(&dst[i][(c & 3) * 8]);
+        d4[0] = make_float4(f[0], f[1], f[2], f[3]);
+        d4[1] = make_float4(f[4], f[5], f[6], f[7]);
+      }
     }
   }
   __syncthreads();
@@ -256,7 +268,7 @@ __global__ void __launch_bounds__(256) linattn_ctx_kernel(ClView qkv, float* __r
   m = m_s[lane];
   float z = 0.f;
   for (int i = warp; i < cnt; i += 8) {
-    const float pe = expf(ks[i][lane] - m);
+    const float pe = __expf(ks[i][lane] - m);
     ks[i][lane] = pe;
     z += pe;
   }
@@ -269,68 +281,110 @@ __global__ void __launch_bounds__(256) linattn_ctx_kernel(ClView qkv, float* __r
     for (int w = 0; w < 8; ++w) zz += red[w][lane];
     z_s[lane] = zz;
   }
-  const int d = tid >> 3, e4 = (tid & 7) * 4;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int i = 0; i < cnt; ++i) {
-    const float pe = ks[i][d];
+  // ctx partial: 4 row groups x 64 threads, each thread a 4 (d) x 4 (e) register tile -> 2 LDS.128 per 16 FMA
+  const int rg = tid >> 6, tt = tid & 63, d4 = (tt >> 3) * 4, e4 = (tt & 7) * 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int i = rg; i < cnt; i += 4) {
+    const float4 pe = *reinterpret_cast<const float4*>(&ks[i][d4]);
     const float4 v = *reinterpret_cast<const float4*>(&vs[i][e4]);
-    acc.x += pe * v.x; acc.y += pe * v.y; acc.z += pe * v.z; acc.w += pe * v.w;
+    acc[0][0] += pe.x * v.x; acc[0][1] += pe.x * v.y; acc[0][2] += pe.x * v.z; acc[0][3] += pe.x * v.w;
+    acc[1][0] += pe.y * v.x; acc[1][1] += pe.y * v.y; acc[1][2] += pe.y * v.z; acc[1][3] += pe.y * v.w;
+    acc[2][0] += pe.z * v.x; acc[2][1] += pe.z * v.y; acc[2][2] += pe.z * v.z; acc[2][3] += pe.z * v.w;
+    acc[3][0] += pe.w * v.x; acc[3][1] += pe.w * v.y; acc[3][2] += pe.w * v.z; acc[3][3] += pe.w * v.w;
+  }
+  __syncthreads();          // everyone is done with ks/vs: row groups 1..3 park their tiles in vs, group 0 sums them in order
+  float* pool = &vs[0][0];  // [3][32][32]
+  if (rg > 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<float4*>(pool + ((rg - 1) * 32 + d4 + i) * 32 + e4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
   }
   __syncthreads();
   const float scale = 0.17677669529663687f;  // 32^-0.5 (q * scale, unet.py:216)
-  float* cout = ctx + (((long long)b * 4 + h) * 32 + d) * 32 + e4;
-  if (nsplit == 1) {
-    const float inv = scale / z_s[d];
-    *reinterpret_cast<float4*>(cout) = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
-    return;
+  if (rg == 0) {
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 o = *reinterpret_cast<const float4*>(pool + (g * 32 + d4 + i) * 32 + e4);
+        acc[i][0] += o.x; acc[i][1] += o.y; acc[i][2] += o.z; acc[i][3] += o.w;
+      }
+    if (nsplit == 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float inv = scale / z_s[d4 + i];
+        *reinterpret_cast<float4*>(ctx + (((long long)b * 4 + h) * 32 + d4 + i) * 32 + e4) =
+            make_float4(acc[i][0] * inv, acc[i][1] * inv, acc[i][2] * inv, acc[i][3] * inv);
+      }
+    } else {
+      float* pp = part + (((long long)b * 4 + h) * nsplit + sp) * LA_PART;
+      if (tt < 32) { pp[tt] = m_s[tt]; pp[32 + tt] = z_s[tt]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<float4*>(pp + 64 + (d4 + i) * 32 + e4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
   }
-  float* pp = part + (((long long)b * 4 + h) * nsplit + sp) * LA_PART;
-  if (tid < 32) { pp[tid] = m_s[tid]; pp[32 + tid] = z_s[tid]; }
-  *reinterpret_cast<float4*>(pp + 64 + d * 32 + e4) = acc;
+  if (nsplit == 1) return;
   __threadfence();
   __syncthreads();
   if (tid == 0) is_last = atomicAdd(&counters[b * 4 + h], 1) == nsplit - 1;
   __syncthreads();
   if (!is_last) return;
   __threadfence();
+  // the last CTA of this (clip, head) merges the segment partials in segment order (independent of CTA scheduling)
+  const int d = tid >> 3, ee = (tid & 7) * 4;
   const float* p0 = part + ((long long)b * 4 + h) * nsplit * LA_PART;
   float M = -INFINITY;
-  for (int s = 0; s < nsplit; ++s) M = fmaxf(M, __ldcg(p0 + (long long)s * LA_PART + d));
+  for (int s2 = 0; s2 < nsplit; ++s2) M = fmaxf(M, __ldcg(p0 + (long long)s2 * LA_PART + d));
   float Z = 0.f;
-  acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int s = 0; s < nsplit; ++s) {
-    const float* ps = p0 + (long long)s * LA_PART;
-    const float w = expf(__ldcg(ps + d) - M);
+  float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s2 = 0; s2 < nsplit; ++s2) {
+    const float* ps = p0 + (long long)s2 * LA_PART;
+    const float w = __expf(__ldcg(ps + d) - M);
     Z += w * __ldcg(ps + 32 + d);
-    const float4 c = __ldcg(reinterpret_cast<const float4*>(ps + 64 + d * 32 + e4));
-    acc.x += w * c.x; acc.y += w * c.y; acc.z += w * c.z; acc.w += w * c.w;
+    const float4 c = __ldcg(reinterpret_cast<const float4*>(ps + 64 + d * 32 + ee));
+    a4.x += w * c.x; a4.y += w * c.y; a4.z += w * c.z; a4.w += w * c.w;
   }
   const float inv = scale / Z;
-  *reinterpret_cast<float4*>(cout) = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+  *reinterpret_cast<float4*>(ctx + (((long long)b * 4 + h) * 32 + d) * 32 + ee) = make_float4(a4.x * inv, a4.y * inv, a4.z * inv, a4.w * inv);
   if (tid == 0) counters[b * 4 + h] = 0;     // ready for the next launch on this stream
 }
 
 // out[b][n][h*32+e] = sum_d ctx[h][d][e] softmax_d(q[n,h,:])[d]      grid (ceil(L/64), B), 256 threads
-// warp w: head w&3, rows 32*(w>>2) + lane; one (row, head) per thread: q row in registers, ctx broadcast from smem
-__global__ void __launch_bounds__(256) linattn_out_kernel(ClView qkv, const float* __restrict__ ctx, ClView out, int L) {
-  pdl_wait();
-  pdl_trigger();
+// warp w: head w&3, rows 32*(w>>2) + lane; one (row, head) per thread: q row in registers (requested before the ctx tile
+// is staged, so both round trips overlap), ctx broadcast from smem
+__global__ void __launch_bounds__(256, 3) linattn_out_kernel(ClView qkv, const float* __restrict__ ctx, ClView out, int L) {
   const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __shared__ __align__(16) float cs[4][32][32];
+  const int h = warp & 3, n = blockIdx.x * 64 + (warp >> 2) * 32 + lane;
+  pdl_wait();
+  pdl_trigger();
+  uint4 qraw[4];
+  if (n < L) {
+    const bf16* qr = qkv.p + (long long)b * qkv.bstride + (long long)n * qkv.pitch + h * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) qraw[i] = __ldcg(reinterpret_cast<const uint4*>(qr + 8 * i));
+  }
   {
     const float4* src = reinterpret_cast<const float4*>(ctx + (long long)b * 4096);
     float4* dst = reinterpret_cast<float4*>(&cs[0][0][0]);
-    for (int i = threadIdx.x; i < 1024; i += 256) dst[i] = src[i];
+    float4 t4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t4[i] = __ldcg(src + threadIdx.x + 256 * i);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[threadIdx.x + 256 * i] = t4[i];
   }
   __syncthreads();
-  const int h = warp & 3, n = blockIdx.x * 64 + (warp >> 2) * 32 + lane;
   if (n >= L) return;
-  const bf16* qr = qkv.p + (long long)b * qkv.bstride + (long long)n * qkv.pitch + h * 32;
   float q[32];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float f[8];
-    unpack8(*reinterpret_cast<const uint4*>(qr + 8 * i), f);
+    unpack8(qraw[i], f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) q[8 * i + j] = f[j];
   }
@@ -339,12 +393,12 @@ __global__ void __launch_bounds__(256) linattn_out_kernel(ClView qkv, const floa
   for (int i = 1; i < 32; ++i) mx = fmaxf(mx, q[i]);
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) { q[i] = expf(q[i] - mx); sum += q[i]; }
+  for (int i = 0; i < 32; ++i) { q[i] = __expf(q[i] - mx); sum += q[i]; }
   const float inv = 1.f / sum;
   float acc[32];
 #pragma unroll
   for (int e = 0; e < 32; ++e) acc[e] = 0.f;
-#pragma unroll 4
+#pragma unroll
   for (int d = 0; d < 32; ++d) {
     const float pd = q[d] * inv;
     const float4* c4 = reinterpret_cast<const float4*>(&cs[h][d][0]);
