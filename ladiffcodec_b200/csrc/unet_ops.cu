@@ -1,6 +1,4 @@
 // Element-wise / normalisation / attention kernels of the UNet (channels-last bf16, fp32 math).
-#include <curand_kernel.h>
-
 #include "unet_ops.cuh"
 
 namespace {
@@ -538,6 +536,27 @@ __global__ void __launch_bounds__(1024) absmax_inv_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------ DDPM posterior step
+// Counter-based noise for the throughput mode: Philox4x32-10 (Salmon et al., SC'11) keyed by the seed, counter =
+// (thread's first element index, step); one call yields the four normals (Box-Muller) of the thread's four elements.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
+  const float u1 = ((float)a + 1.f) * 2.3283064365386963e-10f;     // (0, 1]
+  const float u2 = (float)b * 2.3283064365386963e-10f;              // [0, 1)
+  const float r = sqrtf(-2.f * __logf(u1));
+  float sn, cs;
+  __sincosf(6.283185307179586f * u2, &sn, &cs);
+  n0 = r * cs; n1 = r * sn;
+}
+
 // grid (ceil(L/32), C/32, B), block (32, 8)
 __global__ void ddpm_step_kernel(const float* __restrict__ eps, float* __restrict__ x, const float* __restrict__ noise,
                                  unsigned long long seed, int step_index, const int* __restrict__ t_dev, DdpmTables tb,
@@ -546,37 +565,47 @@ __global__ void ddpm_step_kernel(const float* __restrict__ eps, float* __restric
   const int b = blockIdx.z, c0 = blockIdx.y * 32, l0 = blockIdx.x * 32;
   const int ti = t_dev[b];
   const float a = tb.sqrt_recip_ac[ti], bb = tb.sqrt_recipm1_ac[ti], c1 = tb.coef1[ti], c2 = tb.coef2[ti];
-  const float sigma = ti > 0 ? expf(0.5f * tb.logvar[ti]) : 0.f;
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int l = l0 + i;
-    t[i][threadIdx.x] = (l < L) ? eps[((long long)b * L + l) * C + c0 + threadIdx.x] : 0.f;   // t[l][c]
+  const float sigma = ti > 0 ? __expf(0.5f * tb.logvar[ti]) : 0.f;
+  float ev[4], xv[4], zv[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = threadIdx.y + 8 * k, l = l0 + i;
+    ev[k] = (l < L) ? __ldcg(eps + ((long long)b * L + l) * C + c0 + threadIdx.x) : 0.f;   // t[l][c]
+  }
+  const int lx = l0 + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + threadIdx.y + 8 * k;
+    const long long idx = ((long long)b * C + c) * L + lx;
+    xv[k] = (lx < L) ? x[idx] : 0.f;
+    if (ti > 0 && noise && lx < L) zv[k] = __ldg(noise + idx);
+  }
+  if (ti > 0 && !noise) {
+    const unsigned long long first = ((unsigned long long)b * C + c0 + threadIdx.y) * (unsigned long long)L + lx;
+    const uint4 rnd = philox4x32_10(make_uint4((uint32_t)first, (uint32_t)(first >> 32), (uint32_t)step_index, 0x1ad1ffu),
+                                    make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    box_muller(rnd.x, rnd.y, zv[0], zv[1]);
+    box_muller(rnd.z, rnd.w, zv[2], zv[3]);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) t[threadIdx.y + 8 * k][threadIdx.x] = ev[k];
+  __syncthreads();
+  float xn[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = threadIdx.y + 8 * k;
+    float x0 = a * xv[k] - bb * t[threadIdx.x][i];
+    x0 = fminf(fmaxf(x0, -1.f), 1.f);
+    xn[k] = c1 * x0 + c2 * xv[k] + sigma * zv[k];
+    if (lx < L) x[((long long)b * C + c0 + i) * L + lx] = xn[k];
   }
   __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int c = c0 + i, l = l0 + threadIdx.x;
-    float xn = 0.f;
-    if (l < L) {
-      const long long idx = ((long long)b * C + c) * L + l;
-      const float xv = x[idx];
-      float x0 = a * xv - bb * t[threadIdx.x][i];
-      x0 = fminf(fmaxf(x0, -1.f), 1.f);
-      float z = 0.f;
-      if (ti > 0) {
-        if (noise) z = noise[idx];
-        else {
-          curandStatePhilox4_32_10_t st;
-          curand_init(seed, (unsigned long long)idx, (unsigned long long)step_index, &st);
-          z = curand_normal(&st);
-        }
-      }
-      xn = c1 * x0 + c2 * xv + sigma * z;
-      x[idx] = xn;
-    }
-    t[threadIdx.x][i] = xn;  // t[l][c]: same thread read this element above, no cross-thread hazard
-  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) t[threadIdx.x][threadIdx.y + 8 * k] = lx < L ? xn[k] : 0.f;   // t[l][c]
   __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int l = l0 + i;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = threadIdx.y + 8 * k, l = l0 + i;
     if (l < L) xin.p[(long long)b * xin.bstride + (long long)l * xin.pitch + c0 + threadIdx.x] = __float2bfloat16(t[i][threadIdx.x]);
   }
 }

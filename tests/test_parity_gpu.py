@@ -124,6 +124,34 @@ def test_ddpm_trajectory(case):
     assert torch.equal(x.cpu(), lat)
 
 
+def test_in_kernel_noise_is_standard_normal_and_seeded(case):
+    """Throughput mode (noise=None): the posterior step draws z from the in-kernel counter-based generator.  With the same
+    x and eps, x_noisy - x_zero_noise = sigma_t * z, so z is recovered exactly enough to check its first moments, that it is a
+    function of the seed only, and that different seeds / steps give different draws."""
+    m, fx = case["m"], case["fx"]
+    img, _ = _unet_inputs(case)
+    cond = fx["cond"].cuda()
+    t = 40
+    B, C, L = img.shape
+    base, _ = m.diffusion.p_sample(img.cuda(), t, cond, noise=torch.zeros(1, B, C, L))
+    a, _ = m.diffusion.p_sample(img.cuda(), t, cond, noise=None, seed=7)
+    b, _ = m.diffusion.p_sample(img.cuda(), t, cond, noise=None, seed=7)
+    c, _ = m.diffusion.p_sample(img.cuda(), t, cond, noise=None, seed=8)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    sigma = float(torch.exp(0.5 * case["sdm"]["diffusion.posterior_log_variance_clipped"][t]))
+    z = ((a - base) / sigma).double().flatten().cpu()
+    n = z.numel()
+    assert abs(z.mean().item()) < 6.0 / n ** 0.5
+    assert abs(z.var().item() - 1.0) < 6.0 * (2.0 / n) ** 0.5 + 1e-3
+    assert abs((z ** 3).mean().item()) < 6.0 * (15.0 / n) ** 0.5 + 1e-3          # skewness of N(0,1) is 0
+    assert abs((z ** 4).mean().item() - 3.0) < 6.0 * (96.0 / n) ** 0.5 + 1e-2    # kurtosis 3
+    zc = ((c - base) / sigma).double().flatten().cpu()
+    assert abs(float((z * zc).mean())) < 6.0 / n ** 0.5                           # seeds are uncorrelated
+    zz = z.reshape(B, C, L)
+    assert abs(float((zz[:, :, 1:] * zz[:, :, :-1]).mean())) < 6.0 / n ** 0.5     # neighbours along time
+    assert abs(float((zz[:, 8:, :] * zz[:, :-8, :]).mean())) < 6.0 / n ** 0.5     # the four elements of one generator call
+
+
 def test_decoder(case):
     m, args = case["m"], case["args"]
     img, _ = _unet_inputs(case)
