@@ -241,10 +241,17 @@ def run_ours(a, cfg):
     value, e2e = audio_s / (ms / 1e3), audio_s / (ms_e2e / 1e3)
     pk = peaks()
     roof = None
+    traffic, traffic_note = None, None
+    tp = os.path.join(ROOT, "profiles", "r1c", "conv_dram_traffic.json")
+    if a.config == 2 and not a.batch and os.path.exists(tp):      # committed ncu capture of the same workload (per launch, like `achieved`)
+        t = json.load(open(tp))
+        traffic = (t["dram_read_bytes"] + t["dram_write_bytes"]) / t["conv_launches"]
+        traffic_note = (f"profiles/r1c/conv_dram_traffic.json: DRAM bytes per conv launch, mean over the {t['conv_launches']} launches of one UNet "
+                        f"evaluation (ncu flushes L2 before each launch; L2->SM traffic {t['l2_bytes'] / t['conv_launches'] / 1e6:.0f} MB per launch)")
     if prof and prof["conv_ms"] > 0:
         ach = prof["conv_flops"] / (prof["conv_ms"] * 1e-3) / 1e12
         roof = dict(bound="tensor", kernel="tc_conv_kernel (tcgen05 implicit-GEMM Conv1d)", achieved=ach, peak=pk["bf16_sustained"],
-                    unit="TFLOP/s", frac=ach / pk["bf16_sustained"], traffic=None, peak_source=pk["src"] + " bf16 sustained",
+                    unit="TFLOP/s", frac=ach / pk["bf16_sustained"], traffic=traffic, traffic_source=traffic_note, peak_source=pk["src"] + " bf16 sustained",
                     launches_per_unet_eval=prof["conv_launches"], conv_ms_per_unet_eval=prof["conv_ms"],
                     unet_eval_ms=prof["eval_ms"], algorithmic_gflop_per_clip_eval=prof["conv_flops"] / B / 1e9,
                     how="CUDA events around each of the conv launches of one UNet evaluation, eager pass right after the timed region "

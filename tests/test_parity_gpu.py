@@ -255,3 +255,50 @@ def test_tc_conv_operator_shapes():
                 tol = 2e-4 if f32 else 2e-4 + ref.abs().max().item() * 2 ** -8       # bf16 output rounding
                 assert (y.float().cpu() - ref).abs().max().item() < tol, (B, L, Cin, Cout, k, impl, f32)
                 assert (st[:, :, 0].cpu() - s_ref).abs().max().item() < 1e-2 * max(1.0, s_ref.abs().max().item())
+
+
+def test_full_size_properties_config2():
+    """BASELINE config 2 at its full size (B = 32 clips of 2.4 s, enc_ratios [8,4], L = 1200), through properties that do not
+    need the oracle at that size: RVQ round trip bit-exact, tcgen05 vs the SIMT check kernel on one UNet evaluation,
+    clip-permutation equivariance and sub-batch invariance of the whole path, output normalisation."""
+    import bench
+    from ladiffcodec_b200.sample import synthesize
+    cfg = bench.CONFIGS[2]
+    args, sdm, sdc = bench.build_state(cfg)
+    m, c = pc.cuda_models(args, sdm, sdc)
+    B, T, n_steps = cfg["batch"], bench.T_SAMPLES, 3
+    wav = make_clips_cached(B, T)
+    L = T // 32
+    g = torch.Generator().manual_seed(99)
+    noise = torch.randn(n_steps - 1, B, 128, L, generator=g)
+    # RVQ: codes -> decode reproduces the quantized tensor bit for bit at full size
+    cond, codes = c.get_cond(wav.cuda(), return_codes=True)
+    assert codes.shape == (6, B, T // 320) and int(codes.min()) >= 0 and int(codes.max()) < 1024
+    assert torch.equal(c.quantizer.decode(codes), cond)
+    # one UNet evaluation: tensor-core path vs SIMT check kernel (same bf16 operands, different accumulation order)
+    img = cond
+    for layer in m.diff_model.upsampling_layers:
+        img = layer(img)
+    img = img / (img.abs().reshape(B, -1).max(1).values.reshape(B, 1, 1) + 1e-8)
+    tt = torch.full((B,), 17, dtype=torch.long, device="cuda")
+    e_tc = m.diff_model(img, tt, cond)
+    m.set_conv_impl(1)
+    e_simt = m.diff_model(img, tt, cond)
+    m.set_conv_impl(0)
+    assert pc.rel_l2(e_tc, e_simt) <= pc.TOL["unet_simt_vs_tc_rel_l2"]     # bf16 activations: rounding flips, not a bias
+    # whole path: permuting the clips permutes the outputs; a sub-batch reproduces its clips
+    out = synthesize(m, c, wav.cuda(), n_steps=n_steps, noise=noise)
+    assert out.shape == (B, 1, T) and bool(torch.isfinite(out).all())
+    assert out.abs().reshape(B, -1).max(1).values.sub(1.0).abs().max().item() < 1e-5
+    perm = torch.randperm(B, generator=g)
+    out_p = synthesize(m, c, wav[perm].cuda(), n_steps=n_steps, noise=noise[:, perm])
+    assert pc.snr_db(out_p, out[perm]) > 55.0
+    sub = synthesize(m, c, wav[:4].cuda(), n_steps=n_steps, noise=noise[:, :4])
+    assert pc.snr_db(sub, out[:4]) > 55.0
+    del m, c
+    torch.cuda.empty_cache()
+
+
+def make_clips_cached(B, T):
+    from ladiffcodec_b200.synthetic import make_clips
+    return make_clips(B, T, seed=4242)
