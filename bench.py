@@ -167,6 +167,8 @@ def run_ours(a, cfg):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):    # keeps stdout to the ONE JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from ladiffcodec_b200.layout import ladiff_model_kwargs, cond_model_kwargs
     from ladiffcodec_b200.model import DiffAudioRep
