@@ -142,7 +142,15 @@ int32_t ladiff_synthesize(LadiffHandle* model, LadiffHandle* cond_model, const f
                           uint64_t seed, float* wav_out, float* latent_out, void* ws, int64_t ws_bytes,
                           void* stream);
 
-/* Scratch needed by ladiff_synthesize for this pair of models. */
+/* The same, starting from the codec payload (the receiver of the 1.5/3 kbps stream): codes [n_q,B,F] int64 RVQ
+ * indices (quantizer.decode, srcs/quantization/vq.py:108-113 → core_vq.py:356-362) instead of a waveform;
+ * decodes T = 320·F samples.  Bit-identical to ladiff_synthesize on the waveform those codes came from. */
+int32_t ladiff_synthesize_codes(LadiffHandle* model, LadiffHandle* cond_model, const int64_t* codes, int32_t n_q,
+                                int32_t B, int32_t F, int32_t n_steps, const float* noise, int64_t n_noise,
+                                uint64_t seed, float* wav_out, float* latent_out, void* ws, int64_t ws_bytes,
+                                void* stream);
+
+/* Scratch needed by ladiff_synthesize / ladiff_synthesize_codes for this pair of models. */
 int64_t ladiff_synthesize_workspace_bytes(const LadiffHandle* model, const LadiffHandle* cond_model,
                                           int32_t B, int32_t T);
 

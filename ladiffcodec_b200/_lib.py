@@ -48,6 +48,7 @@ SIGNATURES = {
     "ladiff_ddpm_steps": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_u64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp]),
     "ladiff_decode": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_i64, c_vp]),
     "ladiff_synthesize": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_i64, c_u64, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "ladiff_synthesize_codes": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_u64, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "ladiff_normalize_clips": (c_i32, [c_vp, c_i32, c_i64, c_i32, c_vp]),
     "ladiff_op_conv1d_cl": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp]),
     "ladiff_set_conv_impl": (c_i32, [c_vp, c_i32]),

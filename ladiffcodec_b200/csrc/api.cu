@@ -1276,27 +1276,14 @@ extern "C" int32_t ladiff_normalize_clips(float* x, int32_t B, int64_t n, int32_
   return normalize_clips_launch(x, B, n, mode, (cudaStream_t)stream);
 }
 
-extern "C" int32_t ladiff_synthesize(LadiffHandle* m, LadiffHandle* cm, const float* wav_in, int32_t B, int32_t T, int32_t n_steps,
-                                     const float* noise, int64_t n_noise, uint64_t seed, float* wav_out, float* latent_out, void* ws,
-                                     int64_t ws_bytes, void* stream) {
-  STAGE_PROLOGUE(m);
-  LADIFF_REQUIRE(cm && cm->finalized, LADIFF_ERR_STATE, "conditioning model not finalized");
-  LADIFF_REQUIRE(m->cfg.run_diff && cm->cfg.quantization, LADIFF_ERR_STATE, "synthesize needs a diffusion model and a quantising cond codec");
-  LADIFF_REQUIRE(wav_in && wav_out && B > 0 && T > 0 && T % 640 == 0, LADIFF_ERR_ARG,
-                 "ladiff_synthesize: T=%d must be a multiple of 640 (sample.py:87)", T);
-  LADIFF_REQUIRE(T % m->enc_hop == 0 && T % cm->enc_hop == 0, LADIFF_ERR_ARG, "T=%d is not a multiple of the codec hops", T);
-  const int L = T / m->enc_hop, F = T / cm->enc_hop;
-  const size_t pb = persist_bytes(B, T, L);
-  TRY(check_ws(ws, ws_bytes, (size_t)ladiff_synthesize_workspace_bytes(m, cm, B, T)));
-  Bump bp(ws);
-  float* cond = bp.get<float>((size_t)B * 128 * F);
+// common tail of the two synthesis entry points: cond [B][128][F] (persist region) -> wav_out
+static int synth_from_cond(LadiffHandle* m, const float* cond, int B, int T, int n_steps, const float* noise, int64_t n_noise, uint64_t seed,
+                           float* wav_out, float* latent_out, Bump bp, void* scratch, cudaStream_t st) {
+  const int L = T / m->enc_hop, F = T / 320;
   float* x = latent_out ? latent_out : bp.get<float>((size_t)B * 128 * L);
   float* ta = bp.get<float>((size_t)B * 128 * L);
   float* tb = bp.get<float>((size_t)B * 128 * L);
-  void* scratch = (char*)ws + pb;
-  const int64_t scratch_bytes = ws_bytes - (int64_t)pb;
-  TRY(ladiff_get_cond(cm, wav_in, B, T, cond, nullptr, nullptr, scratch, scratch_bytes, stream));       // sample.py:94
-  TRY(run_cond_upsample(m, cond, B, F, x, ta, tb, st));                                                 // :125-128
+  TRY(run_cond_upsample(m, cond, B, F, x, ta, tb, st));                                                 // sample.py:125-128
   TRY(normalize_clips_launch(x, B, (long long)128 * L, 0, st));                                         // :129
   Plan* pl = nullptr;
   TRY(build_plan(m, scratch, B, L, st, &pl));
@@ -1305,6 +1292,46 @@ extern "C" int32_t ladiff_synthesize(LadiffHandle* m, LadiffHandle* cm, const fl
   TRY(normalize_clips_launch(wav_out, B, T, 1, st));                                                    // :133-134
   m->launches += 2;
   return 0;
+}
+
+extern "C" int32_t ladiff_synthesize(LadiffHandle* m, LadiffHandle* cm, const float* wav_in, int32_t B, int32_t T, int32_t n_steps,
+                                     const float* noise, int64_t n_noise, uint64_t seed, float* wav_out, float* latent_out, void* ws,
+                                     int64_t ws_bytes, void* stream) {
+  STAGE_PROLOGUE(m);
+  LADIFF_REQUIRE(cm && cm->finalized, LADIFF_ERR_STATE, "conditioning model not finalized");
+  LADIFF_REQUIRE(m->cfg.run_diff && cm->cfg.quantization, LADIFF_ERR_STATE, "synthesize needs a diffusion model and a quantising cond codec");
+  LADIFF_REQUIRE(wav_in && wav_out && B > 0 && T > 0 && T % 640 == 0, LADIFF_ERR_ARG,
+                 "ladiff_synthesize: T=%d must be a multiple of 640 (sample.py:87)", T);
+  LADIFF_REQUIRE(T % m->enc_hop == 0 && T % cm->enc_hop == 0 && cm->enc_hop == 320, LADIFF_ERR_ARG, "T=%d is not a multiple of the codec hops", T);
+  const int L = T / m->enc_hop, F = T / cm->enc_hop;
+  const size_t pb = persist_bytes(B, T, L);
+  TRY(check_ws(ws, ws_bytes, (size_t)ladiff_synthesize_workspace_bytes(m, cm, B, T)));
+  Bump bp(ws);
+  float* cond = bp.get<float>((size_t)B * 128 * F);
+  void* scratch = (char*)ws + pb;
+  TRY(ladiff_get_cond(cm, wav_in, B, T, cond, nullptr, nullptr, scratch, ws_bytes - (int64_t)pb, stream));   // sample.py:94
+  return synth_from_cond(m, cond, B, T, n_steps, noise, n_noise, seed, wav_out, latent_out, bp, scratch, st);
+}
+
+// Receiver side of the codec: the conditioning arrives as RVQ indices instead of a waveform.
+extern "C" int32_t ladiff_synthesize_codes(LadiffHandle* m, LadiffHandle* cm, const int64_t* codes, int32_t n_q, int32_t B, int32_t F,
+                                           int32_t n_steps, const float* noise, int64_t n_noise, uint64_t seed, float* wav_out,
+                                           float* latent_out, void* ws, int64_t ws_bytes, void* stream) {
+  STAGE_PROLOGUE(m);
+  LADIFF_REQUIRE(cm && cm->finalized, LADIFF_ERR_STATE, "conditioning model not finalized");
+  LADIFF_REQUIRE(m->cfg.run_diff && cm->cfg.quantization, LADIFF_ERR_STATE, "synthesize needs a diffusion model and a quantising cond codec");
+  LADIFF_REQUIRE(codes && wav_out && B > 0 && F > 0 && F % 2 == 0 && n_q >= 1 && n_q <= cm->cfg.n_q, LADIFF_ERR_ARG,
+                 "ladiff_synthesize_codes: n_q=%d F=%d (F must be even: the script decodes multiples of 640 samples)", n_q, F);
+  const int T = F * 320;
+  LADIFF_REQUIRE(T % m->enc_hop == 0, LADIFF_ERR_ARG, "T=%d is not a multiple of the decoder hop", T);
+  const int L = T / m->enc_hop;
+  const size_t pb = persist_bytes(B, T, L);
+  TRY(check_ws(ws, ws_bytes, (size_t)ladiff_synthesize_workspace_bytes(m, cm, B, T)));
+  Bump bp(ws);
+  float* cond = bp.get<float>((size_t)B * 128 * F);
+  void* scratch = (char*)ws + pb;
+  TRY(ladiff_rvq_decode(cm, codes, n_q, B, F, cond, stream));                                           // vq.py:108-113
+  return synth_from_cond(m, cond, B, T, n_steps, noise, n_noise, seed, wav_out, latent_out, bp, scratch, st);
 }
 
 extern "C" int32_t ladiff_set_conv_impl(LadiffHandle* h, int32_t impl) {

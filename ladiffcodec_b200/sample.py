@@ -77,6 +77,33 @@ def synthesize(model, model_for_cond, wav, n_steps=MIDWAY_T, noise=None, seed=0,
     return (out, latent) if return_latent else out
 
 
+@torch.no_grad()
+def synthesize_from_codes(model, model_for_cond, codes, n_steps=MIDWAY_T, noise=None, seed=0, return_latent=False):
+    """Receiver side: `codes` [n_q,B,F] int64 RVQ indices (what ``get_cond(..., return_codes=True)`` /
+    ``quantizer.encode`` produce, vq.py:100-106) → de-quantised waveform [B,1,320·F].  Same path as ``synthesize`` after
+    the conditioning codec's encoder: quantizer.decode → upsample → normalise → halfway_sampling → decoder → normalise."""
+    dev = model.device
+    codes = codes.to(device=dev, dtype=torch.int64).contiguous()
+    if codes.dim() != 3:
+        raise ValueError("codes must be [n_q,B,F]")
+    n_q, B, F = codes.shape
+    T = 320 * F
+    L = T // model.decoder.hop_length
+    out = torch.empty(B, 1, T, device=dev)
+    latent = torch.empty(B, model.cfg["rep_dims"], L, device=dev) if return_latent else None
+    n_noise = 0
+    if noise is not None:
+        noise = noise.to(device=dev, dtype=torch.float32).contiguous()
+        if noise.dim() != 4 or tuple(noise.shape[1:]) != (B, model.cfg["rep_dims"], L):
+            raise ValueError(f"noise must be [n,{B},{model.cfg['rep_dims']},{L}], got {tuple(noise.shape)}")
+        n_noise = noise.shape[0]
+    ws = model._workspace(B, T, other=model_for_cond)
+    _lib.check(model._lib.ladiff_synthesize_codes(model._h, model_for_cond._h, _ptr(codes), int(n_q), B, F, int(n_steps), _ptr(noise),
+                                                  n_noise, ctypes.c_uint64(seed), _ptr(out), _ptr(latent), _ptr(ws), ws.numel(),
+                                                  _stream()), "synthesize_from_codes")
+    return (out, latent) if return_latent else out
+
+
 def _load_wav(path):
     """torchaudio.load (sample.py:83) with a scipy fallback for images without TorchCodec."""
     try:

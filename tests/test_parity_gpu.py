@@ -182,6 +182,22 @@ def test_synthesize_matches_reference_waveform(case):
     assert fx["n_steps"] < 2 or not torch.equal(a, d)
 
 
+def test_codes_in_decode_is_bit_identical(case):
+    """decoding from the RVQ indices (the codec's wire payload) gives exactly the samples of the
+    waveform-in path, and the indices are the oracle's."""
+    from ladiffcodec_b200.sample import synthesize, synthesize_from_codes
+    m, c, fx = case["m"], case["c"], case["fx"]
+    _, codes = c.get_cond(case["wav"].cuda(), return_codes=True)
+    with torch.no_grad():
+        codes_o = O.get_cond(case["wav"], case["sdc"], case["args"].cond_bandwidth, return_codes=True)[1]
+    assert torch.equal(codes.cpu(), codes_o)
+    a, la = synthesize(m, c, case["wav"].cuda(), n_steps=fx["n_steps"], noise=case["noise"], return_latent=True)
+    b, lb = synthesize_from_codes(m, c, codes, n_steps=fx["n_steps"], noise=case["noise"], return_latent=True)
+    assert torch.equal(a, b) and torch.equal(la, lb)
+    with pytest.raises(Exception):
+        synthesize_from_codes(m, c, codes[:, :, :-1], n_steps=1)      # odd frame count: not a multiple of 640 samples
+
+
 def test_reference_script_surface(case):
     """The literal statement sequence of sample.py:94-134 runs on top of the mirrored objects."""
     m, c, fx, wav = case["m"], case["c"], case["fx"], case["wav"]
@@ -302,3 +318,28 @@ def test_full_size_properties_config2():
 def make_clips_cached(B, T):
     from ladiffcodec_b200.synthetic import make_clips
     return make_clips(B, T, seed=4242)
+
+
+def test_long_utterance_against_oracle():
+    """a whole utterance (5.12 s, Layout-A: latent L = 10240, bottleneck attention over n = 640 positions,
+    encoder LSTM over 256 frames, decoder LSTM over 10240) goes through the same entry point; checked against the oracle."""
+    from ladiffcodec_b200.config import readme_args
+    from ladiffcodec_b200.sample import synthesize
+    args = readme_args()
+    sdm = pc.make_state_dict(seed=11, **pc.ladiff_model_kwargs(args))
+    sdc = pc.make_state_dict(seed=12, **pc.cond_model_kwargs(args))
+    m, c = pc.cuda_models(args, sdm, sdc)
+    T, n_steps = 640 * 128, 2
+    wav = pc.make_clips(1, T, seed=5)
+    L = T // 8
+    noise = torch.randn(n_steps - 1, 1, 128, L, generator=torch.Generator().manual_seed(3))
+    out, lat = synthesize(m, c, wav.cuda(), n_steps=n_steps, noise=noise, return_latent=True)
+    stages = {}
+    with torch.no_grad():
+        ref = O.synthesize(wav, sdm, sdc, n_steps=n_steps, noise=noise, cond_bandwidth=args.cond_bandwidth,
+                           enc_ratios=args.enc_ratios, upsampling_ratios=args.upsampling_ratios, diff_dims=args.diff_dims,
+                           unet_scale_cond=args.unet_scale_cond, fast_lstm=True, stages=stages)
+    assert pc.rel_l2(lat, stages["latent"]) <= pc.TOL["latent_rel_l2"]
+    assert pc.snr_db(out, ref) >= pc.TOL["wav_snr_db"]
+    del m, c
+    torch.cuda.empty_cache()
