@@ -790,28 +790,35 @@ struct PlanBuilder {
       TcConvParams best = ps;
       TcRefView best_rv = rv;
       const bool multi = ps.NCLIP > 1 || ps.Lout + 8 <= 120;
-      for (int c = 0; c < 12; ++c) {
+      static const bool no_t = getenv("LADIFF_NO_TRANSPOSED") != nullptr;
+      for (int c = -1; c < 12; ++c) {
         TcConvDesc dc = d;
-        if (multi) { dc.want_nclip = c + 1; if (c >= 3) break; }
+        if (c < 0) { if (no_t || ps.Lout < 128) continue; dc.want_transposed = 1; }     // positions-on-M kernel
+        else if (multi) { dc.want_nclip = c + 1; if (c >= 3) break; }
         else { dc.want_nt = 256 - 16 * c; if (dc.want_nt < 96) break; }
         TcConvParams pc2;
         TcRefView rv2;
         if (tc_conv_plan(dc, &pc2, &rv2) != 0) continue;                     // shape does not fit (smem, halo): skip
-        if (pc2.NT == ps.NT && pc2.NCLIP == ps.NCLIP) continue;
-        if (want_stats && pc2.n_ptiles * TC_STAT_PARTS * pc2.stat_slots > pl->bufs.stats_slots) continue;
+        if (!pc2.transposed && pc2.NT == ps.NT && pc2.NCLIP == ps.NCLIP) continue;
+        if (want_stats && pc2.n_ptiles * pc2.stat_parts * pc2.stat_slots > pl->bufs.stats_slots) continue;
         float ms = 0.f;
         TRY(time_one(pc2, &ms));
+        static const bool force_t = getenv("LADIFF_FORCE_TRANSPOSED") != nullptr;     // experiment knob
+        if (force_t && pc2.transposed) { best_ms = 0.f; best = pc2; best_rv = rv2; continue; }
         if (ms < best_ms && ms < 0.97f * base_ms) { best_ms = ms; best = pc2; best_rv = rv2; }
       }
       ps = best; rv = best_rv;
     }
     d.tap_share = 0;
-    d.want_nt = ps.NCLIP == 1 ? ps.NT : 0; d.want_nclip = ps.NCLIP > 1 ? ps.NCLIP : 0;
+    d.want_nt = (ps.NCLIP == 1 && !ps.transposed) ? ps.NT : 0; d.want_nclip = ps.NCLIP > 1 ? ps.NCLIP : 0;
+    if (ps.transposed) {          // the per-tap check variant must produce the same GroupNorm-partial layout: reuse the chosen plan
+      pu = ps;
+    } else
     if (tc_conv_plan(d, &pu, nullptr) != 0) { d.want_nt = 0; d.want_nclip = 0; TRY(tc_conv_plan(d, &pu, nullptr)); }
-    LADIFF_REQUIRE(ps.n_ptiles == pu.n_ptiles || !want_stats, LADIFF_ERR_ARG, "plan: tap-shared and per-tap tilings disagree");
+    LADIFF_REQUIRE((ps.n_ptiles == pu.n_ptiles && ps.stat_parts == pu.stat_parts) || !want_stats, LADIFF_ERR_ARG, "plan: tap-shared and per-tap tilings disagree");
     if (want_stats)
-      LADIFF_REQUIRE(ps.n_ptiles * TC_STAT_PARTS * ps.stat_slots <= pl->bufs.stats_slots, LADIFF_ERR_WORKSPACE, "plan: stats buffer too small");
-    if (n_ntiles) *n_ntiles = ps.n_ptiles * TC_STAT_PARTS;
+      LADIFF_REQUIRE(ps.n_ptiles * ps.stat_parts * ps.stat_slots <= pl->bufs.stats_slots, LADIFF_ERR_WORKSPACE, "plan: stats buffer too small");
+    if (n_ntiles) *n_ntiles = ps.n_ptiles * ps.stat_parts;
     H* hh = h;
     pl->ops.push_back([hh, ps, pu, rv](cudaStream_t st) {
       if (hh->conv_impl == 1) return tc_conv_ref_launch(ps, rv, st);
@@ -823,8 +830,9 @@ struct PlanBuilder {
     pl->op_label.resize(pl->ops.size());
     {
       char buf[200];
-      snprintf(buf, sizeof(buf), "conv kind=%d Cout=%d Cin=%d k=%d Lout=%d NT=%d nclip=%d tiles=%d S=%d taps/stage=%d stats=%d direct=%d", pc.kind,
-               pc.CoutV, pc.Cin, pc.K, ps.Lout, ps.NT, ps.NCLIP, ps.MT * ps.n_ntiles, ps.S, ps.a_cap, want_stats ? 1 : 0, ps.direct);
+      snprintf(buf, sizeof(buf), "conv kind=%d Cout=%d Cin=%d k=%d Lout=%d NT=%d nclip=%d tiles=%d S=%d taps/stage=%d stats=%d direct=%d posM=%d", pc.kind,
+               pc.CoutV, pc.Cin, pc.K, ps.Lout, ps.NT, ps.NCLIP, ps.transposed ? ps.n_chtiles * ps.n_ntiles : ps.MT * ps.n_ntiles, ps.S, ps.a_cap,
+               want_stats ? 1 : 0, ps.direct, ps.transposed ? ps.NCH : 0);
       pl->op_label.back() = buf;
     }
     pl->launches_per_run++;
@@ -1394,7 +1402,7 @@ extern "C" int32_t ladiff_op_conv1d_cl(const void* x_bf16, const float* w, const
                                        int32_t Cout, int32_t k, void* y, int32_t y_f32, int32_t impl, float* gn_stats) {
   LADIFF_REQUIRE(x_bf16 && w && y && Cin % 64 == 0 && Cout % 128 == 0 && k >= 1 && k <= TC_MAX_TAPS && (k & 1), LADIFF_ERR_ARG,
                  "ladiff_op_conv1d_cl: Cin %% 64, Cout %% 128, odd k <= %d required", TC_MAX_TAPS);
-  LADIFF_REQUIRE(impl >= 0 && impl <= 2, LADIFF_ERR_ARG, "ladiff_op_conv1d_cl: impl=%d", impl);
+  LADIFF_REQUIRE(impl >= 0 && impl <= 3, LADIFF_ERR_ARG, "ladiff_op_conv1d_cl: impl=%d", impl);
   bf16* wp = nullptr; float2* stats = nullptr;
   LADIFF_CUDA_OK(cudaMalloc((void**)&wp, sizeof(bf16) * (size_t)Cout * Cin * k));
   int rc = pack_conv_launch(w, wp, Cout, Cin, k, 0, 0);
@@ -1406,20 +1414,20 @@ extern "C" int32_t ladiff_op_conv1d_cl(const void* x_bf16, const float* w, const
   d.x = (const bf16*)x_bf16; d.x_bstride = (long long)L * Cin; d.x_pitch = Cin; d.Lin = L;
   if (y_f32) d.out32 = (float*)y;
   else { d.out = (bf16*)y; d.out_bstride = (long long)L * Cout; d.out_pitch = Cout; }
-  d.B = B; d.tap_share = impl == 2 ? 0 : 1;
+  d.B = B; d.tap_share = impl == 2 ? 0 : 1; d.want_transposed = impl == 3 ? 1 : 0;
   TcConvParams p;
   TcRefView rv;
   if (!rc) rc = tc_conv_plan(d, &p, &rv);
   if (!rc && gn_stats) {
-    if (cudaMalloc((void**)&stats, sizeof(float2) * (size_t)B * p.n_ptiles * TC_STAT_PARTS * (Cout / 32)) != cudaSuccess) rc = LADIFF_ERR_CUDA;
-    else cudaMemset(stats, 0, sizeof(float2) * (size_t)B * p.n_ptiles * TC_STAT_PARTS * (Cout / 32));
+    if (cudaMalloc((void**)&stats, sizeof(float2) * (size_t)B * p.n_ptiles * p.stat_parts * (Cout / 32)) != cudaSuccess) rc = LADIFF_ERR_CUDA;
+    else cudaMemset(stats, 0, sizeof(float2) * (size_t)B * p.n_ptiles * p.stat_parts * (Cout / 32));
     p.stats = stats;
   }
   if (!rc) rc = impl == 1 ? tc_conv_ref_launch(p, rv, 0) : tc_conv_launch(p, 0);
   cudaError_t e = cudaDeviceSynchronize();
   if (!rc && e != cudaSuccess) { ladiff_set_error("ladiff_op_conv1d_cl: %s", cudaGetErrorString(e)); rc = LADIFF_ERR_CUDA; }
   if (!rc && gn_stats) {   // reduce the per-tile partials on the host: [B][Cout/32][2]
-    const int npt = p.n_ptiles * TC_STAT_PARTS;
+    const int npt = p.n_ptiles * p.stat_parts;
     std::vector<float2> hst((size_t)B * npt * (Cout / 32));
     cudaMemcpy(hst.data(), stats, sizeof(float2) * hst.size(), cudaMemcpyDeviceToHost);
     std::vector<float> red((size_t)B * (Cout / 32) * 2, 0.f);

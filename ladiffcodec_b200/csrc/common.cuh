@@ -119,6 +119,7 @@ struct TcConvDesc {
   int B;
   int tap_share;            // 1: all taps of a chunk read one shared activation tile; 0: one tile load per tap
   int want_nt, want_nclip;  // > 0: force the tile shape (rows per clip region / clip regions per tile); 0: cost model
+  int want_transposed;      // 1: positions-on-M kernel (tc_conv_t_kernel): 128-row position tiles x <= 256-channel tiles
 };
 
 struct TcConvParams {
@@ -157,6 +158,13 @@ struct TcConvParams {
   const bf16* res;
   long long res_bstride;
   int res_pitch;
+  // positions-on-M variant (tc_conv_t_kernel): D[position, channel]; rows = 128 positions of one clip, columns = NCH channels
+  int transposed;
+  int NCH;                    // channels per tile (multiple of 16, <= 256, divides Cout and every tap's channel range)
+  int n_chtiles;              // Cout / NCH
+  int stat_parts;             // GroupNorm partials per (clip, position tile): 2 (epilogue warpgroups) or 4 (epilogue warps)
+  CUtensorMap tmWt;           // weights, box {64, NCH}
+  void* out2v; long long out2_bstride; int out2_pitch;   // second output (split_m) for the direct-store epilogue
   unsigned long long* prof;   // debug (LADIFF_TC_PROF): per-CTA wait-cycle counters [grid][8]
   int dbg;                    // debug (LADIFF_TC_DBG, only with LADIFF_TC_PROF): ablation bits, see tc_conv_launch
 };

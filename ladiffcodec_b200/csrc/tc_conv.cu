@@ -432,6 +432,230 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
   }
 }
 
+// ================================================================================================ positions-on-M variant
+// D[m = position (128 TMEM lanes), n = output channel (NCH <= 256 columns)]:
+//   A = activation tile [128 + halo rows][64 ch] (one TMA box per 64-channel chunk; a tap is a row-shifted descriptor start)
+//   B = weight tile [NCH rows][64 ch] per (tap, chunk), in its own ring
+// An epilogue thread owns one position: it reads 16 consecutive channels per tcgen05.ld and stores them as 32 contiguous bytes —
+// no shared-memory staging, no barriers, GroupNorm partials reduced per 32-channel slot with warp shuffles.  One activation load
+// serves all <= 256 output channels of the tile (the channels-on-M kernel re-reads it per 128-channel tile).
+constexpr int kThreadsT = 192;
+constexpr int kActSlots = 3, kActBytes = 18432;        // 136 rows x 128 B, rounded to 1 KB
+constexpr int kMaxWSlots = 8;
+constexpr size_t kSmemLimitT = 232448 - 3072;         // 227 KB minus this kernel's static shared memory (barriers, bias tiles)
+
+__global__ void __launch_bounds__(kThreadsT, 1) tc_conv_t_kernel(const __grid_constant__ TcConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t af[kActSlots], ae[kActSlots], wf[kMaxWSlots], we[kMaxWSlots], tf[2], te[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_bias[2][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_base = smem_base + kActSlots * kActBytes;
+  const uint32_t w_bytes = (uint32_t)p.NCH * 128u;
+  const int SW = p.S;                                     // weight-ring slots
+  uint32_t acc_stride = 32;
+  while ((int)acc_stride < p.NCH) acc_stride <<= 1;
+  const uint32_t tmem_cols = 2 * acc_stride;
+  const int total_tiles = p.n_chtiles * p.n_ptiles * p.B;
+  const bool prof = p.prof != nullptr;
+  const long long t_begin = prof ? clock64() : 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kActSlots; ++s) { mbar_init(&af[s], 1); mbar_init(&ae[s], 1); }
+    for (int s = 0; s < SW; ++s) { mbar_init(&wf[s], 1); mbar_init(&we[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tf[s], 1); mbar_init(&te[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmWt) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmX) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  pdl_wait();
+  pdl_trigger();
+
+  auto tile_of = [&](int t, int& n0, int& l0, int& b) {
+    const int ct = t % p.n_chtiles, r = t / p.n_chtiles;
+    n0 = ct * p.NCH; l0 = (r % p.n_ptiles) * 128; b = r / p.n_ptiles;
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ---------------- TMA producer
+      int sa = 0, sw = 0; uint32_t pa = 0, pw = 0;
+      long long w_empty = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int n0, l0, b;
+        tile_of(t, n0, l0, b);
+        for (int g = 0; g < p.ngrp; ++g) {
+          const TcGroup& gr = p.grp[g];
+          int n_a = 0, kof[TC_MAX_TAPS];
+          for (int tp = 0; tp < gr.ntaps; ++tp) {
+            const TcTap tap = gr.tap[tp];
+            if (n0 >= tap.m_lo && n0 < tap.m_hi) kof[n_a++] = tap.kofs;
+          }
+          if (n_a == 0) continue;
+          for (int c = 0; c < gr.nchunk; ++c) {
+            const int kc = c * TC_BK;
+            mbar_wait_t(&ae[sa], pa ^ 1, w_empty, prof);
+            mbar_expect_tx(&af[sa], (uint32_t)p.BOXROWS * 128u);
+            tma_load_3d(smem_base + (uint32_t)sa * kActBytes, &p.tmX, &af[sa], gr.ch0 + kc, l0 + gr.shift, b);
+            if (++sa == kActSlots) { sa = 0; pa ^= 1; }
+            for (int a = 0; a < n_a; ++a) {
+              mbar_wait_t(&we[sw], pw ^ 1, w_empty, prof);
+              mbar_expect_tx(&wf[sw], w_bytes);
+              tma_load_2d(w_base + (uint32_t)sw * w_bytes, &p.tmWt, &wf[sw], kof[a] + kc, n0);
+              if (++sw == SW) { sw = 0; pw ^= 1; }
+            }
+          }
+        }
+      }
+      if (prof) p.prof[blockIdx.x * 8 + 0] = (unsigned long long)w_empty;
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ---------------- MMA issuer: M = 128 positions, N = NCH channels, K = 16 per instruction
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NCH >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int sa = 0, sw = 0, tl = 0; uint32_t pa = 0, pw = 0;
+      long long w_full = 0, w_tmem = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+        int n0, l0, b;
+        tile_of(t, n0, l0, b);
+        const int acc = tl & 1;
+        mbar_wait_t(&te[acc], ((tl >> 1) & 1) ^ 1, w_tmem, prof);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_stride;
+        uint32_t accumulate = 0;
+        for (int g = 0; g < p.ngrp; ++g) {
+          const TcGroup& gr = p.grp[g];
+          int n_a = 0; uint32_t ro[TC_MAX_TAPS];
+          for (int tp = 0; tp < gr.ntaps; ++tp) {
+            const TcTap tap = gr.tap[tp];
+            if (n0 >= tap.m_lo && n0 < tap.m_hi) ro[n_a++] = (uint32_t)tap.row_off * 8u;
+          }
+          if (n_a == 0) continue;
+          for (int c = 0; c < gr.nchunk; ++c) {
+            mbar_wait_t(&af[sa], pa, w_full, prof);
+            tc_fence_after();
+            const uint64_t adesc0 = umma_desc(smem_base + (uint32_t)sa * kActBytes);
+            for (int a = 0; a < n_a; ++a) {
+              mbar_wait_t(&wf[sw], pw, w_full, prof);
+              tc_fence_after();
+              const uint64_t adesc = adesc0 + ro[a];
+              const uint64_t bdesc = umma_desc(w_base + (uint32_t)sw * w_bytes);
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k) { umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate); accumulate = 1; }
+              tc_commit(&we[sw]);
+              if (++sw == SW) { sw = 0; pw ^= 1; }
+            }
+            tc_commit(&ae[sa]);
+            if (++sa == kActSlots) { sa = 0; pa ^= 1; }
+          }
+        }
+        tc_commit(&tf[acc]);
+      }
+      if (prof) { p.prof[blockIdx.x * 8 + 1] = (unsigned long long)w_full; p.prof[blockIdx.x * 8 + 2] = (unsigned long long)w_tmem; }
+    }
+    __syncwarp();
+  } else {
+    // ---------------- epilogue: warp w owns TMEM lanes 32*(w&3)..+31 = positions l0 + 32*(w&3) + lane
+    const int q = warp & 3, et = threadIdx.x - 64;
+    int tl = 0;
+    long long w_acc = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+      int n0, l0, b;
+      tile_of(t, n0, l0, b);
+      const int acc = tl & 1;
+      float* sb = s_bias[tl & 1];
+      for (int i = et; i < p.NCH; i += 128) sb[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int l = l0 + q * 32 + lane;
+      const bool valid = l < p.Lout;
+      const bool second = p.split_m && n0 >= p.split_m;
+      char* obase;                                           // first output element of this thread's row, channel n0
+      if (second) obase = (char*)p.out2v + ((long long)b * p.out2_bstride + (long long)l * p.out2_pitch + (n0 - p.split_m)) * 2;
+      else if (p.up_cout) obase = (char*)p.out + ((long long)b * p.out_bstride + (long long)(2 * l + n0 / p.up_cout) * p.out_pitch + n0 % p.up_cout) * 2;
+      else obase = (char*)p.out + ((long long)b * p.out_bstride + (long long)l * p.out_pitch + n0) * (p.out_f32 ? 4 : 2);
+      const bf16* rbase = p.res ? p.res + (long long)b * p.res_bstride + (long long)l * p.res_pitch + n0 : nullptr;
+      const bool want_stats = p.stats && !second;
+      mbar_wait_t(&tf[acc], (tl >> 1) & 1, w_acc, prof);
+      tc_fence_after();
+      const uint32_t tlane = tmem_base + (uint32_t)acc * acc_stride + ((uint32_t)(q * 32) << 16);
+      // 64 columns per tcgen05.wait::ld: the wait is the expensive part of a TMEM read while the tensor pipe is busy
+      for (int c0 = 0; c0 < p.NCH; c0 += 64) {
+        uint32_t r0[16], r1[16], r2[16], r3[16];
+        tmem_ld16_async(tlane + (uint32_t)c0, r0);
+        tmem_ld16_async(tlane + (uint32_t)(c0 + 16), r1);
+        tmem_ld16_async(tlane + (uint32_t)(c0 + 32), r2);
+        tmem_ld16_async(tlane + (uint32_t)(c0 + 48), r3);
+        tmem_ld_wait();
+        float a1 = 0.f, a2 = 0.f;
+        auto consume = [&](const uint32_t (&r)[16], int cb) {
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + sb[cb + i];
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { a1 += v[i]; a2 += v[i] * v[i]; }
+            if (rbase) {
+              const uint4 q0 = __ldcg(reinterpret_cast<const uint4*>(rbase + cb)), q1 = __ldcg(reinterpret_cast<const uint4*>(rbase + cb + 8));
+              const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&q0);
+              const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&q1);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f0 = __bfloat1622float2(h0[i]), f1 = __bfloat1622float2(h1[i]);
+                v[2 * i] += f0.x; v[2 * i + 1] += f0.y; v[8 + 2 * i] += f1.x; v[8 + 2 * i + 1] += f1.y;
+              }
+            }
+            if (p.out_f32 && !second) {
+              float4* o = reinterpret_cast<float4*>(obase + (size_t)cb * 4);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            } else {
+              uint4 o0, o1;
+              __nv_bfloat162* g0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+              __nv_bfloat162* g1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { g0[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); g1[i] = __floats2bfloat162_rn(v[8 + 2 * i], v[8 + 2 * i + 1]); }
+              uint4* o = reinterpret_cast<uint4*>(obase + (size_t)cb * 2);
+              o[0] = o0; o[1] = o1;
+            }
+          }
+        };
+        auto flush_slot = [&](int cb) {                      // one 32-channel GroupNorm slot finished: reduce over the warp's 32 positions
+          if (want_stats) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+              a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+            }
+            if (lane == 0)
+              p.stats[(((long long)b * p.n_ptiles + l0 / 128) * p.stat_parts + q) * p.stat_slots + ((n0 + cb) >> 5)] = make_float2(a1, a2);
+          }
+          a1 = 0.f; a2 = 0.f;
+        };
+        consume(r0, c0); consume(r1, c0 + 16); flush_slot(c0);
+        consume(r2, c0 + 32); consume(r3, c0 + 48); flush_slot(c0 + 32);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&te[acc]);
+    }
+    if (prof && threadIdx.x == 64) { p.prof[blockIdx.x * 8 + 3] = (unsigned long long)w_acc; p.prof[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - t_begin); }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
 // SIMT check kernel: identical operands, tiling and epilogue semantics, plain FMA loop.
 // grid (n_ptiles, Cout/32, B), 128 threads: lane = channel, warp w handles rows w, w+4, ...
 __global__ void __launch_bounds__(128) tc_conv_ref_kernel(TcConvParams p, TcRefView v) {
@@ -484,9 +708,9 @@ __global__ void __launch_bounds__(128) tc_conv_ref_kernel(TcConvParams p, TcRefV
         c += __shfl_xor_sync(0xffffffffu, c, o);
       }
       if (lane == 0) {
-        float2* sp = p.stats + (((long long)b * p.n_ptiles + pt) * kEpiGroups) * p.stat_slots + blockIdx.y;
+        float2* sp = p.stats + (((long long)b * p.n_ptiles + pt) * p.stat_parts) * p.stat_slots + blockIdx.y;
         sp[0] = make_float2(a, c);
-        for (int gi = 1; gi < kEpiGroups; ++gi) sp[(long long)gi * p.stat_slots] = make_float2(0.f, 0.f);
+        for (int gi = 1; gi < p.stat_parts; ++gi) sp[(long long)gi * p.stat_slots] = make_float2(0.f, 0.f);
       }
     }
   }
@@ -543,6 +767,19 @@ int tc_num_sms() {
       n = 148;
   }
   return n;
+}
+
+static int make_tmap_wt(CUtensorMap* tm, const bf16* w, int Cout, int Ktot, int nch) {
+  auto enc = get_encode();
+  LADIFF_REQUIRE(enc != nullptr, LADIFF_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
+  cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+  cuuint32_t box[2] = {TC_BK, (cuuint32_t)nch};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LADIFF_REQUIRE(r == CUDA_SUCCESS, LADIFF_ERR_CUDA, "cuTensorMapEncodeTiled(Wt %dx%d box %d) failed: %d", Cout, Ktot, nch, (int)r);
+  return 0;
 }
 
 int tc_make_tmap_w(CUtensorMap* tm, const bf16* w, int Cout, int Ktot) {
@@ -668,6 +905,44 @@ int tc_conv_plan(const TcConvDesc& d, TcConvParams* pp, TcRefView* rv) {
   p.up_cout = d.kind == TC_KIND_UP ? d.CoutV / 2 : 0;
   p.split_m = d.split_m;
   p.stat_slots = (d.split_m ? d.split_m : d.CoutV) / 32;
+  p.stat_parts = kEpiGroups;
+  if (d.want_transposed) {
+    // positions-on-M kernel: 128-row position tiles of one clip x NCH-channel tiles; NCH must divide every tap's channel range
+    int nch = 0;
+    for (int cand : {256, 192, 128}) {
+      bool ok = d.CoutV % cand == 0 && (!d.split_m || d.split_m % cand == 0) && (!p.up_cout || p.up_cout % cand == 0);
+      for (int g = 0; ok && g < p.ngrp; ++g)
+        for (int t2 = 0; ok && t2 < p.grp[g].ntaps; ++t2)
+          ok = p.grp[g].tap[t2].m_lo % cand == 0 && (p.grp[g].tap[t2].m_hi % cand == 0 || p.grp[g].tap[t2].m_hi == d.CoutV);
+      if (ok) { nch = cand; break; }
+    }
+    LADIFF_REQUIRE(nch > 0 && tile_halo <= 8, LADIFF_ERR_ARG, "tc_conv(transposed): no channel tile fits");
+    p.transposed = 1; p.NCH = nch; p.n_chtiles = d.CoutV / nch; p.stat_parts = 4;
+    p.NT = 128; p.NCLIP = 1; p.n_ptiles = cdiv(Lout, 128); p.NMMA = nch; p.n_ntiles = d.B * p.n_ptiles; p.BOXROWS = 136; p.CR = 32;
+    const long wslots = ((long)kSmemLimitT - 2048 - (long)kActSlots * kActBytes) / ((long)nch * 128);
+    p.S = wslots > kMaxWSlots ? kMaxWSlots : (int)wslots;
+    LADIFF_REQUIRE(p.S >= 3, LADIFF_ERR_ARG, "tc_conv(transposed): weight ring too small");
+    p.direct = (d.out32 != nullptr || d.res != nullptr) ? 1 : 0;
+    p.tmW = *d.tmW;
+    int rc = make_tmap_x(&p.tmX, d.x, d.B, Lv, Cv, pitch_v, d.x_bstride, p.BOXROWS);
+    if (rc) return rc;
+    rc = make_tmap_wt(&p.tmWt, d.w, d.CoutV, d.Ktot, nch);
+    if (rc) return rc;
+    if (d.out32) { p.out = d.out32; p.out_f32 = 1; p.out_pitch = d.CoutV; p.out_bstride = (long long)Lout * d.CoutV; }
+    else { p.out = d.out; p.out_f32 = 0; p.out_pitch = d.out_pitch; p.out_bstride = d.out_bstride; }
+    p.out2v = d.out2; p.out2_bstride = d.out2_bstride; p.out2_pitch = d.out2_pitch;
+    p.res = d.res; p.res_bstride = d.res_bstride; p.res_pitch = d.res_pitch;
+    LADIFF_REQUIRE(((uintptr_t)p.out % 16) == 0 && p.out_pitch % 8 == 0 && p.out_bstride % 8 == 0 &&
+                       (!d.out2 || (((uintptr_t)d.out2 % 16) == 0 && d.out2_pitch % 8 == 0 && d.out2_bstride % 8 == 0)) &&
+                       (!d.res || (((uintptr_t)d.res % 16) == 0 && d.res_pitch % 8 == 0 && d.res_bstride % 8 == 0)),
+                   LADIFF_ERR_ARG, "tc_conv(transposed): output / residual views are not 16-byte aligned");
+    if (rv) {
+      rv->x = d.x; rv->bstride = d.x_bstride; rv->pitch = pitch_v; rv->Lv = Lv; rv->Cv = Cv; rv->w = d.w; rv->Ktot = d.Ktot;
+      rv->out = d.out; rv->out_bstride = d.out_bstride; rv->out_pitch = d.out_pitch;
+      rv->out2 = d.out2; rv->out2_bstride = d.out2_bstride; rv->out2_pitch = d.out2_pitch;
+    }
+    return 0;
+  }
   pick_tiling(Lout, d.B, p.MT, tile_halo, d.want_nt, d.want_nclip, &p.NT, &p.NCLIP, &p.n_ptiles);
   p.NMMA = p.NT * p.NCLIP;
   p.n_ntiles = p.NCLIP == 1 ? d.B * p.n_ptiles : cdiv(d.B, p.NCLIP);
@@ -727,7 +1002,41 @@ static size_t tc_smem_bytes(const TcConvParams& p) {
   return (size_t)p.S * p.stage_bytes + (p.direct ? (p.res ? (size_t)p.NMMA * 256 : 0) : (size_t)2 * kEpiGroups * p.CR * 256) + 2048;
 }
 
+static int tc_conv_t_launch(const TcConvParams& p, cudaStream_t st) {
+  const size_t smem = (size_t)kActSlots * kActBytes + (size_t)p.S * p.NCH * 128 + 2048;
+  LADIFF_REQUIRE(smem <= kSmemLimitT, LADIFF_ERR_ARG, "tc_conv(transposed): smem %zu too large", smem);
+  static bool attr_set = false;
+  if (!attr_set) {
+    LADIFF_CUDA_OK(cudaFuncSetAttribute(tc_conv_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimitT));
+    attr_set = true;
+  }
+  const int tiles = p.n_chtiles * p.n_ptiles * p.B, nsm = tc_num_sms();
+  const int grid = tiles < nsm ? tiles : nsm;
+  static const bool want_prof = getenv("LADIFF_TC_PROF") != nullptr;
+  if (!want_prof) {
+    LADIFF_CUDA_OK(launch_pdl(tc_conv_t_kernel, dim3(grid), dim3(kThreadsT), smem, st, p));
+    return 0;
+  }
+  TcConvParams q = p;
+  unsigned long long* dprof = nullptr;
+  LADIFF_CUDA_OK(cudaMalloc((void**)&dprof, sizeof(unsigned long long) * 8 * grid));
+  LADIFF_CUDA_OK(cudaMemset(dprof, 0, sizeof(unsigned long long) * 8 * grid));
+  q.prof = dprof;
+  tc_conv_t_kernel<<<grid, kThreadsT, smem, st>>>(q);
+  LADIFF_CUDA_OK(cudaGetLastError());
+  LADIFF_CUDA_OK(cudaStreamSynchronize(st));
+  std::vector<unsigned long long> hp((size_t)8 * grid);
+  LADIFF_CUDA_OK(cudaMemcpy(hp.data(), dprof, sizeof(unsigned long long) * hp.size(), cudaMemcpyDeviceToHost));
+  cudaFree(dprof);
+  double a[5] = {0, 0, 0, 0, 0};
+  for (int i = 0; i < grid; ++i) for (int k = 0; k < 5; ++k) a[k] += (double)hp[(size_t)i * 8 + k] / grid;
+  fprintf(stderr, "[tc_prof_t] Cout=%d NCH=%d Wslots=%d grid=%d tiles=%d | cycles/CTA: total %.0f  producer-wait-empty %.0f  mma-wait-full %.0f  "
+                  "mma-wait-tmem %.0f  epi-wait-acc %.0f\n", p.Cout, p.NCH, p.S, grid, tiles, a[4], a[0], a[1], a[2], a[3]);
+  return 0;
+}
+
 int tc_conv_launch(const TcConvParams& p, cudaStream_t st) {
+  if (p.transposed) return tc_conv_t_launch(p, st);
   const size_t smem = tc_smem_bytes(p);
   LADIFF_REQUIRE(smem <= kSmemLimit, LADIFF_ERR_ARG, "tc_conv: smem %zu too large", smem);
   static bool attr_set = false;     // opt in to the full dynamic shared memory once
