@@ -791,9 +791,9 @@ struct PlanBuilder {
       TcRefView best_rv = rv;
       const bool multi = ps.NCLIP > 1 || ps.Lout + 8 <= 120;
       static const bool no_t = getenv("LADIFF_NO_TRANSPOSED") != nullptr;
-      for (int c = -1; c < 12; ++c) {
+      for (int c = -2; c < 12; ++c) {
         TcConvDesc dc = d;
-        if (c < 0) { if (no_t || ps.Lout < 128) continue; dc.want_transposed = 1; }     // positions-on-M kernel
+        if (c < 0) { if (no_t || ps.Lout < 128) continue; dc.want_transposed = -c; }    // positions-on-M kernel: one CTA / CTA pair per tile
         else if (multi) { dc.want_nclip = c + 1; if (c >= 3) break; }
         else { dc.want_nt = 256 - 16 * c; if (dc.want_nt < 96) break; }
         TcConvParams pc2;
@@ -803,8 +803,8 @@ struct PlanBuilder {
         if (want_stats && pc2.n_ptiles * pc2.stat_parts * pc2.stat_slots > pl->bufs.stats_slots) continue;
         float ms = 0.f;
         TRY(time_one(pc2, &ms));
-        static const bool force_t = getenv("LADIFF_FORCE_TRANSPOSED") != nullptr;     // experiment knob
-        if (force_t && pc2.transposed) { best_ms = 0.f; best = pc2; best_rv = rv2; continue; }
+        static const int force_t = getenv("LADIFF_FORCE_TRANSPOSED") ? atoi(getenv("LADIFF_FORCE_TRANSPOSED")) : 0;     // experiment knob
+        if (force_t && pc2.transposed == force_t) { best_ms = 0.f; best = pc2; best_rv = rv2; continue; }
         if (ms < best_ms && ms < 0.97f * base_ms) { best_ms = ms; best = pc2; best_rv = rv2; }
       }
       ps = best; rv = best_rv;
@@ -1402,7 +1402,7 @@ extern "C" int32_t ladiff_op_conv1d_cl(const void* x_bf16, const float* w, const
                                        int32_t Cout, int32_t k, void* y, int32_t y_f32, int32_t impl, float* gn_stats) {
   LADIFF_REQUIRE(x_bf16 && w && y && Cin % 64 == 0 && Cout % 128 == 0 && k >= 1 && k <= TC_MAX_TAPS && (k & 1), LADIFF_ERR_ARG,
                  "ladiff_op_conv1d_cl: Cin %% 64, Cout %% 128, odd k <= %d required", TC_MAX_TAPS);
-  LADIFF_REQUIRE(impl >= 0 && impl <= 3, LADIFF_ERR_ARG, "ladiff_op_conv1d_cl: impl=%d", impl);
+  LADIFF_REQUIRE(impl >= 0 && impl <= 4, LADIFF_ERR_ARG, "ladiff_op_conv1d_cl: impl=%d", impl);
   bf16* wp = nullptr; float2* stats = nullptr;
   LADIFF_CUDA_OK(cudaMalloc((void**)&wp, sizeof(bf16) * (size_t)Cout * Cin * k));
   int rc = pack_conv_launch(w, wp, Cout, Cin, k, 0, 0);
@@ -1414,7 +1414,7 @@ extern "C" int32_t ladiff_op_conv1d_cl(const void* x_bf16, const float* w, const
   d.x = (const bf16*)x_bf16; d.x_bstride = (long long)L * Cin; d.x_pitch = Cin; d.Lin = L;
   if (y_f32) d.out32 = (float*)y;
   else { d.out = (bf16*)y; d.out_bstride = (long long)L * Cout; d.out_pitch = Cout; }
-  d.B = B; d.tap_share = impl == 2 ? 0 : 1; d.want_transposed = impl == 3 ? 1 : 0;
+  d.B = B; d.tap_share = impl == 2 ? 0 : 1; d.want_transposed = impl == 3 ? 1 : (impl == 4 ? 2 : 0);
   TcConvParams p;
   TcRefView rv;
   if (!rc) rc = tc_conv_plan(d, &p, &rv);

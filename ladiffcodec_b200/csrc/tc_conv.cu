@@ -444,6 +444,47 @@ constexpr int kActSlots = 3, kActBytes = 18432;        // 136 rows x 128 B, roun
 constexpr int kMaxWSlots = 8;
 constexpr size_t kSmemLimitT = 232448 - 3072;         // 227 KB minus this kernel's static shared memory (barriers, bias tiles)
 
+// ---- CTA-pair (cta_group::2) helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA loads of a CTA pair: the data lands in this CTA's shared memory, the bytes are accounted on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tm, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* tm, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {      // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+
+// CG = 1: one CTA per tile.  CG = 2: a CTA pair (cta_group::2) computes 256 positions x NCH channels; CTA r loads its own 128
+// positions and rows [r*NCH/2, (r+1)*NCH/2) of every weight tile, so the weight bytes landing in each SM are halved; the leader
+// (rank 0) issues the M = 256 MMAs, its commits free the ring slots of both CTAs.
+template <int CG>
 __global__ void __launch_bounds__(kThreadsT, 1) tc_conv_t_kernel(const __grid_constant__ TcConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t af[kActSlots], ae[kActSlots], wf[kMaxWSlots], we[kMaxWSlots], tf[2], te[2];
@@ -452,28 +493,38 @@ __global__ void __launch_bounds__(kThreadsT, 1) tc_conv_t_kernel(const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = smem_base + kActSlots * kActBytes;
-  const uint32_t w_bytes = (uint32_t)p.NCH * 128u;
+  const uint32_t w_bytes = (uint32_t)(p.NCH / CG) * 128u;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
   const int SW = p.S;                                     // weight-ring slots
   uint32_t acc_stride = 32;
   while ((int)acc_stride < p.NCH) acc_stride <<= 1;
   const uint32_t tmem_cols = 2 * acc_stride;
-  const int total_tiles = p.n_chtiles * p.n_ptiles * p.B;
+  const int n_pt = CG == 2 ? (p.Lout + 255) / 256 : p.n_ptiles;      // position tiles (pairs of 128-row tiles for CG = 2)
+  const int total_tiles = p.n_chtiles * n_pt * p.B;
+  const int tile0 = (int)blockIdx.x / CG, tile_step = (int)gridDim.x / CG;
   const bool prof = p.prof != nullptr;
   const long long t_begin = prof ? clock64() : 0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kActSlots; ++s) { mbar_init(&af[s], 1); mbar_init(&ae[s], 1); }
     for (int s = 0; s < SW; ++s) { mbar_init(&wf[s], 1); mbar_init(&we[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tf[s], 1); mbar_init(&te[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tf[s], 1); mbar_init(&te[s], 4 * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmWt) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmX) : "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();          // the peer's barriers are initialised before any remote arrive / TMA completion
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   pdl_wait();
@@ -481,7 +532,7 @@ __global__ void __launch_bounds__(kThreadsT, 1) tc_conv_t_kernel(const __grid_co
 
   auto tile_of = [&](int t, int& n0, int& l0, int& b) {
     const int ct = t % p.n_chtiles, r = t / p.n_chtiles;
-    n0 = ct * p.NCH; l0 = (r % p.n_ptiles) * 128; b = r / p.n_ptiles;
+    n0 = ct * p.NCH; l0 = (r % n_pt) * (128 * CG) + 128 * (int)rank; b = r / n_pt;
   };
 
   if (warp == 0) {
@@ -489,7 +540,7 @@ __global__ void __launch_bounds__(kThreadsT, 1) tc_conv_t_kernel(const __grid_co
       // ---------------- TMA producer
       int sa = 0, sw = 0; uint32_t pa = 0, pw = 0;
       long long w_empty = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = tile0; t < total_tiles; t += tile_step) {
         int n0, l0, b;
         tile_of(t, n0, l0, b);
         for (int g = 0; g < p.ngrp; ++g) {
@@ -503,13 +554,23 @@ __global__ void __launch_bounds__(kThreadsT, 1) tc_conv_t_kernel(const __grid_co
           for (int c = 0; c < gr.nchunk; ++c) {
             const int kc = c * TC_BK;
             mbar_wait_t(&ae[sa], pa ^ 1, w_empty, prof);
-            mbar_expect_tx(&af[sa], (uint32_t)p.BOXROWS * 128u);
-            tma_load_3d(smem_base + (uint32_t)sa * kActBytes, &p.tmX, &af[sa], gr.ch0 + kc, l0 + gr.shift, b);
+            if (CG == 1) {
+              mbar_expect_tx(&af[sa], (uint32_t)p.BOXROWS * 128u);
+              tma_load_3d(smem_base + (uint32_t)sa * kActBytes, &p.tmX, &af[sa], gr.ch0 + kc, l0 + gr.shift, b);
+            } else {
+              if (leader) mbar_expect_tx(&af[sa], 2u * (uint32_t)p.BOXROWS * 128u);
+              tma_load_3d_pair(smem_base + (uint32_t)sa * kActBytes, &p.tmX, mapa_u32(smem_u32(&af[sa]), 0), gr.ch0 + kc, l0 + gr.shift, b);
+            }
             if (++sa == kActSlots) { sa = 0; pa ^= 1; }
             for (int a = 0; a < n_a; ++a) {
               mbar_wait_t(&we[sw], pw ^ 1, w_empty, prof);
-              mbar_expect_tx(&wf[sw], w_bytes);
-              tma_load_2d(w_base + (uint32_t)sw * w_bytes, &p.tmWt, &wf[sw], kof[a] + kc, n0);
+              if (CG == 1) {
+                mbar_expect_tx(&wf[sw], w_bytes);
+                tma_load_2d(w_base + (uint32_t)sw * w_bytes, &p.tmWt, &wf[sw], kof[a] + kc, n0);
+              } else {
+                if (leader) mbar_expect_tx(&wf[sw], 2u * w_bytes);
+                tma_load_2d_pair(w_base + (uint32_t)sw * w_bytes, &p.tmWt, mapa_u32(smem_u32(&wf[sw]), 0), kof[a] + kc, n0 + (int)rank * (p.NCH / 2));
+              }
               if (++sw == SW) { sw = 0; pw ^= 1; }
             }
           }
@@ -519,12 +580,12 @@ __global__ void __launch_bounds__(kThreadsT, 1) tc_conv_t_kernel(const __grid_co
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (elect_one()) {
-      // ---------------- MMA issuer: M = 128 positions, N = NCH channels, K = 16 per instruction
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NCH >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    if (leader && elect_one()) {
+      // ---------------- MMA issuer: M = 128*CG positions, N = NCH channels, K = 16 per instruction
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NCH >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
       int sa = 0, sw = 0, tl = 0; uint32_t pa = 0, pw = 0;
       long long w_full = 0, w_tmem = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+      for (int t = tile0; t < total_tiles; t += tile_step, ++tl) {
         int n0, l0, b;
         tile_of(t, n0, l0, b);
         const int acc = tl & 1;
@@ -550,15 +611,19 @@ __global__ void __launch_bounds__(kThreadsT, 1) tc_conv_t_kernel(const __grid_co
               const uint64_t adesc = adesc0 + ro[a];
               const uint64_t bdesc = umma_desc(w_base + (uint32_t)sw * w_bytes);
 #pragma unroll
-              for (int k = 0; k < TC_BK / 16; ++k) { umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate); accumulate = 1; }
-              tc_commit(&we[sw]);
+              for (int k = 0; k < TC_BK / 16; ++k) {
+                if (CG == 1) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
+                else umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
+                accumulate = 1;
+              }
+              if (CG == 1) tc_commit(&we[sw]); else tc_commit_pair(&we[sw]);
               if (++sw == SW) { sw = 0; pw ^= 1; }
             }
-            tc_commit(&ae[sa]);
+            if (CG == 1) tc_commit(&ae[sa]); else tc_commit_pair(&ae[sa]);
             if (++sa == kActSlots) { sa = 0; pa ^= 1; }
           }
         }
-        tc_commit(&tf[acc]);
+        if (CG == 1) tc_commit(&tf[acc]); else tc_commit_pair(&tf[acc]);
       }
       if (prof) { p.prof[blockIdx.x * 8 + 1] = (unsigned long long)w_full; p.prof[blockIdx.x * 8 + 2] = (unsigned long long)w_tmem; }
     }
@@ -568,7 +633,7 @@ __global__ void __launch_bounds__(kThreadsT, 1) tc_conv_t_kernel(const __grid_co
     const int q = warp & 3, et = threadIdx.x - 64;
     int tl = 0;
     long long w_acc = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+    for (int t = tile0; t < total_tiles; t += tile_step, ++tl) {
       int n0, l0, b;
       tile_of(t, n0, l0, b);
       const int acc = tl & 1;
@@ -583,7 +648,7 @@ __global__ void __launch_bounds__(kThreadsT, 1) tc_conv_t_kernel(const __grid_co
       else if (p.up_cout) obase = (char*)p.out + ((long long)b * p.out_bstride + (long long)(2 * l + n0 / p.up_cout) * p.out_pitch + n0 % p.up_cout) * 2;
       else obase = (char*)p.out + ((long long)b * p.out_bstride + (long long)l * p.out_pitch + n0) * (p.out_f32 ? 4 : 2);
       const bf16* rbase = p.res ? p.res + (long long)b * p.res_bstride + (long long)l * p.res_pitch + n0 : nullptr;
-      const bool want_stats = p.stats && !second;
+      const bool want_stats = p.stats && !second && l0 < p.Lout;    // (a pair's second tile can lie wholly past the clip)
       mbar_wait_t(&tf[acc], (tl >> 1) & 1, w_acc, prof);
       tc_fence_after();
       const uint32_t tlane = tmem_base + (uint32_t)acc * acc_stride + ((uint32_t)(q * 32) << 16);
@@ -645,14 +710,16 @@ __global__ void __launch_bounds__(kThreadsT, 1) tc_conv_t_kernel(const __grid_co
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&te[acc]);
+      if (lane == 0) { if (CG == 1) mbar_arrive(&te[acc]); else mbar_arrive_cluster(mapa_u32(smem_u32(&te[acc]), 0)); }
     }
     if (prof && threadIdx.x == 64) { p.prof[blockIdx.x * 8 + 3] = (unsigned long long)w_acc; p.prof[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - t_begin); }
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();          // neither CTA may free TMEM / exit while the pair's MMAs or remote arrives are in flight
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
 
@@ -917,16 +984,17 @@ int tc_conv_plan(const TcConvDesc& d, TcConvParams* pp, TcRefView* rv) {
       if (ok) { nch = cand; break; }
     }
     LADIFF_REQUIRE(nch > 0 && tile_halo <= 8, LADIFF_ERR_ARG, "tc_conv(transposed): no channel tile fits");
-    p.transposed = 1; p.NCH = nch; p.n_chtiles = d.CoutV / nch; p.stat_parts = 4;
+    p.transposed = d.want_transposed == 2 ? 2 : 1; p.NCH = nch; p.n_chtiles = d.CoutV / nch; p.stat_parts = 4;
+    LADIFF_REQUIRE(p.transposed == 1 || nch % 32 == 0, LADIFF_ERR_ARG, "tc_conv(pair): channel tile");
     p.NT = 128; p.NCLIP = 1; p.n_ptiles = cdiv(Lout, 128); p.NMMA = nch; p.n_ntiles = d.B * p.n_ptiles; p.BOXROWS = 136; p.CR = 32;
-    const long wslots = ((long)kSmemLimitT - 2048 - (long)kActSlots * kActBytes) / ((long)nch * 128);
+    const long wslots = ((long)kSmemLimitT - 2048 - (long)kActSlots * kActBytes) / ((long)(nch / p.transposed) * 128);
     p.S = wslots > kMaxWSlots ? kMaxWSlots : (int)wslots;
     LADIFF_REQUIRE(p.S >= 3, LADIFF_ERR_ARG, "tc_conv(transposed): weight ring too small");
     p.direct = (d.out32 != nullptr || d.res != nullptr) ? 1 : 0;
     p.tmW = *d.tmW;
     int rc = make_tmap_x(&p.tmX, d.x, d.B, Lv, Cv, pitch_v, d.x_bstride, p.BOXROWS);
     if (rc) return rc;
-    rc = make_tmap_wt(&p.tmWt, d.w, d.CoutV, d.Ktot, nch);
+    rc = make_tmap_wt(&p.tmWt, d.w, d.CoutV, d.Ktot, nch / p.transposed);
     if (rc) return rc;
     if (d.out32) { p.out = d.out32; p.out_f32 = 1; p.out_pitch = d.CoutV; p.out_bstride = (long long)Lout * d.CoutV; }
     else { p.out = d.out; p.out_f32 = 0; p.out_pitch = d.out_pitch; p.out_bstride = d.out_bstride; }
@@ -1002,37 +1070,57 @@ static size_t tc_smem_bytes(const TcConvParams& p) {
   return (size_t)p.S * p.stage_bytes + (p.direct ? (p.res ? (size_t)p.NMMA * 256 : 0) : (size_t)2 * kEpiGroups * p.CR * 256) + 2048;
 }
 
-static int tc_conv_t_launch(const TcConvParams& p, cudaStream_t st) {
-  const size_t smem = (size_t)kActSlots * kActBytes + (size_t)p.S * p.NCH * 128 + 2048;
+template <int CG>
+static int tc_conv_t_launch_cg(const TcConvParams& p, cudaStream_t st) {
+  const size_t smem = (size_t)kActSlots * kActBytes + (size_t)p.S * (p.NCH / CG) * 128 + 2048;
   LADIFF_REQUIRE(smem <= kSmemLimitT, LADIFF_ERR_ARG, "tc_conv(transposed): smem %zu too large", smem);
   static bool attr_set = false;
   if (!attr_set) {
-    LADIFF_CUDA_OK(cudaFuncSetAttribute(tc_conv_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimitT));
+    LADIFF_CUDA_OK(cudaFuncSetAttribute(tc_conv_t_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimitT));
     attr_set = true;
   }
-  const int tiles = p.n_chtiles * p.n_ptiles * p.B, nsm = tc_num_sms();
-  const int grid = tiles < nsm ? tiles : nsm;
+  const int n_pt = CG == 2 ? (p.Lout + 255) / 256 : p.n_ptiles;
+  const int tiles = p.n_chtiles * n_pt * p.B, nsm = tc_num_sms();
+  const int slots = nsm / CG;
+  const int grid = (tiles < slots ? tiles : slots) * CG;
   static const bool want_prof = getenv("LADIFF_TC_PROF") != nullptr;
-  if (!want_prof) {
-    LADIFF_CUDA_OK(launch_pdl(tc_conv_t_kernel, dim3(grid), dim3(kThreadsT), smem, st, p));
-    return 0;
-  }
   TcConvParams q = p;
   unsigned long long* dprof = nullptr;
-  LADIFF_CUDA_OK(cudaMalloc((void**)&dprof, sizeof(unsigned long long) * 8 * grid));
-  LADIFF_CUDA_OK(cudaMemset(dprof, 0, sizeof(unsigned long long) * 8 * grid));
-  q.prof = dprof;
-  tc_conv_t_kernel<<<grid, kThreadsT, smem, st>>>(q);
-  LADIFF_CUDA_OK(cudaGetLastError());
+  if (want_prof) {
+    LADIFF_CUDA_OK(cudaMalloc((void**)&dprof, sizeof(unsigned long long) * 8 * grid));
+    LADIFF_CUDA_OK(cudaMemset(dprof, 0, sizeof(unsigned long long) * 8 * grid));
+    q.prof = dprof;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreadsT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CG == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (ladiff_pdl_enabled() && !want_prof) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
+  LADIFF_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_conv_t_kernel<CG>, q));
+  if (!want_prof) return 0;
   LADIFF_CUDA_OK(cudaStreamSynchronize(st));
   std::vector<unsigned long long> hp((size_t)8 * grid);
   LADIFF_CUDA_OK(cudaMemcpy(hp.data(), dprof, sizeof(unsigned long long) * hp.size(), cudaMemcpyDeviceToHost));
   cudaFree(dprof);
   double a[5] = {0, 0, 0, 0, 0};
-  for (int i = 0; i < grid; ++i) for (int k = 0; k < 5; ++k) a[k] += (double)hp[(size_t)i * 8 + k] / grid;
-  fprintf(stderr, "[tc_prof_t] Cout=%d NCH=%d Wslots=%d grid=%d tiles=%d | cycles/CTA: total %.0f  producer-wait-empty %.0f  mma-wait-full %.0f  "
-                  "mma-wait-tmem %.0f  epi-wait-acc %.0f\n", p.Cout, p.NCH, p.S, grid, tiles, a[4], a[0], a[1], a[2], a[3]);
+  for (int i = 0; i < grid; i += CG) for (int k = 0; k < 5; ++k) a[k] += (double)hp[(size_t)i * 8 + k] / (grid / CG);
+  fprintf(stderr, "[tc_prof_t] CG=%d Cout=%d NCH=%d Wslots=%d grid=%d tiles=%d | cycles/CTA(leader): total %.0f  producer-wait-empty %.0f  mma-wait-full %.0f  "
+                  "mma-wait-tmem %.0f  epi-wait-acc %.0f\n", CG, p.Cout, p.NCH, p.S, grid, tiles, a[4], a[0], a[1], a[2], a[3]);
   return 0;
+}
+static int tc_conv_t_launch(const TcConvParams& p, cudaStream_t st) {
+  return p.transposed == 2 ? tc_conv_t_launch_cg<2>(p, st) : tc_conv_t_launch_cg<1>(p, st);
 }
 
 int tc_conv_launch(const TcConvParams& p, cudaStream_t st) {

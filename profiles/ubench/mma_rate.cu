@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256, 1) mma_rate_kernel(int N, int stages, int
 #pragma unroll
       for (int tap = 0; tap < 3; ++tap) {
         if (tap >= ntap) break;
-        const uint64_t a = adesc + ((mode & 2) ? 0 : tap * (16384 >> 4));
+        const uint64_t a = adesc + ((mode & 2) ? 0 : tap * (16384 >> 4)) + ((mode & 8) ? tap * 8 : 0);   // bit 3: row-shifted A start
         const uint64_t b = bdesc + ((mode & 1) ? tap * 8 : 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma<CG>(d, a + 2 * k, b + 2 * k, idesc, (tap | k) ? 1u : 0u);
@@ -196,6 +196,12 @@ int main(int argc, char** argv) {
   for (int n : ns) run<1>(n, 1 | 4 | 512, nsm, dout);
   printf("-- + both\n");
   for (int n : ns) run<1>(n, 1 | 4 | 256 | 512, nsm, dout);
+  printf("-- free-running issue: B start shifted by tap rows (bit0) / A start shifted (bit3) / neither\n");
+  for (int n : ns) run<1>(n, 0, nsm, dout);
+  for (int n : ns) run<1>(n, 1, nsm, dout);
+  for (int n : ns) run<1>(n, 8, nsm, dout);
+  for (int n : ns) run<2>(n == 144 ? 128 : n, 8, nsm, dout);
+  for (int n : ns) run<2>(n == 144 ? 128 : n, 0, nsm, dout);
   printf("-- both, on ONE SM only\n");
   for (int n : ns) run<1>(n, 1 | 4 | 256 | 512, 1, dout);
   return 0;

@@ -246,7 +246,7 @@ def test_strict_loader_errors():
 def test_tc_conv_operator_shapes():
     """tcgen05 conv operator vs torch on bf16-rounded operands: ragged L (not a tile multiple), k in {1,3,7}, Cin up to 2048,
     minimum size, several short clips packed per tile; fp32 (direct epilogue) and bf16 (smem-staged TMA-store epilogue)
-    outputs; tap-shared (impl 0) and per-tap (impl 2) activation tiles; the positions-on-M kernel (impl 3)."""
+    outputs; tap-shared (impl 0) and per-tap (impl 2) activation tiles; the positions-on-M kernel with one CTA (impl 3) and a cta_group::2 CTA pair (impl 4) per tile."""
     import torch.nn.functional as F
     from ladiffcodec_b200 import _lib
     lib = _lib.get_lib()
@@ -261,7 +261,7 @@ def test_tc_conv_operator_shapes():
         ref = F.conv1d(x.float().permute(0, 2, 1), w.to(torch.bfloat16).float(), bias, padding=(k - 1) // 2).permute(0, 2, 1)
         s_ref = ref.reshape(B, L, Cout // 32, 32).sum(dim=(1, 3))
         xd, wd, bd = x.cuda(), w.cuda(), bias.cuda()
-        for impl in (0, 2, 3):
+        for impl in (0, 2, 3, 4):
             for f32 in (1, 0):
                 y = torch.full((B, L, Cout), float("nan"), device="cuda", dtype=torch.float32 if f32 else torch.bfloat16)
                 st = torch.zeros(B, Cout // 32, 2, device="cuda")
