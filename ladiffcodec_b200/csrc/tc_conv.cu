@@ -379,20 +379,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
               }
             }
           };
-          // two register sets: the TMEM load of the next 16 columns is in flight while the current ones are consumed
+          // both 16-column loads of a chunk are issued back to back and waited for ONCE: tcgen05.wait::ld costs a few hundred
+          // cycles while the tensor pipe is busy, whatever is outstanding
           uint32_t ra[16], rb[16];
-          if (!no_ld) tmem_ld16_async(tcol, ra);
-          for (int c0 = 0; c0 < nrows; c0 += 32) {
-            tmem_ld_wait();
-            const bool has_b = c0 + 16 < nrows;
-            if (has_b && !no_ld) tmem_ld16_async(tcol + (uint32_t)(c0 + 16), rb);
-            consume(ra, c0);
-            if (has_b) {
-              tmem_ld_wait();
-              if (c0 + 32 < nrows && !no_ld) tmem_ld16_async(tcol + (uint32_t)(c0 + 32), ra);
-              consume(rb, c0 + 16);
-            }
-          }
+          const bool has_b = nrows > 16;
+          if (!no_ld) { tmem_ld16_async(tcol, ra); if (has_b) tmem_ld16_async(tcol + 16u, rb); }
+          tmem_ld_wait();
+          consume(ra, 0);
+          if (has_b) consume(rb, 16);
           const long long te2 = prof ? clock64() : 0;
           if (!p.direct) {
             fence_async_smem();

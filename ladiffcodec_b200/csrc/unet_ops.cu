@@ -1,4 +1,6 @@
 // Element-wise / normalisation / attention kernels of the UNet (channels-last bf16, fp32 math).
+#include <stdlib.h>
+
 #include "unet_ops.cuh"
 
 namespace {
@@ -140,10 +142,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a, int rows_p
 // ------------------------------------------------------------------ channel LayerNorm: each warp normalises LN_R rows at once
 // (all of their loads are issued before the first reduction: the kernel is latency-bound, not bandwidth-bound)
 template <int NVEC>
-__global__ void __launch_bounds__(256) layernorm_cl_kernel(ClView x, const float* __restrict__ g, ClView res, ClView out, int L) {
+__global__ void __launch_bounds__(256) layernorm_cl_kernel(ClView x, const float* __restrict__ g, ClView res, ClView out, int L, int B) {
   constexpr int LN_R = NVEC >= 4 ? 1 : (NVEC >= 2 ? 2 : 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = (blockIdx.x * 8 + warp) * LN_R, b = blockIdx.y;
   constexpr int C = NVEC * 256;
   float gg[NVEC][8];
 #pragma unroll
@@ -155,55 +156,58 @@ __global__ void __launch_bounds__(256) layernorm_cl_kernel(ClView x, const float
   }
   pdl_wait();       // the gains above are parameters: fetched while the producing kernel drains
   pdl_trigger();
-  if (row0 >= L) return;
-  uint4 raw[LN_R][NVEC], rres[LN_R][NVEC];
+  const int gpc = (L + LN_R - 1) / LN_R, total = gpc * B;      // row groups per clip / in all
+  for (int rg = blockIdx.x * 8 + warp; rg < total; rg += gridDim.x * 8) {
+    const int b = rg / gpc, row0 = (rg - b * gpc) * LN_R;
+    uint4 raw[LN_R][NVEC], rres[LN_R][NVEC];
 #pragma unroll
-  for (int r = 0; r < LN_R; ++r) {
-    if (row0 + r >= L) break;
-    const bf16* xr = x.p + (long long)b * x.bstride + (long long)(row0 + r) * x.pitch;
+    for (int r = 0; r < LN_R; ++r) {
+      if (row0 + r >= L) break;
+      const bf16* xr = x.p + (long long)b * x.bstride + (long long)(row0 + r) * x.pitch;
 #pragma unroll
-    for (int i = 0; i < NVEC; ++i) raw[r][i] = __ldcg(reinterpret_cast<const uint4*>(xr + (lane + 32 * i) * 8));
-    if (res.p) {
-      const bf16* rr = res.p + (long long)b * res.bstride + (long long)(row0 + r) * res.pitch;
-#pragma unroll
-      for (int i = 0; i < NVEC; ++i) rres[r][i] = __ldcg(reinterpret_cast<const uint4*>(rr + (lane + 32 * i) * 8));
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < LN_R; ++r) {
-    if (row0 + r >= L) break;
-    float v[NVEC][8];
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < NVEC; ++i) {
-      unpack8(raw[r][i], v[i]);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s += v[i][j];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s / (float)C;
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < NVEC; ++i)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; q += d * d; }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = rsqrtf(q / (float)C + 1e-5f);
-    bf16* orow = out.p + (long long)b * out.bstride + (long long)(row0 + r) * out.pitch;
-#pragma unroll
-    for (int i = 0; i < NVEC; ++i) {
-      float f[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = (v[i][j] - mean) * rstd * gg[i][j];
+      for (int i = 0; i < NVEC; ++i) raw[r][i] = __ldcg(reinterpret_cast<const uint4*>(xr + (lane + 32 * i) * 8));
       if (res.p) {
-        float rr[8];
-        unpack8(rres[r][i], rr);
+        const bf16* rr = res.p + (long long)b * res.bstride + (long long)(row0 + r) * res.pitch;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] += rr[j];
+        for (int i = 0; i < NVEC; ++i) rres[r][i] = __ldcg(reinterpret_cast<const uint4*>(rr + (lane + 32 * i) * 8));
       }
-      *reinterpret_cast<uint4*>(orow + (lane + 32 * i) * 8) = pack8(f);
+    }
+#pragma unroll
+    for (int r = 0; r < LN_R; ++r) {
+      if (row0 + r >= L) break;
+      float v[NVEC][8];
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < NVEC; ++i) {
+        unpack8(raw[r][i], v[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += v[i][j];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mean = sum / (float)C;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < NVEC; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; q += d * d; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = rsqrtf(q / (float)C + 1e-5f);
+      bf16* orow = out.p + (long long)b * out.bstride + (long long)(row0 + r) * out.pitch;
+#pragma unroll
+      for (int i = 0; i < NVEC; ++i) {
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = (v[i][j] - mean) * rstd * gg[i][j];
+        if (res.p) {
+          float rr[8];
+          unpack8(rres[r][i], rr);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] += rr[j];
+        }
+        *reinterpret_cast<uint4*>(orow + (lane + 32 * i) * 8) = pack8(f);
+      }
     }
   }
 }
@@ -666,7 +670,8 @@ int gn_apply_launch(const GnApplyArgs& a, int B, cudaStream_t st) {
   const int C = a.y.C;
   LADIFF_REQUIRE(C == 256 || C == 512 || C == 1024, LADIFF_ERR_ARG, "gn_apply: C=%d", C);
   const int rstep = 256 / (C / 8);
-  int rows = cdiv(a.L * B, 3 * 148);                     // one wave of ~3 CTAs per SM, resident before the producer ends (PDL)
+  static const int gn_cps = getenv("LADIFF_GN_CPS") ? atoi(getenv("LADIFF_GN_CPS")) : 2;   // CTAs per SM (experiment knob)
+  int rows = cdiv(a.L * B, gn_cps * 148);                // one wave of ~gn_cps CTAs per SM, resident before the producer ends (PDL)
   rows = cdiv(rows < rstep ? rstep : rows, rstep) * rstep;
   dim3 grid(cdiv(a.L, rows), B);
   LADIFF_CARVEOUT_ONCE(gn_apply_kernel);
@@ -676,12 +681,15 @@ int gn_apply_launch(const GnApplyArgs& a, int B, cudaStream_t st) {
 
 int layernorm_cl_launch(ClView x, const float* g, ClView res, ClView out, int B, int L, cudaStream_t st) {
   const int nvec = x.C / 256, ln_r = nvec >= 4 ? 1 : (nvec >= 2 ? 2 : 4);   // rows per warp, as in the kernel
-  dim3 grid(cdiv(L, 8 * ln_r), B);
+  static const int ln_cps = getenv("LADIFF_LN_CPS") ? atoi(getenv("LADIFF_LN_CPS")) : 0;   // CTAs per SM (0: one row group per warp)
+  int nblk = cdiv(cdiv(L, ln_r) * B, 8);
+  if (ln_cps > 0 && nblk > ln_cps * 148) nblk = ln_cps * 148;
+  dim3 grid(nblk);
   switch (x.C) {
-    case 256: LADIFF_CARVEOUT_ONCE(layernorm_cl_kernel<1>); LADIFF_CUDA_OK(launch_pdl(layernorm_cl_kernel<1>, grid, dim3(256), 0, st, x, g, res, out, L)); break;
-    case 512: LADIFF_CARVEOUT_ONCE(layernorm_cl_kernel<2>); LADIFF_CUDA_OK(launch_pdl(layernorm_cl_kernel<2>, grid, dim3(256), 0, st, x, g, res, out, L)); break;
-    case 768: LADIFF_CARVEOUT_ONCE(layernorm_cl_kernel<3>); LADIFF_CUDA_OK(launch_pdl(layernorm_cl_kernel<3>, grid, dim3(256), 0, st, x, g, res, out, L)); break;
-    case 1024: LADIFF_CARVEOUT_ONCE(layernorm_cl_kernel<4>); LADIFF_CUDA_OK(launch_pdl(layernorm_cl_kernel<4>, grid, dim3(256), 0, st, x, g, res, out, L)); break;
+    case 256: LADIFF_CARVEOUT_ONCE(layernorm_cl_kernel<1>); LADIFF_CUDA_OK(launch_pdl(layernorm_cl_kernel<1>, grid, dim3(256), 0, st, x, g, res, out, L, B)); break;
+    case 512: LADIFF_CARVEOUT_ONCE(layernorm_cl_kernel<2>); LADIFF_CUDA_OK(launch_pdl(layernorm_cl_kernel<2>, grid, dim3(256), 0, st, x, g, res, out, L, B)); break;
+    case 768: LADIFF_CARVEOUT_ONCE(layernorm_cl_kernel<3>); LADIFF_CUDA_OK(launch_pdl(layernorm_cl_kernel<3>, grid, dim3(256), 0, st, x, g, res, out, L, B)); break;
+    case 1024: LADIFF_CARVEOUT_ONCE(layernorm_cl_kernel<4>); LADIFF_CUDA_OK(launch_pdl(layernorm_cl_kernel<4>, grid, dim3(256), 0, st, x, g, res, out, L, B)); break;
     default: LADIFF_REQUIRE(false, LADIFF_ERR_ARG, "layernorm_cl: unsupported C=%d", x.C);
   }
   LADIFF_CUDA_OK(cudaGetLastError());
@@ -689,7 +697,8 @@ int layernorm_cl_launch(ClView x, const float* g, ClView res, ClView out, int B,
 }
 
 void linattn_split(int B, int L, int* S, int* nsplit) {
-  const int target = cdiv(600, 4 * B);                  // ~4 CTAs per SM over (split, head, clip)
+  static const int la_ctas = getenv("LADIFF_LA_CTAS") ? atoi(getenv("LADIFF_LA_CTAS")) : 600;   // CTAs aimed at over (split, head, clip)
+  const int target = cdiv(la_ctas, 4 * B);
   int s = cdiv(L, target < 1 ? 1 : target);
   s = s < 32 ? 32 : (s > LA_S ? LA_S : s);
   *S = s;
