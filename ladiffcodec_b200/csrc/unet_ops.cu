@@ -6,6 +6,13 @@
 namespace {
 
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+// SiLU(2h) = h + h*tanh(h): one MUFU (tanh.approx.f32, rel. error 2^-11 -> <= 2^-12 of the result, below the bf16 rounding of
+// the stored activation) instead of ex2 + rcp; callers fold the factor 1/2 into their affine transform
+__device__ __forceinline__ float silu_from_half(float h) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -109,7 +116,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a, int rows_p
         g *= sc;
         bb = bb * sc + fsh[j];
       }
-      sa[j] = g; sb[j] = bb;
+      sa[j] = 0.5f * g; sb[j] = 0.5f * bb;      // half-scale: silu_from_half
     }
   }
   for (;;) {
@@ -120,7 +127,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a, int rows_p
       float f[8];
       unpack8(u[k], f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j] * sa[j] + sb[j]);
+      for (int j = 0; j < 8; ++j) f[j] = silu_from_half(fmaf(f[j], sa[j], sb[j]));
       if (rb) {
         float rr[8];
         unpack8(ur[k], rr);
