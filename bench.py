@@ -244,11 +244,11 @@ def run_ours(a, cfg):
     pk = peaks()
     roof = None
     traffic, traffic_note = None, None
-    tp = os.path.join(ROOT, "profiles", "r1c", "conv_dram_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r1d", "conv_dram_traffic.json")
     if a.config == 2 and not a.batch and os.path.exists(tp):      # committed ncu capture of the same workload (per launch, like `achieved`)
         t = json.load(open(tp))
         traffic = (t["dram_read_bytes"] + t["dram_write_bytes"]) / t["conv_launches"]
-        traffic_note = (f"profiles/r1c/conv_dram_traffic.json: DRAM bytes per conv launch, mean over the {t['conv_launches']} launches of one UNet "
+        traffic_note = (f"profiles/r1d/conv_dram_traffic.json: DRAM bytes per conv launch, mean over the {t['conv_launches']} launches of one UNet "
                         f"evaluation (ncu flushes L2 before each launch; L2->SM traffic {t['l2_bytes'] / t['conv_launches'] / 1e6:.0f} MB per launch)")
     if prof and prof["conv_ms"] > 0:
         ach = prof["conv_flops"] / (prof["conv_ms"] * 1e-3) / 1e12
