@@ -343,3 +343,42 @@ def test_long_utterance_against_oracle():
     assert pc.snr_db(out, ref) >= pc.TOL["wav_snr_db"]
     del m, c
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("B,T,layout", [(1, 640, "A"), (3, 1280, "A"), (5, 1920, "B"), (2, 640 * 7, "B")])
+def test_edge_shapes_against_oracle(B, T, layout):
+    """Smallest legal clip (one 640-sample block: 2 conditioning frames, latent L = 80 / 20 → bottleneck of 5 / 1.25 → L must
+    be a multiple of 16 for the UNet: Layout-B needs T % 512 == 0, so those cases use multiples that satisfy both), odd batch
+    sizes, lengths that are not multiples of any tile size — all through the one-call entry, against the oracle."""
+    from ladiffcodec_b200.config import readme_args, sample_args
+    from ladiffcodec_b200.sample import synthesize
+    if layout == "A":
+        args = readme_args()
+        hop = 8
+    else:
+        args = sample_args(run_diff=True, cond_bandwidth=3.0, enc_ratios=[8, 4], upsampling_ratios=[5, 2], diff_dims=256,
+                           model_for_cond="c", model_path="m")
+        hop = 32
+    if (T // hop) % 16 != 0:
+        T = (T // (hop * 16) + 1) * hop * 16
+        T = (T + 639) // 640 * 640
+        while (T // hop) % 16 != 0 or T % 640 != 0:
+            T += 640
+    sdm = pc.make_state_dict(seed=21, **pc.ladiff_model_kwargs(args))
+    sdc = pc.make_state_dict(seed=22, **pc.cond_model_kwargs(args))
+    m, c = pc.cuda_models(args, sdm, sdc)
+    n_steps = 2
+    wav = pc.make_clips(B, T, seed=B * 7 + T)
+    L = T // hop
+    noise = torch.randn(n_steps - 1, B, 128, L, generator=torch.Generator().manual_seed(B + T))
+    out, lat = synthesize(m, c, wav.cuda(), n_steps=n_steps, noise=noise, return_latent=True)
+    stages = {}
+    with torch.no_grad():
+        ref = O.synthesize(wav, sdm, sdc, n_steps=n_steps, noise=noise, cond_bandwidth=args.cond_bandwidth,
+                           enc_ratios=args.enc_ratios, upsampling_ratios=args.upsampling_ratios, diff_dims=args.diff_dims,
+                           unet_scale_cond=args.unet_scale_cond, fast_lstm=True, stages=stages)
+    assert out.shape == (B, 1, T)
+    assert pc.rel_l2(lat, stages["latent"]) <= pc.TOL["latent_rel_l2"]
+    assert pc.snr_db(out, ref) >= pc.TOL["wav_snr_db"]
+    del m, c
+    torch.cuda.empty_cache()
