@@ -838,9 +838,11 @@ struct PlanBuilder {
     pl->launches_per_run++;
     return 0;
   }
-  int gn(ClView y, int L, int n_ntiles, const float* g, const float* b, const float* film, ClView res, ClView out, bool do_tanh) {
+  int gn(ClView y, int L, int n_ntiles, const float* g, const float* b, const float* film, ClView res, ClView out, bool do_tanh,
+         const float* ln_g = nullptr, ClView ln_out = ClView{nullptr, 0, 0, 0}) {
     GnApplyArgs a;
     memset(&a, 0, sizeof(a));
+    a.ln_g = ln_g; a.ln_out = ln_out;
     a.y = y; a.stats = pl->bufs.stats; a.n_ntiles = n_ntiles; a.gamma = g; a.beta = b; a.film = film;
     a.film_stride = h->un.film_stride; a.t_dev = pl->bufs.t_dev; a.res = res; a.out = out; a.L = L; a.do_tanh = do_tanh ? 1 : 0;
     const int BB = B;
@@ -850,7 +852,9 @@ struct PlanBuilder {
     return 0;
   }
   // ResnetBlock (unet.py:176-192): out = SiLU(GN(conv2(SiLU(FiLM(GN(conv1(x))))))) + res_conv(x)
-  int resnet(const ResnetW& r, ClView x, int L, ClView out, bool do_tanh = false) {
+  // ln_g != null: the block's output also leaves channel-LayerNorm'ed (the following attention's pre-norm) in ln_out
+  int resnet(const ResnetW& r, ClView x, int L, ClView out, bool do_tanh = false, const float* ln_g = nullptr,
+             ClView ln_out = ClView{nullptr, 0, 0, 0}) {
     UnetBufs& u = pl->bufs;
     ClView none; memset(&none, 0, sizeof(none));
     ClView y = view(u.tY, L, r.Cout, r.Cout), hh = view(u.tH, L, r.Cout, r.Cout);
@@ -864,7 +868,7 @@ struct PlanBuilder {
     }
     TRY(gn(y, L, nt, r.g1, r.b1, h->un.film + r.film_off, none, hh, false));
     TRY(conv(r.c2, hh, L, y, nullptr, true, &nt, none));
-    TRY(gn(y, L, nt, r.g2, r.b2, nullptr, resv, out, do_tanh));
+    TRY(gn(y, L, nt, r.g2, r.b2, nullptr, resv, out, do_tanh, ln_g, ln_out));
     return 0;
   }
   int layernorm(ClView x, const float* g, ClView res, ClView out, int L) {
@@ -875,11 +879,12 @@ struct PlanBuilder {
     return 0;
   }
   // Residual(PreNorm(LinearAttention)) (unet.py:194-222) / Residual(PreNorm(Attention)) (:224-246)
-  int attention(const AttnW& a, ClView x, int L, ClView out, bool linear) {
+  // pre_normed: `ln` (tH) already holds LN(x)*norm_g, written by the producing GroupNorm-apply
+  int attention(const AttnW& a, ClView x, int L, ClView out, bool linear, bool pre_normed = false) {
     UnetBufs& u = pl->bufs;
     ClView none; memset(&none, 0, sizeof(none));
     ClView ln = view(u.tH, L, a.C, a.C), qkv = view(u.qkv, L, 384, 384), ao = view(u.ao, L, 128, 128);
-    TRY(layernorm(x, a.norm_g, none, ln, L));
+    if (!pre_normed) TRY(layernorm(x, a.norm_g, none, ln, L));
     TRY(conv(a.qkv, ln, L, qkv, nullptr, false, nullptr, none));
     const int BB = B; float* ctx = u.ctx; float* lap = u.la_part; int* lac = u.la_cnt;
     if (linear) {
@@ -921,6 +926,7 @@ int build_plan(H* h, void* ws_unet, int B, int L, cudaStream_t st, Plan** out) {
   ClView none; memset(&none, 0, sizeof(none));
   int rc = 0;
   auto CHECK = [&](int r) { if (r && !rc) rc = r; };
+  static const bool fuse_ln = getenv("LADIFF_NO_LN_FUSE") == nullptr;   // attention pre-norm fused into the producing GroupNorm-apply
   // init_conv on cat(cond_up, x); its output is also `r` of the final concat (unet.py:430-435,464)
   ClView xin = view(u.xin, L, 256, 256);
   ClView r0 = view(u.FC, L, 2 * d[0], d[0], d[0]);
@@ -932,8 +938,8 @@ int build_plan(H* h, void* ws_unet, int B, int L, cudaStream_t st, Plan** out) {
     ClView skip2 = view(u.CA[i], Li, pitchC, C, d[i + 1]);
     ClView o2 = view(u.tO, Li, C, C);
     CHECK(pb.resnet(w.d[i][0], x, Li, skip1));
-    CHECK(pb.resnet(w.d[i][1], skip1, Li, o2));
-    CHECK(pb.attention(w.da[i], o2, Li, skip2, true));
+    CHECK(pb.resnet(w.d[i][1], skip1, Li, o2, false, fuse_ln ? w.da[i].norm_g : nullptr, view(u.tH, Li, C, C)));
+    CHECK(pb.attention(w.da[i], o2, Li, skip2, true, fuse_ln));
     const int Ln = i < 4 ? Li / 2 : Li;
     ClView xn = view(u.X[i + 1], Ln, d[i + 1], d[i + 1]);
     CHECK(pb.conv(w.down[i], skip2, Li, xn, nullptr, false, nullptr, none));
@@ -943,8 +949,8 @@ int build_plan(H* h, void* ws_unet, int B, int L, cudaStream_t st, Plan** out) {
   if (!rc) {
     ClView m1 = view(u.tO, Lm, Cm, Cm), m2 = view(u.tA, Lm, Cm, Cm);
     ClView m3 = view(u.CA[4], Lm, d[5] + d[4], d[5], 0);
-    CHECK(pb.resnet(w.mid1, x, Lm, m1));
-    CHECK(pb.attention(w.mida, m1, Lm, m2, false));
+    CHECK(pb.resnet(w.mid1, x, Lm, m1, false, fuse_ln ? w.mida.norm_g : nullptr, view(u.tH, Lm, Cm, Cm)));
+    CHECK(pb.attention(w.mida, m1, Lm, m2, false, fuse_ln));
     CHECK(pb.resnet(w.mid2, m2, Lm, m3));
   }
   for (int j = 0; j < 5 && !rc; ++j) {
@@ -953,8 +959,8 @@ int build_plan(H* h, void* ws_unet, int B, int L, cudaStream_t st, Plan** out) {
     ClView b1 = view(u.CB[i], Li, pitchC, Cout, 0);
     ClView o2 = view(u.tO, Li, Cout, Cout), at = view(u.tA, Li, Cout, Cout);
     CHECK(pb.resnet(w.u[j][0], ca, Li, b1));
-    CHECK(pb.resnet(w.u[j][1], cb, Li, o2));
-    CHECK(pb.attention(w.ua[j], o2, Li, at, true));
+    CHECK(pb.resnet(w.u[j][1], cb, Li, o2, false, fuse_ln ? w.ua[j].norm_g : nullptr, view(u.tH, Li, Cout, Cout)));
+    CHECK(pb.attention(w.ua[j], o2, Li, at, true, fuse_ln));
     if (j < 4) {
       const int pn = d[i] + d[i - 1];   // pitch of CA[i-1]; x part = channels [0, d[i])
       ClView dst = view(u.CA[i - 1], 2 * Li, pn, d[i], 0);

@@ -45,7 +45,12 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a, int rows_p
   const int cv = C / 8;                       // 8-channel chunks per row: 32, 64 or 128
   const int c0 = (threadIdx.x % cv) * 8, rsub = threadIdx.x / cv, rstep = 256 / cv;
   __shared__ float s_mean[8], s_rstd[8];
-  float ga[8], be[8], fsc[8], fsh[8];
+  __shared__ float2 ln_part[2][GN_U][8];      // fused LayerNorm: per-warp (sum, sumsq) of a row segment, double-buffered by batch
+  float ga[8], be[8], fsc[8], fsh[8], lng[8];
+  if (a.ln_g) {
+    const float4 l0 = __ldg(reinterpret_cast<const float4*>(a.ln_g + c0)), l1 = __ldg(reinterpret_cast<const float4*>(a.ln_g + c0) + 1);
+    lng[0] = l0.x; lng[1] = l0.y; lng[2] = l0.z; lng[3] = l0.w; lng[4] = l1.x; lng[5] = l1.y; lng[6] = l1.z; lng[7] = l1.w;
+  }
   {
     const float4* g4 = reinterpret_cast<const float4*>(a.gamma + c0);
     const float4* b4 = reinterpret_cast<const float4*>(a.beta + c0);
@@ -119,30 +124,95 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a, int rows_p
       sa[j] = 0.5f * g; sb[j] = 0.5f * bb;      // half-scale: silu_from_half
     }
   }
-  for (;;) {
+  if (!a.ln_g) {
+    for (;;) {
+#pragma unroll
+      for (int k = 0; k < GN_U; ++k) {
+        const int r = row + k * rstep;
+        if (r >= r1) break;
+        float f[8];
+        unpack8(u[k], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = silu_from_half(fmaf(f[j], sa[j], sb[j]));
+        if (rb) {
+          float rr[8];
+          unpack8(ur[k], rr);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] += rr[j];
+        }
+        if (a.do_tanh) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = tanhf(f[j]);
+        }
+        *reinterpret_cast<uint4*>(ob + (long long)r * a.out.pitch) = pack8(f);
+      }
+      row += GN_U * rstep;
+      if (row >= r1) break;
+      load_batch(row);
+    }
+    return;
+  }
+  // ---- with the attention pre-norm fused: the cv threads that share a row (cv/32 whole warps) reduce (sum, sumsq) of the
+  // bf16-rounded result, so LN sees exactly the tensor the unfused kernel would read back.  Uniform trip count per CTA.
+  const int wpr = cv >> 5;                                 // warps per row
+  bf16* lb = a.ln_out.p + (long long)b * a.ln_out.bstride + c0;
+  const int nbatch = (r1 - r0 + GN_U * rstep - 1) / (GN_U * rstep);
+  for (int it = 0; it < nbatch; ++it) {
+    uint4 o[GN_U];
+    float2 st[GN_U];
 #pragma unroll
     for (int k = 0; k < GN_U; ++k) {
       const int r = row + k * rstep;
-      if (r >= r1) break;
-      float f[8];
-      unpack8(u[k], f);
+      st[k] = make_float2(0.f, 0.f);
+      o[k] = make_uint4(0u, 0u, 0u, 0u);
+      if (r < r1) {
+        float f[8];
+        unpack8(u[k], f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = silu_from_half(fmaf(f[j], sa[j], sb[j]));
-      if (rb) {
-        float rr[8];
-        unpack8(ur[k], rr);
+        for (int j = 0; j < 8; ++j) f[j] = silu_from_half(fmaf(f[j], sa[j], sb[j]));
+        if (rb) {
+          float rr[8];
+          unpack8(ur[k], rr);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] += rr[j];
+          for (int j = 0; j < 8; ++j) f[j] += rr[j];
+        }
+        o[k] = pack8(f);
+        *reinterpret_cast<uint4*>(ob + (long long)r * a.out.pitch) = o[k];
+        unpack8(o[k], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { st[k].x += f[j]; st[k].y = fmaf(f[j], f[j], st[k].y); }
       }
-      if (a.do_tanh) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = tanhf(f[j]);
+      for (int sh = 16; sh > 0; sh >>= 1) {
+        st[k].x += __shfl_xor_sync(0xffffffffu, st[k].x, sh);
+        st[k].y += __shfl_xor_sync(0xffffffffu, st[k].y, sh);
       }
-      *reinterpret_cast<uint4*>(ob + (long long)r * a.out.pitch) = pack8(f);
+      if (wpr > 1 && lane == 0) ln_part[it & 1][k][warp] = st[k];
     }
-    row += GN_U * rstep;
-    if (row >= r1) break;
-    load_batch(row);
+    if (wpr > 1) __syncthreads();
+    const int rnext = row + GN_U * rstep;
+    if (it + 1 < nbatch) load_batch(rnext);                // next batch in flight during the normalisation
+#pragma unroll
+    for (int k = 0; k < GN_U; ++k) {
+      const int r = row + k * rstep;
+      if (r >= r1) continue;
+      float2 t = st[k];
+      if (wpr > 1) {
+        const int w0 = (warp / wpr) * wpr;
+        t = make_float2(0.f, 0.f);
+        for (int w = w0; w < w0 + wpr; ++w) { const float2 v = ln_part[it & 1][k][w]; t.x += v.x; t.y += v.y; }
+      }
+      const float mean = t.x / (float)C;
+      float var = t.y / (float)C - mean * mean;
+      var = var < 0.f ? 0.f : var;
+      const float rstd = rsqrtf(var + 1e-5f);
+      float f[8];
+      unpack8(o[k], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean) * rstd * lng[j];
+      *reinterpret_cast<uint4*>(lb + (long long)r * a.ln_out.pitch) = pack8(f);
+    }
+    row = rnext;
   }
 }
 

@@ -24,6 +24,9 @@ struct GnApplyArgs {
   ClView out;
   int L;
   int do_tanh;
+  // optional fused channel LayerNorm of the result (the attention block's pre-norm, unet.py:82-101): ln_out = LN(out) * ln_g
+  const float* ln_g;   // [C] or null
+  ClView ln_out;
 };
 int gn_apply_launch(const GnApplyArgs& a, int B, cudaStream_t st);
 

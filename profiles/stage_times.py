@@ -51,10 +51,13 @@ def main():
                 best = min(best, e0.elapsed_time(e1))
         return best
 
-    ta, tb = t(a.steps_a), t(a.steps_b)
+    model.take_launch_count(); cmodel.take_launch_count()
+    ta = t(a.steps_a)
+    launches_a = (model.take_launch_count() + cmodel.take_launch_count()) // 4
+    tb = t(a.steps_b)
     per_step = (tb - ta) / (a.steps_b - a.steps_a)
     out = dict(config=a.config, batch=B, ms_a=ta, ms_b=tb, steps_a=a.steps_a, steps_b=a.steps_b, ms_per_ddpm_step=per_step,
-               ms_fixed=ta - a.steps_a * per_step,
+               ms_fixed=ta - a.steps_a * per_step, launches_per_pass_a=launches_a,
                env={k: os.environ[k] for k in os.environ if k.startswith("LADIFF_")})
     print(json.dumps(out))
 
