@@ -568,6 +568,77 @@ __global__ void __launch_bounds__(256) fullattn_kernel(ClView qkv, ClView out, i
       out.p[(long long)b * out.bstride + (long long)qi[u] * out.pitch + h * 32 + lane] = __float2bfloat16(acc[u] / l[u]);
 }
 
+// ------------------------------------------------------------------ full attention, keys resident in shared memory
+// grid (ceil(n/128), 4, B), 128 threads: one query per thread (registers), K and V of the (clip, head) staged once as fp32;
+// exact two-pass softmax (scores recomputed in the second pass instead of stored).  Used when n <= FA2_MAX_KEYS.
+constexpr int FA2_MAX_KEYS = 512;
+__global__ void __launch_bounds__(128) fullattn2_kernel(ClView qkv, ClView out, int L) {
+  extern __shared__ __align__(16) float fa_sm[];
+  float* ks = fa_sm;                 // [L][32]
+  float* vs = fa_sm + (size_t)L * 32;
+  const int h = blockIdx.y, b = blockIdx.z;
+  pdl_wait();
+  pdl_trigger();
+  const bf16* base = qkv.p + (long long)b * qkv.bstride;
+  for (int i = threadIdx.x; i < L * 8; i += 128) {          // 8 x 16 B per key row: k (4) then v (4)
+    const int j = i >> 3, c = i & 7;
+    float f[8];
+    unpack8(__ldcg(reinterpret_cast<const uint4*>(base + (long long)j * qkv.pitch + (c < 4 ? 128 : 256) + h * 32 + (c & 3) * 8)), f);
+    float4* d4 = reinterpret_cast<float4*>((c < 4 ? ks : vs) + (size_t)j * 32 + (c & 3) * 8);
+    d4[0] = make_float4(f[0], f[1], f[2], f[3]);
+    d4[1] = make_float4(f[4], f[5], f[6], f[7]);
+  }
+  const int qi = blockIdx.x * 128 + threadIdx.x;
+  float q[32];
+  if (qi < L) {
+    const bf16* qr = base + (long long)qi * qkv.pitch + h * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float f[8];
+      unpack8(__ldcg(reinterpret_cast<const uint4*>(qr + 8 * i)), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) q[8 * i + j] = f[j] * 0.17677669529663687f;     // q * 32^-0.5 (unet.py:238)
+    }
+  }
+  __syncthreads();
+  if (qi >= L) return;
+  auto score = [&](int j) {
+    const float4* k4 = reinterpret_cast<const float4*>(ks + (size_t)j * 32);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      const float4 a = k4[i], c = k4[i + 1];
+      s0 += q[4 * i] * a.x; s0 += q[4 * i + 1] * a.y; s0 += q[4 * i + 2] * a.z; s0 += q[4 * i + 3] * a.w;
+      s1 += q[4 * i + 4] * c.x; s1 += q[4 * i + 5] * c.y; s1 += q[4 * i + 6] * c.z; s1 += q[4 * i + 7] * c.w;
+    }
+    return s0 + s1;
+  };
+  float m = -INFINITY;
+  for (int j = 0; j < L; ++j) m = fmaxf(m, score(j));
+  float l = 0.f, acc[32];
+#pragma unroll
+  for (int e = 0; e < 32; ++e) acc[e] = 0.f;
+  for (int j = 0; j < L; ++j) {
+    const float pj = __expf(score(j) - m);
+    l += pj;
+    const float4* v4 = reinterpret_cast<const float4*>(vs + (size_t)j * 32);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 v = v4[i];
+      acc[4 * i] += pj * v.x; acc[4 * i + 1] += pj * v.y; acc[4 * i + 2] += pj * v.z; acc[4 * i + 3] += pj * v.w;
+    }
+  }
+  const float inv = 1.f / l;
+  bf16* orow = out.p + (long long)b * out.bstride + (long long)qi * out.pitch + h * 32;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = acc[8 * i + j] * inv;
+    *reinterpret_cast<uint4*>(orow + 8 * i) = pack8(f);
+  }
+}
+
 // ------------------------------------------------------------------ layout conversion
 // NCL f32 -> channels-last bf16 (optionally scaled per clip).  grid (ceil(L/32), C/32, B), block (32, 8)
 __global__ void ncl_to_cl_kernel(const float* __restrict__ x, const float* __restrict__ inv_scale, ClView out, int C, int L) {
@@ -798,6 +869,18 @@ int linattn_launch(ClView qkv, float* ctx, float* part, int* counters, ClView ou
 }
 
 int fullattn_launch(ClView qkv, ClView out, int B, int L, cudaStream_t st) {
+  static const bool no_fa2 = getenv("LADIFF_NO_FA2") != nullptr;
+  if (L <= FA2_MAX_KEYS && !no_fa2) {
+    const size_t smem = (size_t)L * 64 * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+      LADIFF_CUDA_OK(cudaFuncSetAttribute(fullattn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA2_MAX_KEYS * 64 * (int)sizeof(float)));
+      prefer_max_smem_carveout(fullattn2_kernel);
+      attr = true;
+    }
+    LADIFF_CUDA_OK(launch_pdl(fullattn2_kernel, dim3(cdiv(L, 128), 4, B), dim3(128), smem, st, qkv, out, L));
+    return 0;
+  }
   LADIFF_CARVEOUT_ONCE(fullattn_kernel);
   LADIFF_CUDA_OK(launch_pdl(fullattn_kernel, dim3(cdiv(L, 32), 4, B), dim3(256), 0, st, qkv, out, L));
   return 0;
