@@ -98,6 +98,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
@@ -415,7 +416,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);   // 8 warps -> accumulator stage free for the MMA issuer
     }
-    if (store_warp) bulk_wait_all();
+    // the staging buffers must outlive the stores' shared-memory reads; their global writes are covered by grid completion
+    // (and by griddepcontrol.wait in the dependent kernel), so the CTA does not wait for them
+    if (store_warp) bulk_wait_read_0();
     if (prof && threadIdx.x == 64) { p.prof[blockIdx.x * 8 + 3] = (unsigned long long)w_acc; p.prof[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - t_begin);
       p.prof[blockIdx.x * 8 + 5] = (unsigned long long)w_e1; p.prof[blockIdx.x * 8 + 6] = (unsigned long long)w_e2; p.prof[blockIdx.x * 8 + 7] = (unsigned long long)w_e3; }
   }
