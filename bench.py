@@ -200,12 +200,16 @@ def run_ours(a, cfg):
         drain()
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if a.profiler_range and sets is dev_sets:
+            torch.cuda.profiler.start()
         e0.record()
         for i in range(a.steps):
             fn(sets[i % n_sets], a.warmup + i)
         drain()
         e1.record()
         sync_all()
+        if a.profiler_range and sets is dev_sets:
+            torch.cuda.profiler.stop()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -328,6 +332,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="clips per GPU (default: the config's)")
     ap.add_argument("--ddpm_steps", type=int, default=0)
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--profiler_range", action="store_true",
+                    help="bracket the timed `value` region with cudaProfilerStart/Stop (for `ncu --profile-from-start off`)")
     ap.add_argument("--depth", type=int, default=2, help="batches in flight (SynthesisPipeline); 1 = strictly one pass at a time")
     ap.add_argument("--dump_profile", default="", help="write the per-conv-launch table of one UNet evaluation here")
     a = ap.parse_args()
