@@ -791,15 +791,17 @@ struct PlanBuilder {
       TcRefView best_rv = rv;
       const bool multi = ps.NCLIP > 1 || ps.Lout + 8 <= 120;
       static const bool no_t = getenv("LADIFF_NO_TRANSPOSED") != nullptr;
-      for (int c = -2; c < 12; ++c) {
+      static const bool no_two = getenv("LADIFF_NO_TWO_PER_SM") != nullptr;
+      for (int c = -5; c < 12; ++c) {
         TcConvDesc dc = d;
-        if (c < 0) { if (no_t || ps.Lout < 128) continue; dc.want_transposed = -c; }    // positions-on-M kernel: one CTA / CTA pair per tile
+        if (c < -2) { if (no_two || multi) continue; dc.want_two_per_sm = 1; dc.want_nt = 128 - 16 * (-3 - c); }   // two CTAs per SM: NT = 128, 112, 96
+        else if (c < 0) { if (no_t || ps.Lout < 128) continue; dc.want_transposed = -c; }    // positions-on-M kernel: one CTA / CTA pair per tile
         else if (multi) { dc.want_nclip = c + 1; if (c >= 3) break; }
         else { dc.want_nt = 256 - 16 * c; if (dc.want_nt < 96) break; }
         TcConvParams pc2;
         TcRefView rv2;
         if (tc_conv_plan(dc, &pc2, &rv2) != 0) continue;                     // shape does not fit (smem, halo): skip
-        if (!pc2.transposed && pc2.NT == ps.NT && pc2.NCLIP == ps.NCLIP) continue;
+        if (!pc2.transposed && pc2.minb == ps.minb && pc2.NT == ps.NT && pc2.NCLIP == ps.NCLIP) continue;
         if (want_stats && pc2.n_ptiles * pc2.stat_parts * pc2.stat_slots > pl->bufs.stats_slots) continue;
         float ms = 0.f;
         TRY(time_one(pc2, &ms));
@@ -811,6 +813,7 @@ struct PlanBuilder {
     }
     d.tap_share = 0;
     d.want_nt = (ps.NCLIP == 1 && !ps.transposed) ? ps.NT : 0; d.want_nclip = ps.NCLIP > 1 ? ps.NCLIP : 0;
+    d.want_two_per_sm = 0;
     if (ps.transposed) {          // the per-tap check variant must produce the same GroupNorm-partial layout: reuse the chosen plan
       pu = ps;
     } else
@@ -830,9 +833,9 @@ struct PlanBuilder {
     pl->op_label.resize(pl->ops.size());
     {
       char buf[200];
-      snprintf(buf, sizeof(buf), "conv kind=%d Cout=%d Cin=%d k=%d Lout=%d NT=%d nclip=%d tiles=%d S=%d taps/stage=%d stats=%d direct=%d posM=%d", pc.kind,
+      snprintf(buf, sizeof(buf), "conv kind=%d Cout=%d Cin=%d k=%d Lout=%d NT=%d nclip=%d tiles=%d S=%d taps/stage=%d stats=%d direct=%d posM=%d perSM=%d", pc.kind,
                pc.CoutV, pc.Cin, pc.K, ps.Lout, ps.NT, ps.NCLIP, ps.transposed ? ps.n_chtiles * ps.n_ntiles : ps.MT * ps.n_ntiles, ps.S, ps.a_cap,
-               want_stats ? 1 : 0, ps.direct, ps.transposed ? ps.NCH : 0);
+               want_stats ? 1 : 0, ps.direct, ps.transposed ? ps.NCH : 0, ps.transposed ? 1 : ps.minb);
       pl->op_label.back() = buf;
     }
     pl->launches_per_run++;
@@ -1408,7 +1411,7 @@ extern "C" int32_t ladiff_op_conv1d_cl(const void* x_bf16, const float* w, const
                                        int32_t Cout, int32_t k, void* y, int32_t y_f32, int32_t impl, float* gn_stats) {
   LADIFF_REQUIRE(x_bf16 && w && y && Cin % 64 == 0 && Cout % 128 == 0 && k >= 1 && k <= TC_MAX_TAPS && (k & 1), LADIFF_ERR_ARG,
                  "ladiff_op_conv1d_cl: Cin %% 64, Cout %% 128, odd k <= %d required", TC_MAX_TAPS);
-  LADIFF_REQUIRE(impl >= 0 && impl <= 4, LADIFF_ERR_ARG, "ladiff_op_conv1d_cl: impl=%d", impl);
+  LADIFF_REQUIRE(impl >= 0 && impl <= 5, LADIFF_ERR_ARG, "ladiff_op_conv1d_cl: impl=%d", impl);
   bf16* wp = nullptr; float2* stats = nullptr;
   LADIFF_CUDA_OK(cudaMalloc((void**)&wp, sizeof(bf16) * (size_t)Cout * Cin * k));
   int rc = pack_conv_launch(w, wp, Cout, Cin, k, 0, 0);
@@ -1421,6 +1424,7 @@ extern "C" int32_t ladiff_op_conv1d_cl(const void* x_bf16, const float* w, const
   if (y_f32) d.out32 = (float*)y;
   else { d.out = (bf16*)y; d.out_bstride = (long long)L * Cout; d.out_pitch = Cout; }
   d.B = B; d.tap_share = impl == 2 ? 0 : 1; d.want_transposed = impl == 3 ? 1 : (impl == 4 ? 2 : 0);
+  if (impl == 5) { d.want_two_per_sm = 1; d.want_nt = 128; }
   TcConvParams p;
   TcRefView rv;
   if (!rc) rc = tc_conv_plan(d, &p, &rv);

@@ -35,6 +35,7 @@ constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;  // 16 KB
 constexpr int kMaxStages = 6;
 constexpr int kStageTaps = 3;    // weight tiles per pipeline stage
 constexpr size_t kSmemLimit = 232448 - 1024;     // 227 KB minus the static barriers
+constexpr size_t kSmemLimit2 = 112 * 1024;        // per CTA when two CTAs share an SM (228 KB per SM, 1 KB reserved per CTA)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -101,7 +102,10 @@ __device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void bulk_wait_read_0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
+__device__ __forceinline__ void epi_bar(int wg) {      // constant ids: ptxas then reserves 4 named barriers per CTA, not all 16
+  if (wg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+  else asm volatile("bar.sync 2, 128;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -140,7 +144,10 @@ __device__ __forceinline__ TileCoord decode_tile(const TcConvParams& p, int t) {
   return c;
 }
 
-__global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_constant__ TcConvParams p) {
+// MINB = 2: the same code compiled to <= 102 registers so that two CTAs of a small-footprint launch (<= 112 KB shared memory, <= 256
+// TMEM columns) share an SM: one CTA's prologue / epilogue then overlaps the other's main loop.
+template <int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_constant__ TcConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -1021,13 +1028,18 @@ int tc_conv_plan(const TcConvDesc& d, TcConvParams* pp, TcRefView* rv) {
   // shared-memory budget: S pipeline stages + 2 epilogue staging chunks per epilogue warpgroup + 1 KB alignment + 1 KB tap over-read.
   // Smaller staging chunks (32 rows) are used when they buy another pipeline stage.
   auto stages_for = [&](int cr) {
-    const long rest = (long)kSmemLimit - 2048 - (p.direct ? (d.res ? (long)p.NMMA * 256 : 0) : (long)2 * kEpiGroups * cr * 256);
+    const long rest = (long)(d.want_two_per_sm ? kSmemLimit2 : kSmemLimit) - 2048 - (p.direct ? (d.res ? (long)p.NMMA * 256 : 0) : (long)2 * kEpiGroups * cr * 256);
     const int s2 = (int)(rest / p.stage_bytes);
     return s2 > kMaxStages ? kMaxStages : s2;
   };
   p.CR = p.NT < 32 ? p.NT : 32;
   if (p.NT > 16 && stages_for(16) > stages_for(p.CR)) p.CR = 16;
   p.S = stages_for(p.CR);
+  p.minb = 1;
+  if (d.want_two_per_sm) {
+    LADIFF_REQUIRE(p.NMMA <= 128 && p.S >= 2, LADIFF_ERR_ARG, "tc_conv: shape does not fit two CTAs per SM");
+    p.minb = 2;
+  }
   LADIFF_REQUIRE(p.S >= 2, LADIFF_ERR_ARG, "tc_conv: tile N=%d with %d taps per stage does not fit two pipeline stages", p.NMMA, p.a_cap);
   p.tmW = *d.tmW;
   int rc = make_tmap_x(&p.tmX, d.x, d.B, Lv, Cv, pitch_v, d.x_bstride, p.BOXROWS);
@@ -1120,20 +1132,21 @@ static int tc_conv_t_launch(const TcConvParams& p, cudaStream_t st) {
   return p.transposed == 2 ? tc_conv_t_launch_cg<2>(p, st) : tc_conv_t_launch_cg<1>(p, st);
 }
 
-int tc_conv_launch(const TcConvParams& p, cudaStream_t st) {
-  if (p.transposed) return tc_conv_t_launch(p, st);
+template <int MINB>
+static int tc_conv_launch_minb(const TcConvParams& p, cudaStream_t st) {
   const size_t smem = tc_smem_bytes(p);
-  LADIFF_REQUIRE(smem <= kSmemLimit, LADIFF_ERR_ARG, "tc_conv: smem %zu too large", smem);
-  static bool attr_set = false;     // opt in to the full dynamic shared memory once
+  const size_t limit = MINB == 2 ? kSmemLimit2 : kSmemLimit;
+  LADIFF_REQUIRE(smem <= limit, LADIFF_ERR_ARG, "tc_conv: smem %zu too large", smem);
+  static bool attr_set = false;     // opt in to the dynamic shared memory once
   if (!attr_set) {
-    LADIFF_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    LADIFF_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
     attr_set = true;
   }
-  const int tiles = p.MT * p.n_ntiles, nsm = tc_num_sms();
-  const int grid = tiles < nsm ? tiles : nsm;
+  const int tiles = p.MT * p.n_ntiles, slots = tc_num_sms() * MINB;
+  const int grid = tiles < slots ? tiles : slots;
   static const bool want_prof = getenv("LADIFF_TC_PROF") != nullptr;   // debug aid: per-role mbarrier wait cycles, printed per launch
   if (!want_prof) {
-    LADIFF_CUDA_OK(launch_pdl(tc_conv_kernel, dim3(grid), dim3(kThreads), smem, st, p));
+    LADIFF_CUDA_OK(launch_pdl(tc_conv_kernel<MINB>, dim3(grid), dim3(kThreads), smem, st, p));
     return 0;
   }
   TcConvParams q = p;
@@ -1142,7 +1155,7 @@ int tc_conv_launch(const TcConvParams& p, cudaStream_t st) {
   LADIFF_CUDA_OK(cudaMalloc((void**)&dprof, sizeof(unsigned long long) * 8 * grid));
   LADIFF_CUDA_OK(cudaMemset(dprof, 0, sizeof(unsigned long long) * 8 * grid));
   q.prof = dprof;
-  tc_conv_kernel<<<grid, kThreads, smem, st>>>(q);
+  tc_conv_kernel<MINB><<<grid, kThreads, smem, st>>>(q);
   LADIFF_CUDA_OK(cudaGetLastError());
   LADIFF_CUDA_OK(cudaStreamSynchronize(st));
   std::vector<unsigned long long> hp((size_t)8 * grid);
@@ -1150,9 +1163,14 @@ int tc_conv_launch(const TcConvParams& p, cudaStream_t st) {
   cudaFree(dprof);
   double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int i = 0; i < grid; ++i) for (int k = 0; k < 8; ++k) a[k] += (double)hp[(size_t)i * 8 + k] / grid;
-  fprintf(stderr, "[tc_prof] dbg=%d Cout=%d N=%d(NT=%d x%d) S=%d a_cap=%d grid=%d tiles=%d | cycles/CTA: total %.0f  producer-wait-empty %.0f  mma-wait-full %.0f  "
-                  "mma-wait-tmem %.0f  epi-wait-acc %.0f  epi(wg0): entry %.0f body %.0f exit %.0f\n", q.dbg, p.Cout, p.NMMA, p.NT, p.NCLIP, p.S, p.a_cap, grid, tiles, a[4], a[0], a[1], a[2], a[3], a[5], a[6], a[7]);
+  fprintf(stderr, "[tc_prof] dbg=%d minb=%d Cout=%d N=%d(NT=%d x%d) S=%d a_cap=%d grid=%d tiles=%d | cycles/CTA: total %.0f  producer-wait-empty %.0f  mma-wait-full %.0f  "
+                  "mma-wait-tmem %.0f  epi-wait-acc %.0f  epi(wg0): entry %.0f body %.0f exit %.0f\n", q.dbg, MINB, p.Cout, p.NMMA, p.NT, p.NCLIP, p.S, p.a_cap, grid, tiles, a[4], a[0], a[1], a[2], a[3], a[5], a[6], a[7]);
   return 0;
+}
+
+int tc_conv_launch(const TcConvParams& p, cudaStream_t st) {
+  if (p.transposed) return tc_conv_t_launch(p, st);
+  return p.minb == 2 ? tc_conv_launch_minb<2>(p, st) : tc_conv_launch_minb<1>(p, st);
 }
 
 int tc_conv_ref_launch(const TcConvParams& p, const TcRefView& v, cudaStream_t st) {

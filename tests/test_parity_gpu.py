@@ -261,7 +261,9 @@ def test_tc_conv_operator_shapes():
         ref = F.conv1d(x.float().permute(0, 2, 1), w.to(torch.bfloat16).float(), bias, padding=(k - 1) // 2).permute(0, 2, 1)
         s_ref = ref.reshape(B, L, Cout // 32, 32).sum(dim=(1, 3))
         xd, wd, bd = x.cuda(), w.cuda(), bias.cuda()
-        for impl in (0, 2, 3, 4):
+        for impl in (0, 2, 3, 4, 5):
+            if impl == 5 and (k != 1 or L <= 120):      # two-CTAs-per-SM shape: small-K single-clip tiles only
+                continue
             for f32 in (1, 0):
                 y = torch.full((B, L, Cout), float("nan"), device="cuda", dtype=torch.float32 if f32 else torch.bfloat16)
                 st = torch.zeros(B, Cout // 32, 2, device="cuda")
