@@ -128,6 +128,48 @@ int32_t ladiff_ddpm_steps(LadiffHandle* h, float* x, const float* cond, const fl
                           int64_t n_noise, uint64_t seed, int32_t t_start, int32_t n_steps,
                           int32_t B, int32_t L, int32_t F, void* ws, int64_t ws_bytes, void* stream);
 
+/* In-kernel noise (noise == NULL in the sampler entry points) is Philox4x32-10 keyed by (seed, absolute timestep, GLOBAL clip
+ * index, element): `clip_offset` is the global index of this handle's clip 0 (a rank's first clip when a job is sharded), so a
+ * job draws the same noise however it is split over calls, streams or GPUs.  Default 0. */
+int32_t ladiff_set_clip_offset(LadiffHandle* h, uint64_t clip_offset);
+
+/* model.diffusion.ddim_sample's loop                                   srcs/losses/ddpm_loss.py:268-303
+ * times: HOST array of n_pairs+1 decreasing timesteps (the reference's reversed linspace(-1, T-1, S+1).int(); the last may be
+ * -1 = "return x_start").  For every pair (time, time_next): eps = Unet1D(x, time, cond); x0 = clamp(a x - b eps, -1, 1);
+ * time_next < 0 → x = x0, else x = x0 sqrt(ac[next]) + c eps + sigma z with sigma = eta sqrt((1-ac/ac_next)(1-ac_next)/(1-ac)),
+ * c = sqrt(1 - ac_next - sigma^2).  noise: pre-drawn [n_noise,B,rep_dims,L], one per pair with time_next >= 0 (the reference
+ * draws it even when eta == 0), or NULL → in-kernel generator.  x [B,rep_dims,L] in place. */
+int32_t ladiff_ddim_steps(LadiffHandle* h, float* x, const float* cond, const int32_t* times, int32_t n_pairs, double eta,
+                          const float* noise, int64_t n_noise, uint64_t seed, int32_t B, int32_t L, int32_t F, void* ws,
+                          int64_t ws_bytes, void* stream);
+/* times_out[0..sampling_timesteps] = the reference's DDIM time grid (ddpm_loss.py:273-274), host array. */
+int32_t ladiff_ddim_times(int32_t total_timesteps, int32_t sampling_timesteps, int32_t* times_out);
+
+/* torch.randn(shape) / torch.rand(shape) stand-ins for the samplers' initial draws (ddpm_loss.py:256,277,336) when the caller
+ * does not pass its own: x [B, n_per_clip] ← N(0,1) (uniform = 0) or U[0,1) (uniform = 1) from the in-kernel generator. */
+int32_t ladiff_randn(LadiffHandle* h, float* x, int32_t B, int64_t n_per_clip, uint64_t seed, int32_t uniform, void* stream);
+
+/* model.diffusion.q_sample(x_start, t, noise)                          srcs/losses/ddpm_loss.py:387-393
+ * out = sqrt_alphas_cumprod[t_b] x_start + sqrt_one_minus_alphas_cumprod[t_b] noise; t [B] int64. ws: >= 1 KB + 4 B bytes. */
+int32_t ladiff_q_sample(LadiffHandle* h, const float* x_start, const int64_t* t, const float* noise, float* out, int32_t B,
+                        int64_t n_per_clip, void* ws, int64_t ws_bytes, void* stream);
+
+/* x ← a x + b y (y NULL: x ← a x).  infilling's `(1 - lam) * img + lam * infill_img` (ddpm_loss.py:360,364) and
+ * DiffAudioRep.scaling's division by the global constant (model.py:137-139).  n elements, fp32, in place. */
+int32_t ladiff_axpby(float* x, double a, const float* y, double b, int64_t n, void* stream);
+
+/* model.diffusion(x_start, cond, t, noise) = GaussianDiffusion1D.forward → p_losses   srcs/losses/ddpm_loss.py:404-450
+ * (loss_type l1, objective pred_noise; forward only — the reference's two UNet evaluations are the same tensor).
+ * x_t = q_sample(x_start, t, noise); model_out = Unet1D(x_t, t, cond); predicted_x_start = a_t x_t - b_t model_out (no clamp);
+ * loss [1] = mean_b( mean|model_out - noise| * p2_loss_weight[t_b] ).  pred_x_start, model_out optional [B,rep_dims,L]. */
+int32_t ladiff_p_losses(LadiffHandle* h, const float* x_start, const int64_t* t, const float* cond, const float* noise, int32_t B,
+                        int32_t L, int32_t F, float* loss, float* pred_x_start, float* x_t, float* model_out, void* ws,
+                        int64_t ws_bytes, void* stream);
+
+/* sdr_loss(est, target) = ClippedSDR(MultiSrcNegSDR("sdsdr"))          srcs/losses/losses_fn.py:54-66 (asteroid's sd-sdr)
+ * est, target [B, n] (one source per clip) → out [B] = max(-sdsdr, clip_value). */
+int32_t ladiff_sdsdr(const float* est, const float* target, float* out, int32_t B, int64_t n, double clip_value, void* stream);
+
 /* model.decoder(z)  = SEANetDecoder.forward                            srcs/modules/seanet.py:246-248
  * z [B,rep_dims,L] → wav [B,1,L*hop]. */
 int32_t ladiff_decode(LadiffHandle* h, const float* z, int32_t B, int32_t L, float* wav,
@@ -141,6 +183,13 @@ int32_t ladiff_synthesize(LadiffHandle* model, LadiffHandle* cond_model, const f
                           int32_t B, int32_t T, int32_t n_steps, const float* noise, int64_t n_noise,
                           uint64_t seed, float* wav_out, float* latent_out, void* ws, int64_t ws_bytes,
                           void* stream);
+
+/* The per-file body with the reference's DDIM sampler (srcs/losses/ddpm_loss.py:268-303) in place of halfway_sampling:
+ * get_cond → ddim_sample((B, rep_dims, L), condition) with `sampling_timesteps` steps from N(0, I) → decoder → normalise.
+ * init_noise [B,rep_dims,L] (NULL: in-kernel generator); noise as in ladiff_ddim_steps. */
+int32_t ladiff_synthesize_ddim(LadiffHandle* model, LadiffHandle* cond_model, const float* wav_in, int32_t B, int32_t T,
+                               int32_t sampling_timesteps, double eta, const float* init_noise, const float* noise, int64_t n_noise,
+                               uint64_t seed, float* wav_out, float* latent_out, void* ws, int64_t ws_bytes, void* stream);
 
 /* The same, starting from the codec payload (the receiver of the 1.5/3 kbps stream): codes [n_q,B,F] int64 RVQ
  * indices (quantizer.decode, srcs/quantization/vq.py:108-113 → core_vq.py:356-362) instead of a waveform;

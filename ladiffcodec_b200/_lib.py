@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libladiff_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_RATIOS = 8
 
 ERR_NAMES = {-1: "LADIFF_ERR_ARG", -2: "LADIFF_ERR_STATE", -3: "LADIFF_ERR_KEY", -4: "LADIFF_ERR_CUDA",
@@ -46,6 +46,17 @@ SIGNATURES = {
     "ladiff_upsample_layer": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "ladiff_unet_forward": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i64, c_vp]),
     "ladiff_ddpm_steps": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_u64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp]),
+    "ladiff_set_clip_offset": (c_i32, [c_vp, c_u64]),
+    "ladiff_ddim_steps": (c_i32, [c_vp, c_vp, c_vp, ctypes.POINTER(c_i32), c_i32, ctypes.c_double, c_vp, c_i64, c_u64, c_i32, c_i32, c_i32,
+                                  c_vp, c_i64, c_vp]),
+    "ladiff_ddim_times": (c_i32, [c_i32, c_i32, ctypes.POINTER(c_i32)]),
+    "ladiff_randn": (c_i32, [c_vp, c_vp, c_i32, c_i64, c_u64, c_i32, c_vp]),
+    "ladiff_q_sample": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, c_vp, c_i64, c_vp]),
+    "ladiff_axpby": (c_i32, [c_vp, ctypes.c_double, c_vp, ctypes.c_double, c_i64, c_vp]),
+    "ladiff_p_losses": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "ladiff_sdsdr": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i64, ctypes.c_double, c_vp]),
+    "ladiff_synthesize_ddim": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, ctypes.c_double, c_vp, c_vp, c_i64, c_u64, c_vp, c_vp, c_vp,
+                                       c_i64, c_vp]),
     "ladiff_decode": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_i64, c_vp]),
     "ladiff_synthesize": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_i64, c_u64, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "ladiff_synthesize_codes": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_u64, c_vp, c_vp, c_vp, c_i64, c_vp]),

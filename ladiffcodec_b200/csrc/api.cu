@@ -27,7 +27,7 @@ bool ladiff_pdl_enabled() {
   static const bool on = getenv("LADIFF_NO_PDL") == nullptr;
   return on;
 }
-extern "C" int32_t ladiff_abi_version(void) { return 1; }
+extern "C" int32_t ladiff_abi_version(void) { return 2; }
 
 #define TRY(expr)              \
   do {                         \
@@ -77,6 +77,9 @@ struct UNetW {
   AttnW da[5], ua[5], mida;
   float* film = nullptr; long long film_stride = 0;
   DdpmTables tb;
+  // host copies of the schedule buffers the samplers read (ddpm_loss.py:140-168), device pointers for the per-clip kernels
+  std::vector<float> h_recip, h_recipm1, h_c1, h_c2, h_logvar, h_ac;
+  const float *d_sqrt_ac = nullptr, *d_sqrt_1m_ac = nullptr, *d_p2w = nullptr;
   std::vector<ConvTrW> cond_up;
 };
 
@@ -131,6 +134,7 @@ struct LadiffHandle {
   int profiling = 0;
   Plan* last_plan = nullptr;
   long long launches = 0;
+  unsigned long long clip_offset = 0;   // global index of this handle's clip 0 (in-kernel noise is keyed by the global clip)
   int enc_hop = 1;
   EncoderW enc; DecoderW dec;
   float* embed = nullptr; float* embed_sq = nullptr;
@@ -548,6 +552,22 @@ int fold_unet(H* h) {
   u.tb.coef1 = Wp(h, "diffusion.posterior_mean_coef1");
   u.tb.coef2 = Wp(h, "diffusion.posterior_mean_coef2");
   u.tb.logvar = Wp(h, "diffusion.posterior_log_variance_clipped");
+  {
+    auto host = [&](const char* name, std::vector<float>& v) -> int {
+      v.resize(kTimesteps);
+      LADIFF_CUDA_OK(cudaMemcpy(v.data(), Wp(h, std::string("diffusion.") + name), sizeof(float) * kTimesteps, cudaMemcpyDeviceToHost));
+      return 0;
+    };
+    TRY(host("sqrt_recip_alphas_cumprod", u.h_recip));
+    TRY(host("sqrt_recipm1_alphas_cumprod", u.h_recipm1));
+    TRY(host("posterior_mean_coef1", u.h_c1));
+    TRY(host("posterior_mean_coef2", u.h_c2));
+    TRY(host("posterior_log_variance_clipped", u.h_logvar));
+    TRY(host("alphas_cumprod", u.h_ac));
+    u.d_sqrt_ac = Wp(h, "diffusion.sqrt_alphas_cumprod");
+    u.d_sqrt_1m_ac = Wp(h, "diffusion.sqrt_one_minus_alphas_cumprod");
+    u.d_p2w = Wp(h, "diffusion.p2_loss_weight");
+  }
   for (int j = 0; j < c.n_upsampling_ratios; ++j) {   // cond upsamplers: plain ConvTranspose1d (no weight-norm)
     const std::string p = pre + ".upsampling_layers." + std::to_string(j) + ".convtr.convtr";
     const int s = c.upsampling_ratios[j], cc = c.cond_channels;
@@ -908,8 +928,15 @@ struct PlanBuilder {
 };
 
 int build_plan(H* h, void* ws_unet, int B, int L, cudaStream_t st, Plan** out) {
-  for (Plan* p : h->plans)
-    if (p->ws == ws_unet && p->B == B && p->L == L) { *out = p; return 0; }
+  for (size_t i = 0; i < h->plans.size(); ++i) {
+    Plan* p = h->plans[i];
+    if (p->ws == ws_unet && p->B == B && p->L == L) {      // most recently used plan at the back (LRU eviction)
+      h->plans.erase(h->plans.begin() + i);
+      h->plans.push_back(p);
+      *out = p;
+      return 0;
+    }
+  }
   LADIFF_REQUIRE(L % 16 == 0 && L >= 16, LADIFF_ERR_ARG, "UNet needs a latent length that is a multiple of 16 (got %d)", L);
   Plan* pl = new Plan();
   pl->ws = ws_unet; pl->B = B; pl->L = L;
@@ -983,7 +1010,11 @@ int build_plan(H* h, void* ws_unet, int B, int L, cudaStream_t st, Plan** out) {
   if (pb.tune_ev[0]) cudaEventDestroy(pb.tune_ev[0]);
   if (pb.tune_ev[1]) cudaEventDestroy(pb.tune_ev[1]);
   if (rc) { delete pl; return rc; }
-  if (h->plans.size() >= 4) { delete h->plans.front(); h->plans.erase(h->plans.begin()); }
+  if (h->plans.size() >= 6) {                                // evict the least recently used plan
+    if (h->last_plan == h->plans.front()) h->last_plan = nullptr;
+    delete h->plans.front();
+    h->plans.erase(h->plans.begin());
+  }
   h->plans.push_back(pl);
   *out = pl;
   return 0;
@@ -1078,6 +1109,26 @@ int check_ws(void* ws, int64_t have, size_t need) {
   return 0;
 }
 
+// p_sample's coefficients at step t (ddpm_loss.py:199-206, 244-251); sigma = exp(0.5 logvar) in fp32 like the reference
+StepCoef ddpm_coef(const UNetW& u, int t) {
+  StepCoef c;
+  c.a = u.h_recip[t]; c.b = u.h_recipm1[t]; c.k0 = u.h_c1[t]; c.k1 = u.h_c2[t];
+  c.ks = t > 0 ? expf(0.5f * u.h_logvar[t]) : 0.f;
+  c.mode = 0;
+  return c;
+}
+// ddim_sample's coefficients for the pair (time, time_next) (ddpm_loss.py:289-300), in the reference's fp32 operation order
+StepCoef ddim_coef(const UNetW& u, int time, int time_next, float eta) {
+  StepCoef c;
+  c.a = u.h_recip[time]; c.b = u.h_recipm1[time];
+  if (time_next < 0) { c.k0 = 1.f; c.k1 = 0.f; c.ks = 0.f; c.mode = 2; return c; }
+  const float alpha = u.h_ac[time], alpha_next = u.h_ac[time_next];
+  const float sigma = eta * sqrtf((1.f - alpha / alpha_next) * (1.f - alpha_next) / (1.f - alpha));
+  const float cc = sqrtf(1.f - alpha_next - sigma * sigma);
+  c.k0 = sqrtf(alpha_next); c.k1 = cc; c.ks = sigma; c.mode = 1;
+  return c;
+}
+
 int ddpm_run(H* h, Plan* pl, float* x, const float* cond, const float* noise, int64_t n_noise, uint64_t seed, int t_start, int n_steps,
              int B, int L, int F, cudaStream_t st) {
   UnetBufs& u = pl->bufs;
@@ -1098,7 +1149,35 @@ int ddpm_run(H* h, Plan* pl, float* x, const float* cond, const float* noise, in
       nz = noise + (size_t)k * B * 128 * L;
       ++k;
     }
-    TRY(ddpm_step_launch(u.eps, x, nz, seed, s, u.t_dev, h->un.tb, xs, B, 128, L, st));
+    TRY(ddpm_step_launch(u.eps, x, nz, seed, t, h->clip_offset, ddpm_coef(h->un, t), xs, B, 128, L, st));
+    h->launches += 2;
+  }
+  return 0;
+}
+
+// ddim_sample (ddpm_loss.py:268-303) over the host array times[0..n_pairs] (decreasing; times[n_pairs] may be -1)
+int ddim_run(H* h, Plan* pl, float* x, const float* cond, const int32_t* times, int n_pairs, float eta, const float* noise, int64_t n_noise,
+             uint64_t seed, int B, int L, int F, cudaStream_t st) {
+  UnetBufs& u = pl->bufs;
+  for (int i = 0; i < n_pairs; ++i)
+    LADIFF_REQUIRE(times[i] >= 0 && times[i] < kTimesteps && times[i + 1] >= -1 && times[i + 1] < times[i], LADIFF_ERR_ARG,
+                   "ddim: times must decrease inside [0, %d) (pair %d: %d -> %d)", kTimesteps, i, times[i], times[i + 1]);
+  TRY(prepare_cond(h, pl, cond, B, L, F, st));
+  ClView xs = view(u.xin, L, 256, 128, 128);
+  TRY(ncl_to_cl_launch(x, nullptr, xs, B, 128, L, st));
+  h->launches++;
+  int64_t k = 0;
+  for (int i = 0; i < n_pairs; ++i) {
+    const int t = times[i], tn = times[i + 1];
+    TRY(fill_t_launch(u.t_dev, t, B, st));
+    TRY(run_plan(h, pl, st));
+    const float* nz = nullptr;
+    if (tn >= 0 && noise) {       // the reference draws randn_like for every pair with time_next >= 0, even at eta = 0
+      LADIFF_REQUIRE(k < n_noise, LADIFF_ERR_ARG, "ddim: pre-drawn noise exhausted at pair %d (have %lld)", i, (long long)n_noise);
+      nz = noise + (size_t)k * B * 128 * L;
+      ++k;
+    }
+    TRY(ddpm_step_launch(u.eps, x, nz, seed, t, h->clip_offset, ddim_coef(h->un, t, tn, eta), xs, B, 128, L, st));
     h->launches += 2;
   }
   return 0;
@@ -1280,6 +1359,73 @@ extern "C" int32_t ladiff_ddpm_steps(LadiffHandle* h, float* x, const float* con
   return ddpm_run(h, pl, x, cond, noise, n_noise, seed, t_start, n_steps, B, L, F, st);
 }
 
+extern "C" int32_t ladiff_set_clip_offset(LadiffHandle* h, uint64_t clip_offset) {
+  LADIFF_REQUIRE(h, LADIFF_ERR_ARG, "null handle");
+  h->clip_offset = clip_offset;
+  return 0;
+}
+
+extern "C" int32_t ladiff_ddim_steps(LadiffHandle* h, float* x, const float* cond, const int32_t* times, int32_t n_pairs, double eta,
+                                     const float* noise, int64_t n_noise, uint64_t seed, int32_t B, int32_t L, int32_t F, void* ws,
+                                     int64_t ws_bytes, void* stream) {
+  STAGE_PROLOGUE(h);
+  LADIFF_REQUIRE(h->cfg.run_diff, LADIFF_ERR_STATE, "this model has no diffusion UNet (run_diff=False)");
+  LADIFF_REQUIRE(x && cond && times && n_pairs >= 0 && B > 0, LADIFF_ERR_ARG, "ladiff_ddim_steps: bad argument");
+  TRY(check_ws(ws, ws_bytes, unet_ws_bytes(h, B, L)));
+  Plan* pl = nullptr;
+  TRY(build_plan(h, ws, B, L, st, &pl));
+  return ddim_run(h, pl, x, cond, times, n_pairs, (float)eta, noise, n_noise, seed, B, L, F, st);
+}
+
+extern "C" int32_t ladiff_randn(LadiffHandle* h, float* x, int32_t B, int64_t n_per_clip, uint64_t seed, int32_t uniform, void* stream) {
+  LADIFF_REQUIRE(h && x && B > 0 && n_per_clip > 0, LADIFF_ERR_ARG, "ladiff_randn: bad argument");
+  h->launches++;
+  return randn_fill_launch(x, (long long)B * n_per_clip, seed, h->clip_offset * (unsigned long long)n_per_clip, uniform ? 1 : 0, (cudaStream_t)stream);
+}
+
+extern "C" int32_t ladiff_q_sample(LadiffHandle* h, const float* x_start, const int64_t* t, const float* noise, float* out, int32_t B,
+                                   int64_t n_per_clip, void* ws, int64_t ws_bytes, void* stream) {
+  STAGE_PROLOGUE(h);
+  LADIFF_REQUIRE(h->cfg.run_diff, LADIFF_ERR_STATE, "this model has no diffusion process (run_diff=False)");
+  LADIFF_REQUIRE(x_start && t && noise && out && B > 0 && n_per_clip > 0, LADIFF_ERR_ARG, "ladiff_q_sample: bad argument");
+  TRY(check_ws(ws, ws_bytes, 1024 + sizeof(int) * (size_t)B));
+  int* t_dev = reinterpret_cast<int*>(ws);
+  TRY(time_to_int_launch((const long long*)t, t_dev, B, st));
+  h->launches += 2;
+  return q_sample_launch(x_start, noise, t_dev, h->un.d_sqrt_ac, h->un.d_sqrt_1m_ac, out, B, n_per_clip, st);
+}
+
+extern "C" int32_t ladiff_axpby(float* x, double a, const float* y, double b, int64_t n, void* stream) {
+  LADIFF_REQUIRE(x && n > 0, LADIFF_ERR_ARG, "ladiff_axpby: bad argument");
+  return axpby_launch(x, (float)a, y, (float)b, n, (cudaStream_t)stream);
+}
+
+extern "C" int32_t ladiff_p_losses(LadiffHandle* h, const float* x_start, const int64_t* t, const float* cond, const float* noise, int32_t B,
+                                   int32_t L, int32_t F, float* loss, float* pred_x_start, float* x_t, float* model_out, void* ws,
+                                   int64_t ws_bytes, void* stream) {
+  STAGE_PROLOGUE(h);
+  LADIFF_REQUIRE(h->cfg.run_diff, LADIFF_ERR_STATE, "this model has no diffusion UNet (run_diff=False)");
+  LADIFF_REQUIRE(x_start && t && cond && noise && loss && x_t && B > 0, LADIFF_ERR_ARG, "ladiff_p_losses: null argument");
+  TRY(check_ws(ws, ws_bytes, unet_ws_bytes(h, B, L)));
+  Plan* pl = nullptr;
+  TRY(build_plan(h, ws, B, L, st, &pl));
+  UnetBufs& u = pl->bufs;
+  TRY(time_to_int_launch((const long long*)t, u.t_dev, B, st));
+  TRY(q_sample_launch(x_start, noise, u.t_dev, h->un.d_sqrt_ac, h->un.d_sqrt_1m_ac, x_t, B, (long long)128 * L, st));   // ddpm_loss.py:410
+  TRY(prepare_cond(h, pl, cond, B, L, F, st));
+  TRY(ncl_to_cl_launch(x_t, nullptr, view(u.xin, L, 256, 128, 128), B, 128, L, st));
+  TRY(run_plan(h, pl, st));                                     // model(x, t, cond): :418 and :423 are the same evaluation forward-only
+  TRY(p_losses_launch(u.eps, noise, x_t, u.t_dev, h->un.tb.sqrt_recip_ac, h->un.tb.sqrt_recipm1_ac, h->un.d_p2w, pred_x_start, model_out,
+                      u.inv_scale, loss, B, 128, L, st));
+  h->launches += 5;
+  return 0;
+}
+
+extern "C" int32_t ladiff_sdsdr(const float* est, const float* target, float* out, int32_t B, int64_t n, double clip_value, void* stream) {
+  LADIFF_REQUIRE(est && target && out && B > 0 && n > 1, LADIFF_ERR_ARG, "ladiff_sdsdr: bad argument");
+  return sdsdr_launch(est, target, out, B, n, (float)clip_value, (cudaStream_t)stream);
+}
+
 extern "C" int32_t ladiff_decode(LadiffHandle* h, const float* z, int32_t B, int32_t L, float* wav, void* ws, int64_t ws_bytes,
                                  void* stream) {
   STAGE_PROLOGUE(h);
@@ -1293,27 +1439,41 @@ extern "C" int32_t ladiff_normalize_clips(float* x, int32_t B, int64_t n, int32_
   return normalize_clips_launch(x, B, n, mode, (cudaStream_t)stream);
 }
 
-// common tail of the two synthesis entry points: cond [B][128][F] (persist region) -> wav_out
-static int synth_from_cond(LadiffHandle* m, const float* cond, int B, int T, int n_steps, const float* noise, int64_t n_noise, uint64_t seed,
-                           float* wav_out, float* latent_out, Bump bp, void* scratch, cudaStream_t st) {
+// common tail of the synthesis entry points: cond [B][128][F] (persist region) -> wav_out
+struct SamplerSpec {
+  int kind = 0;                 // 0: halfway_sampling(t = n_steps) from the upsampled cond; 1: ddim_sample from noise; 2: p_sample_loop from noise
+  int n_steps = 0;
+  std::vector<int32_t> times;   // DDIM time pairs
+  float eta = 0.f;
+  const float* init = nullptr;  // initial noise for kinds 1, 2 (null: in-kernel generator)
+};
+static int synth_from_cond(LadiffHandle* m, const float* cond, int B, int T, const SamplerSpec& sp, const float* noise, int64_t n_noise,
+                           uint64_t seed, float* wav_out, float* latent_out, Bump bp, void* scratch, cudaStream_t st) {
   const int L = T / m->enc_hop, F = T / 320;
   float* x = latent_out ? latent_out : bp.get<float>((size_t)B * 128 * L);
   float* ta = bp.get<float>((size_t)B * 128 * L);
   float* tb = bp.get<float>((size_t)B * 128 * L);
-  TRY(run_cond_upsample(m, cond, B, F, x, ta, tb, st));                                                 // sample.py:125-128
-  TRY(normalize_clips_launch(x, B, (long long)128 * L, 0, st));                                         // :129
   Plan* pl = nullptr;
-  TRY(build_plan(m, scratch, B, L, st, &pl));
-  TRY(ddpm_run(m, pl, x, cond, noise, n_noise, seed, n_steps, n_steps, B, L, F, st));                   // :130
+  if (sp.kind == 0) {
+    TRY(run_cond_upsample(m, cond, B, F, x, ta, tb, st));                                               // sample.py:125-128
+    TRY(normalize_clips_launch(x, B, (long long)128 * L, 0, st));                                       // :129
+    TRY(build_plan(m, scratch, B, L, st, &pl));
+    TRY(ddpm_run(m, pl, x, cond, noise, n_noise, seed, sp.n_steps, sp.n_steps, B, L, F, st));           // :130
+  } else {
+    if (sp.init) LADIFF_CUDA_OK(cudaMemcpyAsync(x, sp.init, sizeof(float) * (size_t)B * 128 * L, cudaMemcpyDeviceToDevice, st));
+    else TRY(randn_fill_launch(x, (long long)B * 128 * L, seed, m->clip_offset * (unsigned long long)128 * L, 0, st));   // torch.randn(shape), ddpm_loss.py:256,277
+    TRY(build_plan(m, scratch, B, L, st, &pl));
+    if (sp.kind == 1) TRY(ddim_run(m, pl, x, cond, sp.times.data(), (int)sp.times.size() - 1, sp.eta, noise, n_noise, seed, B, L, F, st));
+    else TRY(ddpm_run(m, pl, x, cond, noise, n_noise, seed, kTimesteps, sp.n_steps, B, L, F, st));
+  }
   TRY(run_decoder(m, x, B, L, wav_out, Bump(scratch), st));                                             // :131
   TRY(normalize_clips_launch(wav_out, B, T, 1, st));                                                    // :133-134
   m->launches += 2;
   return 0;
 }
 
-extern "C" int32_t ladiff_synthesize(LadiffHandle* m, LadiffHandle* cm, const float* wav_in, int32_t B, int32_t T, int32_t n_steps,
-                                     const float* noise, int64_t n_noise, uint64_t seed, float* wav_out, float* latent_out, void* ws,
-                                     int64_t ws_bytes, void* stream) {
+static int synth_common(LadiffHandle* m, LadiffHandle* cm, const float* wav_in, int32_t B, int32_t T, const SamplerSpec& sp, const float* noise,
+                        int64_t n_noise, uint64_t seed, float* wav_out, float* latent_out, void* ws, int64_t ws_bytes, void* stream) {
   STAGE_PROLOGUE(m);
   LADIFF_REQUIRE(cm && cm->finalized, LADIFF_ERR_STATE, "conditioning model not finalized");
   LADIFF_REQUIRE(m->cfg.run_diff && cm->cfg.quantization, LADIFF_ERR_STATE, "synthesize needs a diffusion model and a quantising cond codec");
@@ -1327,7 +1487,52 @@ extern "C" int32_t ladiff_synthesize(LadiffHandle* m, LadiffHandle* cm, const fl
   float* cond = bp.get<float>((size_t)B * 128 * F);
   void* scratch = (char*)ws + pb;
   TRY(ladiff_get_cond(cm, wav_in, B, T, cond, nullptr, nullptr, scratch, ws_bytes - (int64_t)pb, stream));   // sample.py:94
-  return synth_from_cond(m, cond, B, T, n_steps, noise, n_noise, seed, wav_out, latent_out, bp, scratch, st);
+  return synth_from_cond(m, cond, B, T, sp, noise, n_noise, seed, wav_out, latent_out, bp, scratch, st);
+}
+
+extern "C" int32_t ladiff_synthesize(LadiffHandle* m, LadiffHandle* cm, const float* wav_in, int32_t B, int32_t T, int32_t n_steps,
+                                     const float* noise, int64_t n_noise, uint64_t seed, float* wav_out, float* latent_out, void* ws,
+                                     int64_t ws_bytes, void* stream) {
+  SamplerSpec sp;
+  sp.kind = 0; sp.n_steps = n_steps;
+  return synth_common(m, cm, wav_in, B, T, sp, noise, n_noise, seed, wav_out, latent_out, ws, ws_bytes, stream);
+}
+
+// ddim_sample's time grid (ddpm_loss.py:273-275): torch.linspace(-1, T-1, steps = S+1) in fp32, truncated to int, reversed.
+// torch.linspace computes start + step*i for the first half and end - step*(steps-1-i) for the second half (fp32).
+static void ddim_times(int total, int S, std::vector<int32_t>* out) {
+  const int steps = S + 1;
+  const float start = -1.f, end = (float)(total - 1);
+  const float step = (end - start) / (float)(steps - 1);
+  std::vector<int32_t> t(steps);
+  const int half = steps / 2;
+  for (int i = 0; i < steps; ++i) {
+    const float v = i < half ? start + step * (float)i : end - step * (float)(steps - 1 - i);
+    t[i] = (int32_t)v;      // .int(): truncation toward zero
+  }
+  out->assign(t.rbegin(), t.rend());
+}
+
+// The same per-file body with the reference's DDIM sampler in place of halfway_sampling:
+// get_cond → ddim_sample((B, 128, L), condition) with `sampling_timesteps` steps from N(0, I) → decoder → normalise.
+// init_noise [B,128,L] optional (null: in-kernel generator); noise [n,B,128,L] one per pair with time_next >= 0 (only used if eta != 0).
+extern "C" int32_t ladiff_synthesize_ddim(LadiffHandle* m, LadiffHandle* cm, const float* wav_in, int32_t B, int32_t T,
+                                          int32_t sampling_timesteps, double eta, const float* init_noise, const float* noise, int64_t n_noise,
+                                          uint64_t seed, float* wav_out, float* latent_out, void* ws, int64_t ws_bytes, void* stream) {
+  LADIFF_REQUIRE(sampling_timesteps >= 1 && sampling_timesteps <= kTimesteps, LADIFF_ERR_ARG, "ladiff_synthesize_ddim: sampling_timesteps=%d",
+                 sampling_timesteps);
+  SamplerSpec sp;
+  sp.kind = 1; sp.eta = (float)eta; sp.init = init_noise;
+  ddim_times(kTimesteps, sampling_timesteps, &sp.times);
+  return synth_common(m, cm, wav_in, B, T, sp, noise, n_noise, seed, wav_out, latent_out, ws, ws_bytes, stream);
+}
+
+extern "C" int32_t ladiff_ddim_times(int32_t total_timesteps, int32_t sampling_timesteps, int32_t* times_out) {
+  LADIFF_REQUIRE(times_out && sampling_timesteps >= 1 && total_timesteps >= 1, LADIFF_ERR_ARG, "ladiff_ddim_times: bad argument");
+  std::vector<int32_t> t;
+  ddim_times(total_timesteps, sampling_timesteps, &t);
+  for (size_t i = 0; i < t.size(); ++i) times_out[i] = t[i];
+  return 0;
 }
 
 // Receiver side of the codec: the conditioning arrives as RVQ indices instead of a waveform.
@@ -1348,7 +1553,9 @@ extern "C" int32_t ladiff_synthesize_codes(LadiffHandle* m, LadiffHandle* cm, co
   float* cond = bp.get<float>((size_t)B * 128 * F);
   void* scratch = (char*)ws + pb;
   TRY(ladiff_rvq_decode(cm, codes, n_q, B, F, cond, stream));                                           // vq.py:108-113
-  return synth_from_cond(m, cond, B, T, n_steps, noise, n_noise, seed, wav_out, latent_out, bp, scratch, st);
+  SamplerSpec sp;
+  sp.kind = 0; sp.n_steps = n_steps;
+  return synth_from_cond(m, cond, B, T, sp, noise, n_noise, seed, wav_out, latent_out, bp, scratch, st);
 }
 
 extern "C" int32_t ladiff_set_conv_impl(LadiffHandle* h, int32_t impl) {

@@ -704,10 +704,9 @@ static int conv1d_v2_dispatch(const ConvF32Args& a, int KT, int S, int B, cudaSt
   dim3 grid(cdiv(a.LoutV, 128), cdiv(a.CoutV, CO_T), B);
 #define LADIFF_V2_CASE(KTV)                                                                                                   \
   case KTV: {                                                                                                                 \
-    static bool attr = false;                                                                                                 \
-    if (!attr) {                                                                                                              \
+    static unsigned long long attr = 0;                                                                                       \
+    if (ladiff_first_on_device(&attr)) {                                                                                      \
       LADIFF_CUDA_OK(cudaFuncSetAttribute(conv1d_f32_v2_kernel<RC, KTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); \
-      attr = true;                                                                                                            \
     }                                                                                                                         \
     conv1d_f32_v2_kernel<RC, KTV><<<grid, 256, smem, st>>>(a, CI_T, S);                                                       \
     break;                                                                                                                    \
@@ -760,11 +759,10 @@ int lstm_seq_launch(const float* pre, const float* whh, const float* skip, float
   if (H == 64) {
     lstm_seq_kernel<64, 64><<<B, 256, 0, st>>>(pre, whh, skip, y, T);
   } else if (H == 128) {
-    static bool attr = false;
+    static unsigned long long attr = 0;
     const size_t smem = (size_t)64 * 512 * sizeof(float);
-    if (!attr) {
+    if (ladiff_first_on_device(&attr)) {
       LADIFF_CUDA_OK(cudaFuncSetAttribute(lstm_seq_kernel<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr = true;
     }
     lstm_seq_kernel<128, 64><<<B, 512, smem, st>>>(pre, whh, skip, y, T);
   } else {
@@ -778,10 +776,9 @@ int lstm_persist_launch(const float* pre, const float* whh, const float* skip, f
                         int T, cudaStream_t st) {
   LADIFF_REQUIRE(H % 32 == 0 && H >= 32, LADIFF_ERR_ARG, "lstm_persist: H=%d", H);
   const size_t smem = ((size_t)H * 16 + (size_t)H * LP_B + (size_t)LP_WARPS * 16 * LP_B) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;
+  if (ladiff_first_on_device(&attr)) {
     LADIFF_CUDA_OK(cudaFuncSetAttribute(lstm_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
   }
   LADIFF_REQUIRE(smem <= 200 * 1024 && H / 4 <= tc_num_sms(), LADIFF_ERR_ARG, "lstm_persist: H=%d does not fit one co-resident grid", H);
   LADIFF_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));

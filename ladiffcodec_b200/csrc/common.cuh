@@ -52,10 +52,20 @@ template <typename... KArgs>
 static inline void prefer_max_smem_carveout(void (*kernel)(KArgs...)) {
   cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
+// Function attributes are per device: one-time setup is keyed by the current device ordinal (a second GPU in the same
+// process gets its own opt-in).
+static inline bool ladiff_first_on_device(unsigned long long* mask) {
+  int d = 0;
+  cudaGetDevice(&d);
+  const unsigned long long bit = 1ull << (d & 63);
+  if (*mask & bit) return false;
+  *mask |= bit;
+  return true;
+}
 #define LADIFF_CARVEOUT_ONCE(kernel)                                             \
   do {                                                                           \
-    static bool _done = false;                                                   \
-    if (!_done) { prefer_max_smem_carveout(kernel); _done = true; }              \
+    static unsigned long long _done = 0;                                         \
+    if (ladiff_first_on_device(&_done)) prefer_max_smem_carveout(kernel);        \
   } while (0)
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

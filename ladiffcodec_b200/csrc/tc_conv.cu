@@ -837,7 +837,7 @@ int tc_num_sms() {
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
       n = 148;
   }
-  return n;
+  return n;   // every GPU of one box is the same part
 }
 
 static int make_tmap_wt(CUtensorMap* tm, const bf16* w, int Cout, int Ktot, int nch) {
@@ -1083,10 +1083,9 @@ template <int CG>
 static int tc_conv_t_launch_cg(const TcConvParams& p, cudaStream_t st) {
   const size_t smem = (size_t)kActSlots * kActBytes + (size_t)p.S * (p.NCH / CG) * 128 + 2048;
   LADIFF_REQUIRE(smem <= kSmemLimitT, LADIFF_ERR_ARG, "tc_conv(transposed): smem %zu too large", smem);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_set = 0;
+  if (ladiff_first_on_device(&attr_set)) {
     LADIFF_CUDA_OK(cudaFuncSetAttribute(tc_conv_t_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimitT));
-    attr_set = true;
   }
   const int n_pt = CG == 2 ? (p.Lout + 255) / 256 : p.n_ptiles;
   const int tiles = p.n_chtiles * n_pt * p.B, nsm = tc_num_sms();
@@ -1137,10 +1136,9 @@ static int tc_conv_launch_minb(const TcConvParams& p, cudaStream_t st) {
   const size_t smem = tc_smem_bytes(p);
   const size_t limit = MINB == 2 ? kSmemLimit2 : kSmemLimit;
   LADIFF_REQUIRE(smem <= limit, LADIFF_ERR_ARG, "tc_conv: smem %zu too large", smem);
-  static bool attr_set = false;     // opt in to the dynamic shared memory once
-  if (!attr_set) {
+  static unsigned long long attr_set = 0;     // opt in to the dynamic shared memory once per device
+  if (ladiff_first_on_device(&attr_set)) {
     LADIFF_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
-    attr_set = true;
   }
   const int tiles = p.MT * p.n_ntiles, slots = tc_num_sms() * MINB;
   const int grid = tiles < slots ? tiles : slots;

@@ -709,15 +709,22 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, fl
   n0 = r * cs; n1 = r * sn;
 }
 
+// One sampler step for every element of x [B][C][L] (NCL fp32, in place) given eps [B][L][C] (channels-last fp32):
+//   x0  = clamp(a x - b eps, -1, 1)                      predict_start_from_noise + clamp   ddpm_loss.py:175-179, 237-238
+//   DDPM (mode 0): x <- (k0 x0 + k1 x) + ks z            q_posterior + p_sample             :199-206, 244-251
+//   DDIM (mode 1): x <- (k0 x0 + k1 eps) + ks z          ddim_sample                        :296-300
+//   mode 2:        x <- x0                               ddim_sample's last pair (time_next < 0)  :289-291
+// Every product and sum is rounded separately (no FMA contraction): given the same eps the step reproduces the reference's
+// fp32 tensor algebra bit for bit.  Also writes the new x as bf16 into xin (channels-last view, the UNet's next input).
+// In-kernel noise (noise == null, ks != 0): Philox4x32-10 keyed by the seed, counter = (global element index of the thread's first
+// element [clip_offset + b], absolute timestep t_abs): independent of how a trajectory is split into calls or a job over ranks.
 // grid (ceil(L/32), C/32, B), block (32, 8)
 __global__ void ddpm_step_kernel(const float* __restrict__ eps, float* __restrict__ x, const float* __restrict__ noise,
-                                 unsigned long long seed, int step_index, const int* __restrict__ t_dev, DdpmTables tb,
+                                 unsigned long long seed, int t_abs, unsigned long long clip_offset, StepCoef cf,
                                  ClView xin, int C, int L) {
   __shared__ float t[32][33];
   const int b = blockIdx.z, c0 = blockIdx.y * 32, l0 = blockIdx.x * 32;
-  const int ti = t_dev[b];
-  const float a = tb.sqrt_recip_ac[ti], bb = tb.sqrt_recipm1_ac[ti], c1 = tb.coef1[ti], c2 = tb.coef2[ti];
-  const float sigma = ti > 0 ? __expf(0.5f * tb.logvar[ti]) : 0.f;
+  const bool want_z = cf.ks != 0.f && cf.mode != 2;
   float ev[4], xv[4], zv[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -730,11 +737,11 @@ __global__ void ddpm_step_kernel(const float* __restrict__ eps, float* __restric
     const int c = c0 + threadIdx.y + 8 * k;
     const long long idx = ((long long)b * C + c) * L + lx;
     xv[k] = (lx < L) ? x[idx] : 0.f;
-    if (ti > 0 && noise && lx < L) zv[k] = __ldg(noise + idx);
+    if (want_z && noise && lx < L) zv[k] = __ldg(noise + idx);
   }
-  if (ti > 0 && !noise) {
-    const unsigned long long first = ((unsigned long long)b * C + c0 + threadIdx.y) * (unsigned long long)L + lx;
-    const uint4 rnd = philox4x32_10(make_uint4((uint32_t)first, (uint32_t)(first >> 32), (uint32_t)step_index, 0x1ad1ffu),
+  if (want_z && !noise) {
+    const unsigned long long first = ((clip_offset + (unsigned long long)b) * C + c0 + threadIdx.y) * (unsigned long long)L + lx;
+    const uint4 rnd = philox4x32_10(make_uint4((uint32_t)first, (uint32_t)(first >> 32), (uint32_t)t_abs, 0x1ad1ffu),
                                     make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
     box_muller(rnd.x, rnd.y, zv[0], zv[1]);
     box_muller(rnd.z, rnd.w, zv[2], zv[3]);
@@ -746,9 +753,14 @@ __global__ void ddpm_step_kernel(const float* __restrict__ eps, float* __restric
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int i = threadIdx.y + 8 * k;
-    float x0 = a * xv[k] - bb * t[threadIdx.x][i];
+    const float e = t[threadIdx.x][i];
+    float x0 = __fsub_rn(__fmul_rn(cf.a, xv[k]), __fmul_rn(cf.b, e));
     x0 = fminf(fmaxf(x0, -1.f), 1.f);
-    xn[k] = c1 * x0 + c2 * xv[k] + sigma * zv[k];
+    if (cf.mode == 2) xn[k] = x0;
+    else {
+      const float m = __fadd_rn(__fmul_rn(cf.k0, x0), __fmul_rn(cf.k1, cf.mode == 1 ? e : xv[k]));
+      xn[k] = want_z ? __fadd_rn(m, __fmul_rn(cf.ks, zv[k])) : (cf.mode == 1 ? __fadd_rn(m, 0.f) : m);
+    }
     if (lx < L) x[((long long)b * C + c0 + i) * L + lx] = xn[k];
   }
   __syncthreads();
@@ -758,7 +770,127 @@ __global__ void ddpm_step_kernel(const float* __restrict__ eps, float* __restric
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int i = threadIdx.y + 8 * k, l = l0 + i;
-    if (l < L) xin.p[(long long)b * xin.bstride + (long long)l * xin.pitch + c0 + threadIdx.x] = __float2bfloat16(t[i][threadIdx.x]);
+    if (l < L && xin.p) xin.p[(long long)b * xin.bstride + (long long)l * xin.pitch + c0 + threadIdx.x] = __float2bfloat16(t[i][threadIdx.x]);
+  }
+}
+
+// N(0,1) fill (the initial torch.randn(shape) of p_sample_loop / ddim_sample when the caller passes none): same generator,
+// counter word 3 = 0x1417 so the stream is disjoint from every step's.  One thread = 4 consecutive elements.
+__global__ void randn_fill_kernel(float* __restrict__ x, long long n, unsigned long long seed, unsigned long long elem_offset, int uniform) {
+  const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  const unsigned long long first = elem_offset + (unsigned long long)i4;
+  const uint4 rnd = philox4x32_10(make_uint4((uint32_t)first, (uint32_t)(first >> 32), 0u, 0x1417u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  float z[4];
+  if (uniform) {
+    z[0] = (float)rnd.x * 2.3283064365386963e-10f; z[1] = (float)rnd.y * 2.3283064365386963e-10f;
+    z[2] = (float)rnd.z * 2.3283064365386963e-10f; z[3] = (float)rnd.w * 2.3283064365386963e-10f;
+  } else {
+    box_muller(rnd.x, rnd.y, z[0], z[1]);
+    box_muller(rnd.z, rnd.w, z[2], z[3]);
+  }
+  for (int k = 0; k < 4 && i4 + k < n; ++k) x[i4 + k] = z[k];
+}
+
+// q_sample (ddpm_loss.py:387-393): out = sqrt_ac[t_b] x + sqrt_1m_ac[t_b] noise, per clip; products rounded separately
+__global__ void q_sample_kernel(const float* __restrict__ x, const float* __restrict__ noise, const int* __restrict__ t_dev,
+                                const float* __restrict__ sqrt_ac, const float* __restrict__ sqrt_1m_ac, float* __restrict__ out, long long n) {
+  const int b = blockIdx.y;
+  const float a = sqrt_ac[t_dev[b]], s = sqrt_1m_ac[t_dev[b]];
+  const long long base = (long long)b * n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[base + i] = __fadd_rn(__fmul_rn(a, x[base + i]), __fmul_rn(s, noise[base + i]));
+}
+
+// x <- a x + b y  (infilling's (1 - lam) img + lam infill_img, ddpm_loss.py:360,364; scaling by a constant with b = 0)
+__global__ void axpby_kernel(float* __restrict__ x, float a, const float* __restrict__ y, float b, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float ax = __fmul_rn(a, x[i]);
+    x[i] = y ? __fadd_rn(ax, __fmul_rn(b, y[i])) : ax;
+  }
+}
+
+// p_losses tail (ddpm_loss.py:404-437, loss_type l1, objective pred_noise): per clip b
+//   pred_x0 = a_t x_t - r_t eps (no clamp);  part[b] = mean |eps - noise| * p2_weight[t_b]
+// eps channels-last [B][L][C], the rest NCL.  grid (B), 1024 threads; fixed-order tree reduction (deterministic).
+__global__ void __launch_bounds__(1024) p_losses_kernel(const float* __restrict__ eps, const float* __restrict__ noise, const float* __restrict__ xt,
+                                                        const int* __restrict__ t_dev, const float* __restrict__ recip, const float* __restrict__ recipm1,
+                                                        const float* __restrict__ p2w, float* __restrict__ pred_x0, float* __restrict__ eps_ncl,
+                                                        float* __restrict__ part, int C, int L) {
+  const int b = blockIdx.x, ti = t_dev[b];
+  const float a = recip[ti], r = recipm1[ti];
+  const long long n = (long long)C * L;
+  float acc = 0.f;
+  for (long long i = threadIdx.x; i < n; i += 1024) {
+    const int c = (int)(i / L), l = (int)(i - (long long)c * L);
+    const float e = __ldcg(eps + ((long long)b * L + l) * C + c);
+    const long long o = (long long)b * n + i;
+    acc += fabsf(e - noise[o]);
+    if (pred_x0) pred_x0[o] = __fsub_rn(__fmul_rn(a, xt[o]), __fmul_rn(r, e));
+    if (eps_ncl) eps_ncl[o] = e;
+  }
+  __shared__ float red[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = red[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (threadIdx.x == 0) part[b] = acc / (float)n * p2w[ti];
+  }
+}
+__global__ void mean_small_kernel(const float* __restrict__ part, float* __restrict__ out, int B) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < B; ++i) s += part[i];
+    out[0] = s / (float)B;
+  }
+}
+
+// ClippedSDR(MultiSrcNegSDR("sdsdr")) per clip (losses_fn.py:54-66; asteroid's published sd-sdr, EPS 1e-8):
+//   zero-mean est/target; scaled = <est,tgt> tgt / (|tgt|^2 + EPS); noise = est - tgt;
+//   out[b] = max(-10 log10(|scaled|^2 / (|noise|^2 + EPS) + EPS), clip)        grid (B), 1024 threads, two passes
+__global__ void __launch_bounds__(1024) sdsdr_kernel(const float* __restrict__ est, const float* __restrict__ tgt, float* __restrict__ out, long long n,
+                                                     float clip) {
+  const float* e = est + (long long)blockIdx.x * n;
+  const float* t = tgt + (long long)blockIdx.x * n;
+  __shared__ double red[4][32];
+  __shared__ double tot[4];
+  auto reduce = [&](double (&v)[4], int cnt) {
+    for (int k = 0; k < cnt; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+      if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      for (int k = 0; k < cnt; ++k) {
+        double w = red[k][threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+        if (threadIdx.x == 0) tot[k] = w;
+      }
+    }
+    __syncthreads();
+  };
+  double v[4] = {0, 0, 0, 0};
+  for (long long i = threadIdx.x; i < n; i += 1024) { v[0] += e[i]; v[1] += t[i]; }
+  reduce(v, 2);
+  const float me = (float)(tot[0] / (double)n), mt = (float)(tot[1] / (double)n);
+  __syncthreads();
+  v[0] = v[1] = v[2] = 0;
+  for (long long i = threadIdx.x; i < n; i += 1024) {
+    const float a = e[i] - me, c = t[i] - mt;
+    v[0] += (double)a * c; v[1] += (double)c * c; v[2] += (double)(a - c) * (a - c);
+  }
+  reduce(v, 3);
+  if (threadIdx.x == 0) {
+    const double dot = tot[0], en = tot[1] + 1e-8, nn = tot[2] + 1e-8;
+    const double scaled2 = dot * dot * tot[1] / (en * en);
+    const float neg = (float)(-10.0 * log10(scaled2 / nn + 1e-8));
+    out[blockIdx.x] = neg < clip ? clip : neg;
   }
 }
 
@@ -872,11 +1004,10 @@ int fullattn_launch(ClView qkv, ClView out, int B, int L, cudaStream_t st) {
   static const bool no_fa2 = getenv("LADIFF_NO_FA2") != nullptr;
   if (L <= FA2_MAX_KEYS && !no_fa2) {
     const size_t smem = (size_t)L * 64 * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr = 0;
+    if (ladiff_first_on_device(&attr)) {
       LADIFF_CUDA_OK(cudaFuncSetAttribute(fullattn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA2_MAX_KEYS * 64 * (int)sizeof(float)));
       prefer_max_smem_carveout(fullattn2_kernel);
-      attr = true;
     }
     LADIFF_CUDA_OK(launch_pdl(fullattn2_kernel, dim3(cdiv(L, 128), 4, B), dim3(128), smem, st, qkv, out, L));
     return 0;
@@ -906,11 +1037,42 @@ int absmax_inv_launch(const float* x, float* inv, int B, long long n, float eps,
   return 0;
 }
 
-int ddpm_step_launch(const float* eps, float* x, const float* noise, unsigned long long seed, int step_index, const int* t_dev,
-                     DdpmTables tb, ClView xin, int B, int C, int L, cudaStream_t st) {
+int ddpm_step_launch(const float* eps, float* x, const float* noise, unsigned long long seed, int t_abs, unsigned long long clip_offset,
+                     StepCoef cf, ClView xin, int B, int C, int L, cudaStream_t st) {
   LADIFF_REQUIRE(C % 32 == 0, LADIFF_ERR_ARG, "ddpm_step: C=%d", C);
   LADIFF_CARVEOUT_ONCE(ddpm_step_kernel);
-  ddpm_step_kernel<<<dim3(cdiv(L, 32), C / 32, B), dim3(32, 8), 0, st>>>(eps, x, noise, seed, step_index, t_dev, tb, xin, C, L);
+  ddpm_step_kernel<<<dim3(cdiv(L, 32), C / 32, B), dim3(32, 8), 0, st>>>(eps, x, noise, seed, t_abs, clip_offset, cf, xin, C, L);
+  LADIFF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int randn_fill_launch(float* x, long long n, unsigned long long seed, unsigned long long elem_offset, int uniform, cudaStream_t st) {
+  const long long thr = (n + 3) / 4;
+  randn_fill_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, st>>>(x, n, seed, elem_offset, uniform);
+  LADIFF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int q_sample_launch(const float* x, const float* noise, const int* t_dev, const float* sqrt_ac, const float* sqrt_1m_ac, float* out, int B,
+                    long long n, cudaStream_t st) {
+  const int gx = (int)((n + 255) / 256 < 592 ? (n + 255) / 256 : 592);
+  q_sample_kernel<<<dim3(gx, B), 256, 0, st>>>(x, noise, t_dev, sqrt_ac, sqrt_1m_ac, out, n);
+  LADIFF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int axpby_launch(float* x, float a, const float* y, float b, long long n, cudaStream_t st) {
+  const long long blocks = (n + 255) / 256;
+  axpby_kernel<<<(unsigned)(blocks < 1184 ? blocks : 1184), 256, 0, st>>>(x, a, y, b, n);
+  LADIFF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int p_losses_launch(const float* eps, const float* noise, const float* xt, const int* t_dev, const float* recip, const float* recipm1,
+                    const float* p2w, float* pred_x0, float* eps_ncl, float* part, float* loss, int B, int C, int L, cudaStream_t st) {
+  p_losses_kernel<<<B, 1024, 0, st>>>(eps, noise, xt, t_dev, recip, recipm1, p2w, pred_x0, eps_ncl, part, C, L);
+  mean_small_kernel<<<1, 32, 0, st>>>(part, loss, B);
+  LADIFF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int sdsdr_launch(const float* est, const float* tgt, float* out, int B, long long n, float clip, cudaStream_t st) {
+  sdsdr_kernel<<<B, 1024, 0, st>>>(est, tgt, out, n, clip);
   LADIFF_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -56,12 +56,25 @@ struct DdpmTables {   // device pointers to the (1000,) fp32 buffers of Gaussian
   const float* coef2;
   const float* logvar;
 };
-// One fused posterior step (ddpm_loss.py:175-179,199-206,233-251):
-//   x0 = clamp(a_t x - b_t eps, -1, 1); x <- c1_t x0 + c2_t x + exp(0.5 logvar_t) z   (z = 0 at t == 0)
-// eps channels-last f32 [B][L][C]; x NCL f32 in place; noise NCL f32 (step slice) or null -> Philox(seed, step);
-// also writes the new x as bf16 into xin (channels-last view, channel offset applied by caller).
-int ddpm_step_launch(const float* eps, float* x, const float* noise, unsigned long long seed, int step_index,
-                     const int* t_dev, DdpmTables tb, ClView xin, int B, int C, int L, cudaStream_t st);
+// One fused sampler step (see ddpm_step_kernel): x0 = clamp(a x - b eps, -1, 1);
+//   mode 0 (DDPM): x <- (k0 x0 + k1 x) + ks z;  mode 1 (DDIM): x <- (k0 x0 + k1 eps) + ks z;  mode 2: x <- x0.
+struct StepCoef { float a, b, k0, k1, ks; int mode; };
+// eps channels-last f32 [B][L][C]; x NCL f32 in place; noise NCL f32 (step slice) or null -> Philox(seed, t_abs, clip_offset + b);
+// also writes the new x as bf16 into xin (channels-last view, channel offset applied by caller; p null = skip).
+int ddpm_step_launch(const float* eps, float* x, const float* noise, unsigned long long seed, int t_abs, unsigned long long clip_offset,
+                     StepCoef cf, ClView xin, int B, int C, int L, cudaStream_t st);
+// x[0..n) <- N(0,1) (uniform = 0) or U[0,1) (uniform = 1) from Philox(seed, elem_offset + i)
+int randn_fill_launch(float* x, long long n, unsigned long long seed, unsigned long long elem_offset, int uniform, cudaStream_t st);
+// q_sample (ddpm_loss.py:387-393), per clip of n elements
+int q_sample_launch(const float* x, const float* noise, const int* t_dev, const float* sqrt_ac, const float* sqrt_1m_ac, float* out, int B,
+                    long long n, cudaStream_t st);
+// x <- a x + b y (y null: x <- a x)
+int axpby_launch(float* x, float a, const float* y, float b, long long n, cudaStream_t st);
+// p_losses tail (ddpm_loss.py:404-437): pred_x0 / eps_ncl optional NCL outputs, part [B] scratch, loss [1]
+int p_losses_launch(const float* eps, const float* noise, const float* xt, const int* t_dev, const float* recip, const float* recipm1,
+                    const float* p2w, float* pred_x0, float* eps_ncl, float* part, float* loss, int B, int C, int L, cudaStream_t st);
+// clamp(sd-sdr negative, min clip) per clip (losses_fn.py:54-66)
+int sdsdr_launch(const float* est, const float* tgt, float* out, int B, long long n, float clip, cudaStream_t st);
 int fill_t_launch(int* t_dev, int t, int B, cudaStream_t st);
 int time_to_int_launch(const long long* time, int* t_dev, int B, cudaStream_t st);
 

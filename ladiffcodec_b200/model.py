@@ -10,6 +10,7 @@ Out of scope and rejected loudly (``NotImplementedError``): training ``forward``
 ``use_film``, ``self_condition``, ``qtz_condition``, ``unet_scale_x``, ``model_type != 'unet'``.
 """
 import ctypes
+import functools
 import math
 from collections import OrderedDict
 from dataclasses import dataclass, field
@@ -27,8 +28,19 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
-def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _on_device(fn):
+    """Runs a method with the model's device current (a model on cuda:1 must not launch on cuda:0's context); the library
+    call then uses the current stream OF THAT DEVICE."""
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        owner = getattr(self, "_m", self)
+        with torch.cuda.device(owner.device):
+            return fn(self, *a, **k)
+    return wrapper
 
 
 def _f32(t, device):
@@ -66,6 +78,7 @@ class SEANetEncoder(_Sub):
         self.hop_length = int(math.prod(self.ratios))
         self.dimension = owner.cfg["rep_dims"]
 
+    @_on_device
     def __call__(self, x):
         m = self._m
         x = _f32(x, m.device)
@@ -89,6 +102,7 @@ class SEANetDecoder(_Sub):
         self.hop_length = int(math.prod(self.ratios))
         self.dimension = owner.cfg["rep_dims"]
 
+    @_on_device
     def __call__(self, z):
         m = self._m
         z = _f32(z, m.device)
@@ -117,6 +131,7 @@ class ResidualVectorQuantizer(_Sub):
     def get_num_quantizers_for_bandwidth(self, sample_rate, bandwidth=None):
         return num_quantizers_at_call(bandwidth, sample_rate, self.n_q, self.bins)
 
+    @_on_device
     def _run(self, x, n_q, want_q, want_codes):
         m = self._m
         x = _f32(x, m.device)
@@ -139,6 +154,7 @@ class ResidualVectorQuantizer(_Sub):
         n_q = self.get_num_quantizers_for_bandwidth(sample_rate, bandwidth)
         return self._run(x, n_q, False, True)[1]
 
+    @_on_device
     def decode(self, codes):
         m = self._m
         codes = codes.to(device=m.device, dtype=torch.int64).contiguous()
@@ -154,6 +170,7 @@ class _UpsamplingLayer:
     def __init__(self, owner, index, ratio):
         self._m, self.index, self.ratio = owner, index, ratio
 
+    @_on_device
     def __call__(self, x):
         m = self._m
         x = _f32(x, m.device)
@@ -177,6 +194,7 @@ class Unet1D(_Sub):
         self.upsampling_ratios = c["upsampling_ratios"]
         self.upsampling_layers = [_UpsamplingLayer(owner, i, r) for i, r in enumerate(c["upsampling_ratios"] or [])]
 
+    @_on_device
     def process_cond(self, x_cond):
         """unet.py:407-420."""
         for layer in self.upsampling_layers:
@@ -187,6 +205,7 @@ class Unet1D(_Sub):
             _lib.check(self._m._lib.ladiff_normalize_clips(_ptr(x_cond), B, x_cond[0].numel(), 2, _stream()), "scaling")
         return x_cond
 
+    @_on_device
     def __call__(self, x, time, x_cond=None):
         m = self._m
         if x_cond is None:
@@ -205,7 +224,13 @@ class Unet1D(_Sub):
 
 
 class GaussianDiffusion1D(_Sub):
-    """model.diffusion — srcs/losses/ddpm_loss.py:78-385 (sampling methods only)."""
+    """model.diffusion — srcs/losses/ddpm_loss.py:78-450: every sampler (p_sample, halfway_sampling, p_sample_loop, sample,
+    ddim_sample, infilling), q_sample and the forward-only training loss (forward → p_losses).
+
+    Randomness.  The reference draws from torch's global generator inside these methods.  Every method here takes the draws
+    explicitly instead: `noise=` a pre-drawn tensor consumed in the reference's draw order (parity mode), "torch" → drawn here
+    with torch.randn per step on the model's device (what the reference does when it runs on that device), or None → the
+    in-kernel counter-based generator keyed by (seed, timestep, global clip, element) (throughput mode)."""
 
     def __init__(self, owner, seq_length, sampling_timesteps=None):
         super().__init__(owner)
@@ -216,11 +241,21 @@ class GaussianDiffusion1D(_Sub):
         self.num_timesteps = NUM_TIMESTEPS
         self.sampling_timesteps = sampling_timesteps if sampling_timesteps is not None else NUM_TIMESTEPS
         self.is_ddim_sampling = False          # ddpm_loss.py:132
+        self.ddim_sampling_eta = 0.0           # ddpm_loss.py:134
         self.objective = "pred_noise"
+        self.loss_type = "l1"
+
+    # ---- plumbing
+    def _check_noise(self, noise, B, C, L):
+        m = self._m
+        noise = _f32(noise, m.device)
+        if noise.dim() != 4 or tuple(noise.shape[1:]) != (B, C, L):
+            raise ValueError(f"noise must be [n,{B},{C},{L}], got {tuple(noise.shape)}")
+        return noise
 
     def _steps(self, x, condition, t_start, n_steps, noise, seed):
-        """x is updated in place.  noise: None → in-kernel Philox(seed); 'torch' → torch.randn_like per step
-        (the draws the reference makes, ddpm_loss.py:249); tensor [n,B,C,L] → consumed in loop order."""
+        """DDPM steps t_start-1 … t_start-n_steps on x, in place.  noise: None → in-kernel generator(seed); 'torch' →
+        torch.randn_like per step (the draws the reference makes, ddpm_loss.py:249); tensor [n,B,C,L] → consumed in loop order."""
         m = self._m
         B, C, L = x.shape
         F = condition.shape[-1]
@@ -228,7 +263,7 @@ class GaussianDiffusion1D(_Sub):
 
         def call(xx, nz, n_nz, t0, n):
             _lib.check(m._lib.ladiff_ddpm_steps(m._h, _ptr(xx), _ptr(condition), _ptr(nz), n_nz, ctypes.c_uint64(seed),
-                                                t0, n, B, L, F, _ptr(ws), ws.numel(), _stream()), "ddpm_steps")
+                                                t0, n, B, L, F, _ptr(ws), ws.numel(), _stream(m.device)), "ddpm_steps")
 
         if isinstance(noise, str):
             if noise != "torch":
@@ -247,13 +282,27 @@ class GaussianDiffusion1D(_Sub):
         elif noise is None:
             call(x, None, 0, t_start, n_steps)
         else:
-            noise = _f32(noise, m.device)
-            if noise.dim() != 4 or tuple(noise.shape[1:]) != (B, C, L):
-                raise ValueError(f"noise must be [n,{B},{C},{L}], got {tuple(noise.shape)}")
+            noise = self._check_noise(noise, B, C, L)
             call(x, noise, noise.shape[0], t_start, n_steps)
         return x
 
+    def _initial(self, shape, init, seed, uniform=False):
+        """The sampler's first draw (torch.randn(shape), ddpm_loss.py:256,277; torch.rand for infilling, :336)."""
+        m = self._m
+        if init is not None and not isinstance(init, str):
+            x = _f32(init, m.device).clone()
+            if tuple(x.shape) != tuple(shape):
+                raise ValueError(f"init must have shape {tuple(shape)}")
+            return x
+        if init == "torch":
+            return (torch.rand if uniform else torch.randn)(tuple(shape), device=m.device)
+        x = torch.empty(tuple(shape), device=m.device)
+        _lib.check(m._lib.ladiff_randn(m._h, _ptr(x), shape[0], x[0].numel(), ctypes.c_uint64(seed), int(uniform), _stream(m.device)), "randn")
+        return x
+
+    # ---- samplers
     @torch.no_grad()
+    @_on_device
     def p_sample(self, x, t: int, condition=None, clip_denoised=True, noise="torch", seed=0):
         """ddpm_loss.py:244-251.  Returns (pred_img, None): x_start is only consumed by self-conditioning,
         which is off on this path."""
@@ -265,6 +314,7 @@ class GaussianDiffusion1D(_Sub):
         return self._steps(x, condition, t + 1, 1, noise, seed), None
 
     @torch.no_grad()
+    @_on_device
     def halfway_sampling(self, img=None, t=None, condition=None, noise="torch", seed=0):
         """ddpm_loss.py:370-385: steps i = t-1 … 0 of the 1000-step schedule starting from `img`."""
         m = self._m
@@ -277,21 +327,132 @@ class GaussianDiffusion1D(_Sub):
         return self._steps(img, condition, int(t), int(t), noise, seed)
 
     @torch.no_grad()
-    def p_sample_loop(self, shape, condition=None, noise="torch", seed=0):
-        """ddpm_loss.py:253-266: from N(0, I), all 1000 steps."""
+    @_on_device
+    def p_sample_loop(self, shape, condition=None, noise="torch", seed=0, init="torch", n_steps=None):
+        """ddpm_loss.py:253-266: from N(0, I), all 1000 steps (`n_steps` < 1000 stops early: the first n_steps of the loop)."""
         m = self._m
-        img = torch.randn(tuple(shape), device=m.device)
-        return self._steps(img, _f32(condition, m.device), self.num_timesteps, self.num_timesteps, noise, seed)
+        img = self._initial(shape, init if noise is not None or init != "torch" else None, seed)
+        n = self.num_timesteps if n_steps is None else int(n_steps)
+        return self._steps(img, _f32(condition, m.device), self.num_timesteps, n, noise, seed)
 
     @torch.no_grad()
-    def sample(self, batch_size=16, condition=None, noise="torch", seed=0):
+    @_on_device
+    def ddim_sample(self, shape, condition=None, clip_denoised=True, noise="torch", seed=0, init="torch"):
+        """ddpm_loss.py:268-303: `sampling_timesteps` DDIM steps from N(0, I) with eta = ddim_sampling_eta."""
+        if not clip_denoised:
+            raise NotImplementedError("clip_denoised=False is not on the sampling path")
+        m = self._m
+        B, C, L = tuple(shape)
+        condition = _f32(condition, m.device)
+        # the reference's own host-side time grid (ddpm_loss.py:273-275); plain Python integers, no tensor work
+        times = torch.linspace(-1, self.num_timesteps - 1, steps=self.sampling_timesteps + 1)
+        times = list(reversed(times.int().tolist()))
+        n_pairs = len(times) - 1
+        img = self._initial(shape, init if noise is not None or init != "torch" else None, seed)
+        if isinstance(noise, str):
+            if noise != "torch":
+                raise ValueError("noise must be None, 'torch' or a tensor")
+            n_draw = sum(1 for tn in times[1:] if tn >= 0)
+            noise = torch.stack([torch.randn_like(img) for _ in range(n_draw)]) if n_draw else torch.empty(0, B, C, L, device=m.device)
+        n_noise = 0
+        if noise is not None:
+            noise = self._check_noise(noise, B, C, L) if noise.numel() else noise
+            n_noise = noise.shape[0]
+        F = condition.shape[-1]
+        ws = m._workspace(B, L * m.decoder.hop_length)
+        arr = (ctypes.c_int32 * len(times))(*times)
+        _lib.check(m._lib.ladiff_ddim_steps(m._h, _ptr(img), _ptr(condition), arr, n_pairs, float(self.ddim_sampling_eta),
+                                            _ptr(noise) if n_noise else None, n_noise, ctypes.c_uint64(seed), B, L, F, _ptr(ws), ws.numel(),
+                                            _stream(m.device)), "ddim_steps")
+        return img
+
+    @torch.no_grad()
+    def sample(self, batch_size=16, condition=None, noise="torch", seed=0, init="torch"):
         """ddpm_loss.py:305-309."""
-        return self.p_sample_loop((batch_size, self.channels, self.seq_length), condition, noise=noise, seed=seed)
+        sample_fn = self.p_sample_loop if not self.is_ddim_sampling else self.ddim_sample
+        return sample_fn((batch_size, self.channels, self.seq_length), condition, noise=noise, seed=seed, init=init)
 
-    def _oos(self, *a, **k):
-        raise NotImplementedError("outside the sampling path of srcs.sample (SURVEY.md §8f): not built")
+    @torch.no_grad()
+    @_on_device
+    def infilling(self, infill_img, condition, midway_t=None, noise=None, offset=0, lam=0.8, step_noise="torch", seed=0, init="torch"):
+        """ddpm_loss.py:331-367.  `noise` and `offset` are accepted and unused, as in the reference (its `noise` only suppresses
+        an unused draw).  Per step t = midway_t-1 … 0: img ← p_sample(img); img ← (1-lam) img + lam infill; infill ← p_sample(infill);
+        img ← (1-lam) img + lam infill.  step_noise: "torch" | None | tensor [2(midway_t-1), B, C, L] in the reference's draw order."""
+        m = self._m
+        condition = _f32(condition, m.device)
+        infill = _f32(infill_img, m.device).clone()
+        B, C, L = condition.shape[0], self.channels, self.seq_length
+        if tuple(infill.shape) != (B, C, L):
+            raise ValueError(f"infill_img must be [{B},{C},{L}] (batch, channels, seq_length), got {tuple(infill.shape)}")
+        img = self._initial((B, C, L), init if step_noise is not None or init != "torch" else None, seed, uniform=True)
+        pre = None
+        if step_noise is not None and not isinstance(step_noise, str):
+            pre = self._check_noise(step_noise, B, C, L)
+        k = 0
+        n = int(B) * C * L
 
-    ddim_sample = interpolate = infilling = q_sample = p_losses = forward = __call__ = _oos
+        def mix():
+            _lib.check(m._lib.ladiff_axpby(_ptr(img), 1 - lam, _ptr(infill), lam, n, _stream(m.device)), "axpby")
+
+        for t in reversed(range(0, int(midway_t))):
+            for which, xx in ((0, img), (1, infill)):
+                if pre is not None:
+                    nz = pre[k:k + 1] if t > 0 else None
+                    k += 1 if t > 0 else 0
+                    self._steps(xx, condition, t + 1, 1, nz if nz is not None else torch.zeros(0, B, C, L, device=m.device), seed)
+                else:
+                    # two draws per timestep: the second p_sample of a step uses a different key
+                    self._steps(xx, condition, t + 1, 1, step_noise, seed if which == 0 else seed ^ 0x9E3779B97F4A7C15)
+                mix()
+        return img
+
+    @torch.no_grad()
+    def interpolate(self, *a, **k):
+        raise NotImplementedError("interpolate (ddpm_loss.py:311-328) calls p_sample without a condition, which the reference's own "
+                                  "conditional UNet (other_cond=True) cannot evaluate (unet.py:428): not usable with the released models")
+
+    @torch.no_grad()
+    @_on_device
+    def q_sample(self, x_start, t, noise=None):
+        """ddpm_loss.py:387-393."""
+        m = self._m
+        x_start = _f32(x_start, m.device)
+        noise = torch.randn_like(x_start) if noise is None else _f32(noise, m.device)
+        t = t.to(device=m.device, dtype=torch.int64).contiguous()
+        out = torch.empty_like(x_start)
+        ws = m._workspace(x_start.shape[0], m.decoder.hop_length * 16)
+        _lib.check(m._lib.ladiff_q_sample(m._h, _ptr(x_start), _ptr(t), _ptr(noise), _ptr(out), x_start.shape[0], x_start[0].numel(),
+                                          _ptr(ws), ws.numel(), _stream(m.device)), "q_sample")
+        return out
+
+    @torch.no_grad()
+    @_on_device
+    def p_losses(self, x_start, t, cond=None, noise=None, return_model_out=False):
+        """ddpm_loss.py:404-437, forward only (no autograd graph): → (loss, predicted_x_start, x_t)."""
+        m = self._m
+        x_start, cond = _f32(x_start, m.device), _f32(cond, m.device)
+        noise = torch.randn_like(x_start) if noise is None else _f32(noise, m.device)
+        t = t.to(device=m.device, dtype=torch.int64).contiguous()
+        B, C, L = x_start.shape
+        F = cond.shape[-1]
+        loss = torch.empty(1, device=m.device)
+        pred, x_t = torch.empty_like(x_start), torch.empty_like(x_start)
+        mo = torch.empty_like(x_start) if return_model_out else None
+        ws = m._workspace(B, L * m.decoder.hop_length)
+        _lib.check(m._lib.ladiff_p_losses(m._h, _ptr(x_start), _ptr(t), _ptr(cond), _ptr(noise), B, L, F, _ptr(loss), _ptr(pred), _ptr(x_t),
+                                          _ptr(mo), _ptr(ws), ws.numel(), _stream(m.device)), "p_losses")
+        out = (loss[0], pred, x_t)
+        return out + (mo,) if return_model_out else out
+
+    def forward(self, x, cond=None, t=None, *args, **kwargs):
+        """ddpm_loss.py:439-450 → (loss, predicted_x_start, x_t, t)."""
+        b, c, n = x.shape
+        assert n == self.seq_length, f"seq length must be {self.seq_length}, now is {n}"
+        if t is None:
+            t = torch.randint(0, self.num_timesteps, (b,), device=self._m.device).long()
+        return (*self.p_losses(x, t, cond, *args, **kwargs), t)
+
+    __call__ = forward
 
 
 class DiffAudioRep:
@@ -431,6 +592,7 @@ class DiffAudioRep:
             self._ws = torch.empty(int(need) + 1024, dtype=torch.uint8, device=self.device)
         return self._ws
 
+    @_on_device
     def get_cond(self, x, return_codes=False):
         """model.py:223-231: encoder → (if quantization) RVQ quantized output."""
         if not self._loaded:
@@ -451,10 +613,53 @@ class DiffAudioRep:
         return num_quantizers_at_call(self.bandwidth, self.frame_rate, self.quantizer.n_q)
 
     def get_scale(self, x):
-        raise NotImplementedError("get_scale is only referenced from commented-out code (sample.py:96)")
+        """model.py:233-238 with scaling_global: the constant."""
+        if not self.scaling_global:
+            raise NotImplementedError("only scaling_global (model.py:137-139) is used by the released configurations")
+        return 18.0
 
-    def forward(self, *a, **k):
-        raise NotImplementedError("DiffAudioRep.forward is the training-loss path (model.py:146-221): out of scope")
+    @torch.no_grad()
+    @_on_device
+    def forward(self, x, t=None, cond=None, noise=None):
+        """model.py:146-221, forward only (validation scoring; no autograd graph) for the configurations of the sampling path:
+        run_diff with an external condition (`cond` from the conditioning codec) and global scaling, or a plain codec
+        (run_diff=False).  Returns what the reference returns:
+          run_diff:  ({'diff_loss', 'neg_loss'}, x_hat, x_rep, predicted_x_start, x_t, t, x_rep_qtz, scale)
+          codec:     ({'tot_loss', 'qtz_loss', 'neg_sdr'}, x_hat)  /  ({'neg_sdr'}, x_hat) without a quantizer."""
+        if not self._loaded:
+            raise _lib.LadiffError("load weights first (utils.load_model)")
+        x = _f32(x, self.device)
+        B = x.shape[0]
+        x_rep = self.encoder(x)
+        x_rep_qtz, qtz_loss = None, None
+        if self.quantization:
+            res = self.quantizer(x_rep, sample_rate=self.frame_rate, bandwidth=self.bandwidth)
+            x_rep_qtz, qtz_loss = res.quantized, res.penalty          # eval mode: commitment penalty is 0 (core_vq.py:299-303)
+
+        def neg_sdr(a, b):                                            # sdr_loss(x, x_hat).mean(), model.py:198
+            out = torch.empty(B, device=self.device)
+            _lib.check(self._lib.ladiff_sdsdr(_ptr(a), _ptr(b), _ptr(out), B, a[0].numel(), -30.0, _stream(self.device)), "sdsdr")
+            return out.mean()
+
+        if self.run_diff:
+            if cond is None:
+                raise NotImplementedError("DiffAudioRep.forward without `cond` (unconditional / qtz_condition training) is out of scope")
+            if not self.scaling_global or self.cfg.get("scaling_frame") or self.cfg.get("scaling_feature"):
+                raise NotImplementedError("only scaling_global (model.py:137-139) is used by the released configurations")
+            scale = 18.0
+            x_rep = x_rep.clone()
+            _lib.check(self._lib.ladiff_axpby(_ptr(x_rep), 1.0 / scale, None, 0.0, x_rep.numel(), _stream(self.device)), "scaling")
+            self.diffusion.seq_length = x_rep.shape[-1] if self.diffusion.seq_length is None else self.diffusion.seq_length
+            diff_loss, predicted_x_start, x_t, t = self.diffusion(x_rep, cond, t=t, noise=noise)
+            in_dec = predicted_x_start.clone()
+            _lib.check(self._lib.ladiff_axpby(_ptr(in_dec), scale, None, 0.0, in_dec.numel(), _stream(self.device)), "unscale")
+            x_hat = self.decoder(in_dec)
+            return ({"diff_loss": diff_loss, "neg_loss": neg_sdr(x, x_hat)}, x_hat, x_rep, predicted_x_start, x_t, t, x_rep_qtz, scale)
+        x_hat = self.decoder(x_rep_qtz if self.quantization else x_rep)
+        nl = neg_sdr(x, x_hat)
+        if not self.quantization:
+            return {"neg_sdr": nl}, x_hat
+        return {"tot_loss": qtz_loss + nl, "qtz_loss": qtz_loss, "neg_sdr": nl}, x_hat
 
     __call__ = forward
 

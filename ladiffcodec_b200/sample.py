@@ -36,7 +36,8 @@ def build_models(inp_args, device=None):
 
 
 @torch.no_grad()
-def synthesize(model, model_for_cond, wav, n_steps=MIDWAY_T, noise=None, seed=0, return_latent=False):
+def synthesize(model, model_for_cond, wav, n_steps=MIDWAY_T, noise=None, seed=0, return_latent=False, sampler="ddpm", eta=0.0,
+               init_noise=None):
     """Batched body of synthesis() (sample.py:94-134) in ONE library call: get_cond → upsample → max-normalise →
     halfway_sampling(t=n_steps) → decoder → std/max-normalise, each normalisation per clip.
 
@@ -44,7 +45,14 @@ def synthesize(model, model_for_cond, wav, n_steps=MIDWAY_T, noise=None, seed=0,
     returned on the host; a CUDA tensor stays on the device.
     noise: None → in-kernel Philox(seed) (throughput mode; differs from torch's stream by design);
            tensor [n_steps-1,B,128,L] → consumed exactly like the reference's per-step randn_like draws.
+    sampler: "ddpm" (the script's halfway_sampling from the upsampled condition) or "ddim" (the reference's ddim_sample,
+           ddpm_loss.py:268-303, `n_steps` = sampling_timesteps, from N(0, I) = `init_noise` [B,128,L] or the in-kernel generator).
     """
+    with torch.cuda.device(model.device):
+        return _synthesize(model, model_for_cond, wav, n_steps, noise, seed, return_latent, sampler, eta, init_noise)
+
+
+def _synthesize(model, model_for_cond, wav, n_steps, noise, seed, return_latent, sampler, eta, init_noise):
     dev = model.device
     on_host = wav.device.type != "cuda"
     if on_host:
@@ -66,13 +74,24 @@ def synthesize(model, model_for_cond, wav, n_steps=MIDWAY_T, noise=None, seed=0,
             raise ValueError(f"noise must be [n,{B},{model.cfg['rep_dims']},{L}], got {tuple(noise.shape)}")
         n_noise = noise.shape[0]
     ws = model._workspace(B, T, other=model_for_cond)
-    _lib.check(model._lib.ladiff_synthesize(model._h, model_for_cond._h, _ptr(x), B, T, int(n_steps), _ptr(noise), n_noise,
-                                            ctypes.c_uint64(seed), _ptr(out), _ptr(latent), _ptr(ws), ws.numel(), _stream()),
-               "synthesize")
+    if sampler == "ddpm":
+        _lib.check(model._lib.ladiff_synthesize(model._h, model_for_cond._h, _ptr(x), B, T, int(n_steps), _ptr(noise), n_noise,
+                                                ctypes.c_uint64(seed), _ptr(out), _ptr(latent), _ptr(ws), ws.numel(), _stream(dev)),
+                   "synthesize")
+    elif sampler == "ddim":
+        if init_noise is not None:
+            init_noise = init_noise.to(device=dev, dtype=torch.float32).contiguous()
+            if tuple(init_noise.shape) != (B, model.cfg["rep_dims"], L):
+                raise ValueError("init_noise must be [B,128,L]")
+        _lib.check(model._lib.ladiff_synthesize_ddim(model._h, model_for_cond._h, _ptr(x), B, T, int(n_steps), float(eta), _ptr(init_noise),
+                                                     _ptr(noise), n_noise, ctypes.c_uint64(seed), _ptr(out), _ptr(latent), _ptr(ws),
+                                                     ws.numel(), _stream(dev)), "synthesize_ddim")
+    else:
+        raise ValueError("sampler must be 'ddpm' or 'ddim'")
     if on_host:
         host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
         host.copy_(out, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        torch.cuda.current_stream(dev).synchronize()
         out = host
     return (out, latent) if return_latent else out
 
@@ -100,7 +119,7 @@ def synthesize_from_codes(model, model_for_cond, codes, n_steps=MIDWAY_T, noise=
     ws = model._workspace(B, T, other=model_for_cond)
     _lib.check(model._lib.ladiff_synthesize_codes(model._h, model_for_cond._h, _ptr(codes), int(n_q), B, F, int(n_steps), _ptr(noise),
                                                   n_noise, ctypes.c_uint64(seed), _ptr(out), _ptr(latent), _ptr(ws), ws.numel(),
-                                                  _stream()), "synthesize_from_codes")
+                                                  _stream(dev)), "synthesize_from_codes")
     return (out, latent) if return_latent else out
 
 
@@ -122,14 +141,21 @@ class SynthesisPipeline:
         self.n = 0
 
     def _workspace(self, slot, B, T):
+        """The slot's scratch is allocated (and, on regrow, dropped) under the slot's own stream, so the caching allocator orders
+        any reuse of the old block after the batch that may still be running in it."""
         need = self.model._lib.ladiff_synthesize_workspace_bytes(self.model._h, self.cmodel._h, B, T)
         if self.ws[slot] is None or self.ws[slot].numel() < need:
-            self.ws[slot] = None
-            self.ws[slot] = torch.empty(int(need) + 1024, dtype=torch.uint8, device=self.model.device)
+            with torch.cuda.stream(self.streams[slot]):
+                self.ws[slot] = None
+                self.ws[slot] = torch.empty(int(need) + 1024, dtype=torch.uint8, device=self.model.device)
         return self.ws[slot]
 
     @torch.no_grad()
-    def submit(self, wav, n_steps=MIDWAY_T, seed=0):
+    def submit(self, wav, n_steps=MIDWAY_T, seed=0, sampler="ddpm"):
+        with torch.cuda.device(self.model.device):
+            return self._submit(wav, n_steps, seed, sampler)
+
+    def _submit(self, wav, n_steps, seed, sampler):
         m, c = self.model, self.cmodel
         slot = self.n % self.depth
         self.n += 1
@@ -150,8 +176,12 @@ class SynthesisPipeline:
                 x = src.to(m.device, non_blocking=True)
             else:
                 x = wav.to(dtype=torch.float32).contiguous()
-            _lib.check(m._lib.ladiff_synthesize(m._h, c._h, _ptr(x), B, T, int(n_steps), None, 0, ctypes.c_uint64(seed), _ptr(out),
-                                                None, _ptr(ws), ws.numel(), ctypes.c_void_p(st.cuda_stream)), "synthesize")
+            if sampler == "ddim":
+                _lib.check(m._lib.ladiff_synthesize_ddim(m._h, c._h, _ptr(x), B, T, int(n_steps), 0.0, None, None, 0, ctypes.c_uint64(seed),
+                                                         _ptr(out), None, _ptr(ws), ws.numel(), ctypes.c_void_p(st.cuda_stream)), "synthesize_ddim")
+            else:
+                _lib.check(m._lib.ladiff_synthesize(m._h, c._h, _ptr(x), B, T, int(n_steps), None, 0, ctypes.c_uint64(seed), _ptr(out),
+                                                    None, _ptr(ws), ws.numel(), ctypes.c_void_p(st.cuda_stream)), "synthesize")
             if on_host:
                 host.copy_(out, non_blocking=True)
             x.record_stream(st)
@@ -194,13 +224,23 @@ def _save_wav(path, wav, sr):
         wavfile.write(path, sr, wav.squeeze(0).numpy())
 
 
-def synthesis(inp_args):
-    """sample.py:50-136, file for file."""
+def _normalize(lib, x, mode, device):
+    """sample.py:129 (mode 0) / :133-134 (mode 1) on the device, per clip (the script runs B = 1: whole tensor == per clip)."""
+    B = x.shape[0]
+    _lib.check(lib.ladiff_normalize_clips(_ptr(x), B, x[0].numel(), mode, _stream(device)), "normalize")
+    return x
+
+
+def synthesis(inp_args, noise_device=None):
+    """sample.py:50-136, file for file.  The reference draws its per-step noise with torch.randn_like on the tensor's device;
+    `noise_device="cpu"` (or LADIFF_NOISE_DEVICE=cpu) draws the same numbers from the CPU generator instead and copies them over,
+    which reproduces a CPU run of the reference under the same torch.manual_seed."""
     import torchaudio
+    noise_device = noise_device or os.environ.get("LADIFF_NOISE_DEVICE", "cuda")
     model, model_for_cond = build_models(inp_args)
     device = model.device
     midway_t = MIDWAY_T
-    with torch.no_grad():
+    with torch.no_grad(), torch.cuda.device(device):
         for wav_file in sorted(glob.glob(os.path.join(inp_args.input_dir, "**/*.wav"), recursive=True)):
             local_path = wav_file[len(inp_args.input_dir):][:-4]
             save_path = inp_args.output_dir + local_path
@@ -220,11 +260,13 @@ def synthesis(inp_args):
             if inp_args.upsampling_ratios is not None:
                 for layer in model.diff_model.upsampling_layers:
                     img = layer(img)
-            img /= torch.max(torch.abs(img.flatten())) + 1e-8
-            sample = model.diffusion.halfway_sampling(img=img, condition=cond, t=midway_t)
+            img = _normalize(model._lib, img, 0, device)                                       # sample.py:129
+            noise = "torch"
+            if noise_device == "cpu":
+                noise = torch.stack([torch.randn(img.shape) for _ in range(midway_t - 1)]).to(device)
+            sample = model.diffusion.halfway_sampling(img=img, condition=cond, t=midway_t, noise=noise)
             x_sample_mid = model.decoder(sample)
-            x_sample_mid /= torch.std(x_sample_mid.flatten()) + 1e-8
-            x_sample_mid /= torch.max(torch.abs(x_sample_mid.flatten())) + 1e-8
+            x_sample_mid = _normalize(model._lib, x_sample_mid, 1, device)                     # sample.py:133-134
             _save_wav(f"{save_path}.wav", x_sample_mid.squeeze(1).cpu(), 16000)
 
 

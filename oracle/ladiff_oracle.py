@@ -451,6 +451,117 @@ def halfway_sampling(img, t, cond, sd, noise, unet_kwargs):
     return img
 
 
+def p_sample_loop(img, cond, sd, noise, unet_kwargs, t_start=1000, n_steps=None, trace=None):
+    """GaussianDiffusion1D.p_sample_loop, ddpm_loss.py:253-266, from the given initial `img` (the reference draws
+    torch.randn(shape) first, then one randn_like per step with t > 0): steps t_start-1 … t_start-n_steps.
+    noise: [n, B, C, L] consumed in loop order.  `trace`, if a list, receives x after every step."""
+    n_steps = t_start if n_steps is None else n_steps
+    k = 0
+    for i in reversed(range(t_start - n_steps, t_start)):
+        z = None
+        if i > 0:
+            z = noise[k]; k += 1
+        img, _ = p_sample(img, i, cond, sd, z, unet_kwargs)
+        if trace is not None:
+            trace.append(img)
+    return img
+
+
+def ddim_time_pairs(total_timesteps, sampling_timesteps):
+    """ddpm_loss.py:273-275."""
+    times = torch.linspace(-1, total_timesteps - 1, steps=sampling_timesteps + 1)
+    times = list(reversed(times.int().tolist()))
+    return list(zip(times[:-1], times[1:]))
+
+
+def ddim_sample(img, cond, sd, noise, unet_kwargs, sampling_timesteps, eta=0.0, total_timesteps=1000, trace=None):
+    """GaussianDiffusion1D.ddim_sample, ddpm_loss.py:268-303 (objective pred_noise, clip_denoised=True, pred_noise NOT
+    re-derived after the clamp: model_predictions' rederive_pred_noise defaults to False), from the given initial `img`.
+    noise: [n, B, C, L], one per pair with time_next >= 0 (the reference draws randn_like even when eta == 0)."""
+    ac = sd["diffusion.alphas_cumprod"]
+    b = img.shape[0]
+    k = 0
+    for time, time_next in ddim_time_pairs(total_timesteps, sampling_timesteps):
+        bt = torch.full((b,), time, dtype=torch.long)
+        pred_noise = unet_forward(img, bt, cond, sd, **unet_kwargs)
+
+        def ext(name):
+            return sd["diffusion." + name].gather(-1, bt).reshape(b, 1, 1)
+
+        x_start = ext("sqrt_recip_alphas_cumprod") * img - ext("sqrt_recipm1_alphas_cumprod") * pred_noise
+        x_start = torch.clamp(x_start, min=-1.0, max=1.0)
+        if time_next < 0:
+            img = x_start
+        else:
+            alpha = ac[time]
+            alpha_next = ac[time_next]
+            sigma = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
+            c = (1 - alpha_next - sigma ** 2).sqrt()
+            z = noise[k]; k += 1
+            img = x_start * alpha_next.sqrt() + c * pred_noise + sigma * z
+        if trace is not None:
+            trace.append(img)
+    return img
+
+
+def infilling(img, infill_img, cond, sd, noise, unet_kwargs, midway_t, lam=0.8):
+    """GaussianDiffusion1D.infilling, ddpm_loss.py:331-367, from the given initial `img` (the reference draws
+    torch.rand — uniform — of shape (B, channels, seq_length)).  Per step t = midway_t-1 … 0 the reference runs p_sample on
+    img, mixes, runs p_sample on infill_img, mixes again; noise: [n, B, C, L] in that draw order (two per step with t > 0)."""
+    k = 0
+    for t in reversed(range(0, midway_t)):
+        z = None
+        if t > 0:
+            z = noise[k]; k += 1
+        img, _ = p_sample(img, t, cond, sd, z, unet_kwargs)
+        img = (1 - lam) * img + lam * infill_img
+        z = None
+        if t > 0:
+            z = noise[k]; k += 1
+        infill_img, _ = p_sample(infill_img, t, cond, sd, z, unet_kwargs)
+        img = (1 - lam) * img + lam * infill_img
+    return img
+
+
+def q_sample(x_start, t, noise, sd):
+    """GaussianDiffusion1D.q_sample, ddpm_loss.py:387-393.  t: [B] long."""
+    b = x_start.shape[0]
+    a = sd["diffusion.sqrt_alphas_cumprod"].gather(-1, t).reshape(b, 1, 1)
+    s = sd["diffusion.sqrt_one_minus_alphas_cumprod"].gather(-1, t).reshape(b, 1, 1)
+    return a * x_start + s * noise
+
+
+def p_losses(x_start, t, cond, noise, sd, unet_kwargs):
+    """GaussianDiffusion1D.p_losses, ddpm_loss.py:404-437 (loss_type l1, objective pred_noise, no self-conditioning):
+    → (loss, predicted_x_start, x_t).  The reference evaluates the UNet twice on the same inputs (once under no_grad for
+    predicted_x_start, once for the loss); forward-only the two evaluations are the same tensor."""
+    b = x_start.shape[0]
+    x = q_sample(x_start, t, noise, sd)
+    model_out = unet_forward(x, t, cond, sd, **unet_kwargs)
+    a = sd["diffusion.sqrt_recip_alphas_cumprod"].gather(-1, t).reshape(b, 1, 1)
+    r = sd["diffusion.sqrt_recipm1_alphas_cumprod"].gather(-1, t).reshape(b, 1, 1)
+    predicted_x_start = a * x - r * model_out              # model_predictions without clipping (clip_x_start=False)
+    loss = F.l1_loss(model_out, noise, reduction="none").reshape(b, -1).mean(dim=1)
+    loss = loss * sd["diffusion.p2_loss_weight"].gather(-1, t)
+    return loss.mean(), predicted_x_start, x
+
+
+def sd_sdr_neg(est, target, eps=1e-8):
+    """asteroid.losses.sdr.MultiSrcNegSDR("sdsdr") (asteroid 0.6, not in the image; published algorithm — Le Roux et al.,
+    "SDR – half-baked or well done?", 2019): zero-mean both, scaled target = <est,tgt>/(|tgt|^2 + eps) * tgt, e_noise =
+    est - tgt (scale-DEPENDENT variant), sdr = 10 log10(|scaled|^2 / (|e_noise|^2 + eps) + eps); returns -mean over sources.
+    est, target: [B, n_src, T].  Used by losses_fn.ClippedSDR (clamp at min -30), called as sdr_loss(x, x_hat) in model.py:198."""
+    target = target - target.mean(dim=2, keepdim=True)
+    est = est - est.mean(dim=2, keepdim=True)
+    dot = (est * target).sum(dim=2, keepdim=True)
+    energy = (target ** 2).sum(dim=2, keepdim=True) + eps
+    scaled = dot * target / energy
+    e_noise = est - target
+    sdr = (scaled ** 2).sum(dim=2) / ((e_noise ** 2).sum(dim=2) + eps)
+    sdr = 10 * torch.log10(sdr + eps)
+    return -sdr.mean(dim=-1)
+
+
 # ----------------------------------------------------------------------------- sample.py
 
 
