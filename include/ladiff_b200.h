@@ -64,6 +64,8 @@ typedef struct LadiffHandle LadiffHandle;
 const char* ladiff_last_error(void);
 /* ABI version of this header; bump on any signature change. */
 int32_t ladiff_abi_version(void);
+/* 16-bit type of the UNet's tensor-core operands and stored activations in this build: "f16" (default) or "bf16". */
+const char* ladiff_act_dtype(void);
 
 /* DiffAudioRep(**kwargs)                                              srcs/model.py:34-106 */
 int32_t ladiff_create(const LadiffConfig* cfg, LadiffHandle** out);
@@ -76,7 +78,7 @@ int32_t ladiff_destroy(LadiffHandle* h);
 int32_t ladiff_load_weight(LadiffHandle* h, const char* name, const float* data,
                            const int64_t* shape, int32_t ndim);
 /* End of strict load: verifies every expected key arrived with the expected shape, then folds
- * (weight-norm g*v/||v||, weight standardisation, time-MLP → FiLM table, bf16 K-major repack).
+ * (weight-norm g*v/||v||, weight standardisation, time-MLP → FiLM table, 16-bit K-major repack).
  * Synchronises the device. */
 int32_t ladiff_finalize(LadiffHandle* h);
 /* Number of keys the strict layout expects (745 for the README LaDiff model, 148 for the codec). */
@@ -209,12 +211,12 @@ int64_t ladiff_synthesize_workspace_bytes(const LadiffHandle* model, const Ladif
 int32_t ladiff_normalize_clips(float* x, int32_t B, int64_t n, int32_t mode, void* stream);
 
 /* ---- operator-level entry points (tests, profiling) ------------------------------------------ */
-/* Channels-last bf16 Conv1d on the tcgen05 path: x [B,L,Cin] bf16, w [Cout,Cin,k] fp32 (PyTorch
- * layout), zero padding (k-1)/2, stride 1 → y [B,L,Cout] (bf16, or fp32 if y_f32).  impl 0 = tcgen05,
+/* Channels-last 16-bit (ladiff_act_dtype()) Conv1d on the tcgen05 path: x [B,L,Cin] f16, w [Cout,Cin,k] fp32 (PyTorch
+ * layout), zero padding (k-1)/2, stride 1 → y [B,L,Cout] (f16, or fp32 if y_f32).  impl 0 = tcgen05,
  * 1 = SIMT check kernel (same packed operands), 2 = tcgen05 with per-tap activation tiles, 3 = tcgen05 positions-on-M
  * kernel, 4 = the same with a cta_group::2 CTA pair per tile,
  * 5 = channels-on-M kernel shaped for two CTAs per SM (small-K convs only).  Allocates and frees its own scratch; synchronises. */
-int32_t ladiff_op_conv1d_cl(const void* x_bf16, const float* w, const float* bias, int32_t B, int32_t L,
+int32_t ladiff_op_conv1d_cl(const void* x_h16, const float* w, const float* bias, int32_t B, int32_t L,
                             int32_t Cin, int32_t Cout, int32_t k, void* y, int32_t y_f32, int32_t impl,
                             float* gn_stats /* [B,Cout/32,2] or NULL */);
 /* Selects the conv implementation used inside the UNet: 0 = tcgen05 (default), 1 = SIMT check kernel. */

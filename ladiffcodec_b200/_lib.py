@@ -31,6 +31,7 @@ class LadiffConfig(ctypes.Structure):
 SIGNATURES = {
     "ladiff_last_error": (c_cp, []),
     "ladiff_abi_version": (c_i32, []),
+    "ladiff_act_dtype": (c_cp, []),
     "ladiff_create": (c_i32, [ctypes.POINTER(LadiffConfig), ctypes.POINTER(c_vp)]),
     "ladiff_destroy": (c_i32, [c_vp]),
     "ladiff_load_weight": (c_i32, [c_vp, c_cp, c_vp, ctypes.POINTER(c_i64), c_i32]),
@@ -91,6 +92,12 @@ def get_lib():
             raise LadiffError(f"ABI mismatch: library {lib.ladiff_abi_version()} != binding {ABI_VERSION}; rebuild")
         _lib = lib
     return _lib
+
+
+def act_dtype():
+    """torch dtype of the UNet's 16-bit operands / stored activations in the loaded build."""
+    import torch
+    return {"f16": torch.float16, "bf16": torch.bfloat16}[get_lib().ladiff_act_dtype().decode()]
 
 
 def check(rc, what=""):

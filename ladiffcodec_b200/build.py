@@ -19,6 +19,8 @@ LIB = os.path.join(HERE, "libladiff_b200.so")
 SOURCES = ["tc_conv.cu", "unet_ops.cu", "codec_ops.cu", "fold.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+if os.environ.get("LADIFF_USE_BF16"):          # A/B build: bf16 instead of fp16 operands / activations (csrc/common.cuh)
+    NVCC_FLAGS.append("-DLADIFF_USE_BF16")
 
 
 def _nvcc():

@@ -28,6 +28,7 @@ bool ladiff_pdl_enabled() {
   return on;
 }
 extern "C" int32_t ladiff_abi_version(void) { return 2; }
+extern "C" const char* ladiff_act_dtype(void) { return LADIFF_DTYPE_NAME; }
 
 #define TRY(expr)              \
   do {                         \
@@ -59,7 +60,7 @@ struct DecoderW { ConvW first, last; std::vector<ConvTrW> up; std::vector<ResBlo
 // ---- folded UNet parameters
 enum ConvKind { CK_PLAIN = TC_KIND_PLAIN, CK_DOWN = TC_KIND_DOWN, CK_UP = TC_KIND_UP };
 struct PackedConv {
-  bf16* w = nullptr; const float* bias = nullptr;
+  h16* w = nullptr; const float* bias = nullptr;
   int CoutV = 0, Cin = 0, K = 1, Ktot = 0, kind = CK_PLAIN;
   int split_m = 0;     // > 0: rows [split_m, CoutV) are a fused 1x1 res_conv of the same input (second output)
   CUtensorMap tmW;
@@ -95,7 +96,7 @@ struct Bump {
 };
 
 struct UnetBufs {
-  bf16 *xin, *FC, *CA[5], *CB[5], *X[6], *tY, *tH, *tO, *tR, *tA, *qkv, *ao;
+  h16 *xin, *FC, *CA[5], *CB[5], *X[6], *tY, *tH, *tO, *tR, *tA, *qkv, *ao;
   float* eps; float* ctx; float* la_part; int* la_cnt; float2* stats; int* t_dev; float* inv_scale; float* condup; float* condtmp;
   int stats_slots;
 };
@@ -449,7 +450,7 @@ int pack_block1_fused(H* h, const std::string& p, int cin, int cout, PackedConv*
   LADIFF_REQUIRE(cin % 64 == 0 && cout % 128 == 0, LADIFF_ERR_UNSUPPORTED, "%s: Cin=%d Cout=%d", p.c_str(), cin, cout);
   pc->Cin = cin; pc->K = 3; pc->kind = CK_PLAIN; pc->CoutV = 2 * cout; pc->Ktot = 3 * cin; pc->split_m = cout;
   TRY(dalloc(h, &pc->w, (size_t)pc->CoutV * pc->Ktot));
-  LADIFF_CUDA_OK(cudaMemset(pc->w, 0, sizeof(bf16) * (size_t)pc->CoutV * pc->Ktot));
+  LADIFF_CUDA_OK(cudaMemset(pc->w, 0, sizeof(h16) * (size_t)pc->CoutV * pc->Ktot));
   TRY(pack_conv_launch(w1, pc->w, cout, cin, 3, 1, 0));
   TRY(pack_conv_launch(wr, pc->w + (size_t)cout * pc->Ktot, cout, cin, 1, 0, 0, pc->Ktot));
   float* b2 = nullptr;
@@ -730,21 +731,21 @@ int run_cond_upsample(H* h, const float* cond, int B, int F, float* out, float* 
 void carve_unet(const H* h, Bump& bp, int B, int L, UnetBufs* u) {
   const int* d = h->un.dims;
   const size_t BL = (size_t)B * L;
-  u->xin = bp.get<bf16>(BL * 256);
-  u->FC = bp.get<bf16>(BL * 2 * d[0]);
+  u->xin = bp.get<h16>(BL * 256);
+  u->FC = bp.get<h16>(BL * 2 * d[0]);
   for (int i = 0; i < 5; ++i) {
     const size_t n = (size_t)B * (L >> i) * (d[i + 1] + d[i]);
-    u->CA[i] = bp.get<bf16>(n);
-    u->CB[i] = bp.get<bf16>(n);
+    u->CA[i] = bp.get<h16>(n);
+    u->CB[i] = bp.get<h16>(n);
   }
   u->X[0] = nullptr;
-  for (int i = 1; i <= 5; ++i) u->X[i] = bp.get<bf16>((size_t)B * (L >> (i < 5 ? i : 4)) * d[i]);
+  for (int i = 1; i <= 5; ++i) u->X[i] = bp.get<h16>((size_t)B * (L >> (i < 5 ? i : 4)) * d[i]);
   size_t tmax = 0;
   for (int i = 0; i < 5; ++i) { const size_t n = (size_t)B * (L >> i) * d[i + 1]; if (n > tmax) tmax = n; }
-  u->tY = bp.get<bf16>(tmax); u->tH = bp.get<bf16>(tmax); u->tO = bp.get<bf16>(tmax); u->tR = bp.get<bf16>(tmax);
-  u->tA = bp.get<bf16>(tmax);
-  u->qkv = bp.get<bf16>(BL * 384);
-  u->ao = bp.get<bf16>(BL * 128);
+  u->tY = bp.get<h16>(tmax); u->tH = bp.get<h16>(tmax); u->tO = bp.get<h16>(tmax); u->tR = bp.get<h16>(tmax);
+  u->tA = bp.get<h16>(tmax);
+  u->qkv = bp.get<h16>(BL * 384);
+  u->ao = bp.get<h16>(BL * 128);
   u->eps = bp.get<float>(BL * 128);
   u->ctx = bp.get<float>((size_t)B * 4096);
   u->la_part = bp.get<float>(linattn_part_floats(B, L));
@@ -757,7 +758,7 @@ void carve_unet(const H* h, Bump& bp, int B, int L, UnetBufs* u) {
   u->condtmp = bp.get<float>(BL * 128);
 }
 
-ClView view(bf16* p, int L, int pitch, int C, int ch0 = 0) {
+ClView view(h16* p, int L, int pitch, int C, int ch0 = 0) {
   ClView v; v.p = p + ch0; v.bstride = (long long)L * pitch; v.pitch = pitch; v.C = C; return v;
 }
 
@@ -770,7 +771,7 @@ struct PlanBuilder {
     pl->op_label.resize(pl->ops.size());
     pl->op_label.back() = buf;
   }
-  // conv: `in` has Lin rows; writes Lout rows into `out` (bf16) or out32 (fp32, contiguous [B][Lout][CoutV])
+  // conv: `in` has Lin rows; writes Lout rows into `out` (h16) or out32 (fp32, contiguous [B][Lout][CoutV])
   int conv(const PackedConv& pc, ClView in, int Lin, ClView out, float* out32, bool want_stats, int* n_ntiles, ClView res,
            ClView out2 = ClView{nullptr, 0, 0, 0}) {
     LADIFF_REQUIRE(in.C == pc.Cin, LADIFF_ERR_ARG, "plan: conv input has %d channels, weights expect %d", in.C, pc.Cin);
@@ -928,12 +929,14 @@ struct PlanBuilder {
 };
 
 int build_plan(H* h, void* ws_unet, int B, int L, cudaStream_t st, Plan** out) {
+  static const bool dbg_plan = getenv("LADIFF_DEBUG_PLAN") != nullptr;
   for (size_t i = 0; i < h->plans.size(); ++i) {
     Plan* p = h->plans[i];
     if (p->ws == ws_unet && p->B == B && p->L == L) {      // most recently used plan at the back (LRU eviction)
       h->plans.erase(h->plans.begin() + i);
       h->plans.push_back(p);
       *out = p;
+      if (dbg_plan) fprintf(stderr, "[plan] hit  %p ws=%p B=%d L=%d runs=%lld\n", (void*)p, ws_unet, B, L, p->runs);
       return 0;
     }
   }
@@ -1017,6 +1020,7 @@ int build_plan(H* h, void* ws_unet, int B, int L, cudaStream_t st, Plan** out) {
   }
   h->plans.push_back(pl);
   *out = pl;
+  if (dbg_plan) fprintf(stderr, "[plan] built %p ws=%p B=%d L=%d (%zu cached)\n", (void*)pl, ws_unet, B, L, h->plans.size());
   return 0;
 }
 
@@ -1134,6 +1138,7 @@ int ddpm_run(H* h, Plan* pl, float* x, const float* cond, const float* noise, in
   UnetBufs& u = pl->bufs;
   LADIFF_REQUIRE(t_start <= kTimesteps && n_steps >= 0 && t_start - n_steps >= 0, LADIFF_ERR_ARG, "ddpm: t_start=%d n_steps=%d",
                  t_start, n_steps);
+  if (getenv("LADIFF_DEBUG_PLAN")) fprintf(stderr, "[ddpm] x=%p cond=%p noise=%p n_noise=%lld t_start=%d n=%d B=%d L=%d F=%d\n", (void*)x, (void*)cond, (void*)noise, (long long)n_noise, t_start, n_steps, B, L, F);
   TRY(prepare_cond(h, pl, cond, B, L, F, st));
   ClView xs = view(u.xin, L, 256, 128, 128);
   TRY(ncl_to_cl_launch(x, nullptr, xs, B, 128, L, st));
@@ -1614,22 +1619,22 @@ extern "C" int64_t ladiff_take_launch_count(LadiffHandle* h) {
   return n;
 }
 
-extern "C" int32_t ladiff_op_conv1d_cl(const void* x_bf16, const float* w, const float* bias, int32_t B, int32_t L, int32_t Cin,
+extern "C" int32_t ladiff_op_conv1d_cl(const void* x_h16, const float* w, const float* bias, int32_t B, int32_t L, int32_t Cin,
                                        int32_t Cout, int32_t k, void* y, int32_t y_f32, int32_t impl, float* gn_stats) {
-  LADIFF_REQUIRE(x_bf16 && w && y && Cin % 64 == 0 && Cout % 128 == 0 && k >= 1 && k <= TC_MAX_TAPS && (k & 1), LADIFF_ERR_ARG,
+  LADIFF_REQUIRE(x_h16 && w && y && Cin % 64 == 0 && Cout % 128 == 0 && k >= 1 && k <= TC_MAX_TAPS && (k & 1), LADIFF_ERR_ARG,
                  "ladiff_op_conv1d_cl: Cin %% 64, Cout %% 128, odd k <= %d required", TC_MAX_TAPS);
   LADIFF_REQUIRE(impl >= 0 && impl <= 5, LADIFF_ERR_ARG, "ladiff_op_conv1d_cl: impl=%d", impl);
-  bf16* wp = nullptr; float2* stats = nullptr;
-  LADIFF_CUDA_OK(cudaMalloc((void**)&wp, sizeof(bf16) * (size_t)Cout * Cin * k));
+  h16* wp = nullptr; float2* stats = nullptr;
+  LADIFF_CUDA_OK(cudaMalloc((void**)&wp, sizeof(h16) * (size_t)Cout * Cin * k));
   int rc = pack_conv_launch(w, wp, Cout, Cin, k, 0, 0);
   CUtensorMap tmW;
   if (!rc) rc = tc_make_tmap_w(&tmW, wp, Cout, Cin * k);
   TcConvDesc d;
   memset(&d, 0, sizeof(d));
   d.kind = TC_KIND_PLAIN; d.Cin = Cin; d.K = k; d.CoutV = Cout; d.w = wp; d.tmW = &tmW; d.Ktot = Cin * k; d.bias = bias;
-  d.x = (const bf16*)x_bf16; d.x_bstride = (long long)L * Cin; d.x_pitch = Cin; d.Lin = L;
+  d.x = (const h16*)x_h16; d.x_bstride = (long long)L * Cin; d.x_pitch = Cin; d.Lin = L;
   if (y_f32) d.out32 = (float*)y;
-  else { d.out = (bf16*)y; d.out_bstride = (long long)L * Cout; d.out_pitch = Cout; }
+  else { d.out = (h16*)y; d.out_bstride = (long long)L * Cout; d.out_pitch = Cout; }
   d.B = B; d.tap_share = impl == 2 ? 0 : 1; d.want_transposed = impl == 3 ? 1 : (impl == 4 ? 2 : 0);
   if (impl == 5) { d.want_two_per_sm = 1; d.want_nt = 128; }
   TcConvParams p;

@@ -1,4 +1,4 @@
-// Load-time weight folds for the UNet: weight standardisation (unet.py:72-80) + bf16 K-major repack.
+// Load-time weight folds for the UNet: weight standardisation (unet.py:72-80) + h16 K-major repack.
 #include "fold.cuh"
 
 namespace {
@@ -12,9 +12,9 @@ __device__ float block_sum128(float v, float* red) {
   return red[0] + red[1] + red[2] + red[3];
 }
 
-// w [Cout][Cin][K] fp32 -> packed [Cout][K*Cin] bf16 with k-index = tap*Cin + c.
+// w [Cout][Cin][K] fp32 -> packed [Cout][K*Cin] h16 with k-index = tap*Cin + c.
 // standardize: per output channel (w - mean) * rsqrt(var_biased + 1e-5) over (Cin, K).     one block (128 thr) per o
-__global__ void __launch_bounds__(128) pack_conv_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cin, int K,
+__global__ void __launch_bounds__(128) pack_conv_kernel(const float* __restrict__ w, h16* __restrict__ out, int Cin, int K,
                                                         int standardize, int out_ld) {
   __shared__ float red[4];
   const int o = blockIdx.x, n = Cin * K;
@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(128) pack_conv_kernel(const float* __restrict_
   }
   for (int i = threadIdx.x; i < n; i += 128) {
     const int c = i / K, tap = i - c * K;
-    out[(long long)o * out_ld + tap * Cin + c] = __float2bfloat16((wr[i] - mean) * rstd);
+    out[(long long)o * out_ld + tap * Cin + c] = f2h((wr[i] - mean) * rstd);
   }
 }
 
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(128) pack_conv_kernel(const float* __restrict_
 //   y[2m]   = W0 x[m-1] + (W1+W2) x[m]            rows [0, Cout)
 //   y[2m+1] = (W0+W1) x[m] + W2 x[m+1]            rows [Cout, 2Cout)
 // w [Cout][Cin][3] -> packed [2Cout][3*Cin] (tap order -1, 0, +1)
-__global__ void pack_up_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin) {
+__global__ void pack_up_kernel(const float* __restrict__ w, h16* __restrict__ out, int Cout, int Cin) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)2 * Cout * 3 * Cin;
   if (i >= total) return;
@@ -51,7 +51,7 @@ __global__ void pack_up_kernel(const float* __restrict__ w, bf16* __restrict__ o
   float v;
   if (m < Cout) v = tap == 0 ? wr[0] : (tap == 1 ? wr[1] + wr[2] : 0.f);
   else v = tap == 0 ? 0.f : (tap == 1 ? wr[0] + wr[1] : wr[2]);
-  out[i] = __float2bfloat16(v);
+  out[i] = f2h(v);
 }
 
 __global__ void dup_bias_kernel(const float* __restrict__ b, float* __restrict__ out, int n) {
@@ -59,19 +59,19 @@ __global__ void dup_bias_kernel(const float* __restrict__ b, float* __restrict__
   if (i < 2 * n) out[i] = b[i % n];
 }
 
-__global__ void f32_to_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long long n) {
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, h16* __restrict__ y, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) y[i] = __float2bfloat16(x[i]);
+  if (i < n) y[i] = f2h(x[i]);
 }
 
 }  // namespace
 
-int pack_conv_launch(const float* w, bf16* out, int Cout, int Cin, int K, int standardize, cudaStream_t st, int out_ld) {
+int pack_conv_launch(const float* w, h16* out, int Cout, int Cin, int K, int standardize, cudaStream_t st, int out_ld) {
   pack_conv_kernel<<<Cout, 128, 0, st>>>(w, out, Cin, K, standardize, out_ld > 0 ? out_ld : Cin * K);
   LADIFF_CUDA_OK(cudaGetLastError());
   return 0;
 }
-int pack_up_launch(const float* w, bf16* out, int Cout, int Cin, cudaStream_t st) {
+int pack_up_launch(const float* w, h16* out, int Cout, int Cin, cudaStream_t st) {
   const long long total = (long long)2 * Cout * 3 * Cin;
   pack_up_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, out, Cout, Cin);
   LADIFF_CUDA_OK(cudaGetLastError());
@@ -82,7 +82,7 @@ int dup_bias_launch(const float* b, float* out, int n, cudaStream_t st) {
   LADIFF_CUDA_OK(cudaGetLastError());
   return 0;
 }
-int f32_to_bf16_launch(const float* x, bf16* y, long long n, cudaStream_t st) {
+int f32_to_bf16_launch(const float* x, h16* y, long long n, cudaStream_t st) {
   f32_to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, n);
   LADIFF_CUDA_OK(cudaGetLastError());
   return 0;

@@ -1,12 +1,12 @@
 // tcgen05 implicit-GEMM Conv1d for the UNet (sm_100a).
 //
 // Replaces every F.conv1d of Unet1D.forward (reference srcs/modules/unet.py:80,61,65,201,204,232,307,369)
-// on channels-last bf16 activations with fp32 accumulation in TMEM.
+// on channels-last h16 activations with fp32 accumulation in TMEM.
 //
 //   D[m, n] (TMEM, fp32; lane = output channel m, column = position n)
 //     = sum over groups / 64-channel chunks / taps of
-//       A = W[m0:m0+128, kofs_tap + 64c : +64]            (bf16, K-major, TMA 2D, SWIZZLE_128B)
-//       B = X[b, l0+shift+row_off_tap : +N, ch0+64c : +64] (bf16, K-major, TMA 3D, SWIZZLE_128B, OOB rows -> 0 = zero padding)
+//       A = W[m0:m0+128, kofs_tap + 64c : +64]            (h16, K-major, TMA 2D, SWIZZLE_128B)
+//       B = X[b, l0+shift+row_off_tap : +N, ch0+64c : +64] (h16, K-major, TMA 3D, SWIZZLE_128B, OOB rows -> 0 = zero padding)
 //
 // The activation tile of a chunk is loaded ONCE with its halo rows; every tap reads it through a shared-memory
 // descriptor whose start address is advanced by row_off*128 B (the 128B-swizzle XOR is a function of the absolute
@@ -16,7 +16,7 @@
 //   warp 0    TMA producer (two rings: weights 16 KB slots, activations)
 //   warp 1    TMEM allocator + MMA issuer (tcgen05.mma cta_group::1 kind::f16, M=128, N<=256, K=16)
 //   warps 2-9 epilogue: two warpgroups (each covers the four TMEM lane quadrants) that take alternate store chunks of a tile:
-//             tcgen05.ld -> +bias -> GroupNorm partial sums -> bf16 -> smem staging -> TMA store
+//             tcgen05.ld -> +bias -> GroupNorm partial sums -> h16 -> smem staging -> TMA store
 // Two TMEM accumulator stages, so the epilogue of tile i overlaps the main loop of tile i+1.
 // Short clips (L < 128) are packed several per tile (one TMA box per clip, per-clip zero padding kept).
 #include <cudaTypedefs.h>
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
     if (elect_one()) {
       // ---------------- MMA issuer.  Instruction descriptor (InstrDescriptor, mma_sm100_desc.hpp):
       // c_format F32 (1<<4) | a_format BF16 (1<<7) | b_format BF16 (1<<10) | K-major A,B | N>>3 <<17 | M>>4 <<24
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NMMA >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (TC_IDESC_AB_FMT << 7) | (TC_IDESC_AB_FMT << 10) | ((uint32_t)(p.NMMA >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       const int S = p.S;
       const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
       const bool no_mma = (p.dbg & 4) != 0;
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
       if (p.bias && t + (int)gridDim.x < total_tiles) bias_next = __ldg(p.bias + decode_tile(p, t + gridDim.x).m0 + q * 32 + lane);
       const bool second = p.split_m && tc.m0 >= p.split_m;
       if (p.res) {
-        // direct epilogue with a residual: its tile ([clip region][row][128 channels] bf16) is staged in shared memory by all
+        // direct epilogue with a residual: its tile ([clip region][row][128 channels] h16) is staged in shared memory by all
         // epilogue threads while the main loop of this tile is still running
         asm volatile("bar.sync 3, 256;" ::: "memory");          // the previous tile's residual has been consumed
         const int et = threadIdx.x - 64;                         // 0..255
@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
                 for (int i = 0; i < 16; ++i) {
                   const float v = __uint_as_float(r[i]) + bias;
                   s1 += v; s2 += v * v;
-                  const unsigned short hv = __bfloat16_as_ushort(__float2bfloat16(v));
+                  const unsigned short hv = h16_bits(f2h(v));
                   asm volatile("st.shared.u16 [%0], %1;" ::"r"(stg + (uint32_t)(c0 + i) * 256u), "h"(hv) : "memory");
                 }
               } else {
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
                 for (int i = 0; i < 16; ++i) {
                   const float v = __uint_as_float(r[i]) + bias;
                   if (r0 + c0 + i < vr) { s1 += v; s2 += v * v; }
-                  const unsigned short hv = __bfloat16_as_ushort(__float2bfloat16(v));
+                  const unsigned short hv = h16_bits(f2h(v));
                   asm volatile("st.shared.u16 [%0], %1;" ::"r"(stg + (uint32_t)(c0 + i) * 256u), "h"(hv) : "memory");
                 }
               }
@@ -378,11 +378,11 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
                   if (p.res) {
                     unsigned short rv16;
                     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(rv16) : "r"(stage0 + (uint32_t)(j * p.NT + row) * 256u + (uint32_t)(q * 32 + lane) * 2u));
-                    v += __bfloat162float(__ushort_as_bfloat16(rv16));
+                    v += h2f(h16_from_bits(rv16));
                   }
                   const long long o = (long long)b * p.out_bstride + (long long)l * p.out_pitch + ch;
                   if (p.out_f32) reinterpret_cast<float*>(p.out)[o] = v;
-                  else reinterpret_cast<bf16*>(p.out)[o] = __float2bfloat16(v);
+                  else reinterpret_cast<h16*>(p.out)[o] = f2h(v);
                 }
               }
             }
@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(kThreadsT, 1) tc_conv_t_kernel(const __grid_co
   } else if (warp == 1) {
     if (leader && elect_one()) {
       // ---------------- MMA issuer: M = 128*CG positions, N = NCH channels, K = 16 per instruction
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NCH >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (TC_IDESC_AB_FMT << 7) | (TC_IDESC_AB_FMT << 10) | ((uint32_t)(p.NCH >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
       int sa = 0, sw = 0, tl = 0; uint32_t pa = 0, pw = 0;
       long long w_full = 0, w_tmem = 0;
       for (int t = tile0; t < total_tiles; t += tile_step, ++tl) {
@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(kThreadsT, 1) tc_conv_t_kernel(const __grid_co
       if (second) obase = (char*)p.out2v + ((long long)b * p.out2_bstride + (long long)l * p.out2_pitch + (n0 - p.split_m)) * 2;
       else if (p.up_cout) obase = (char*)p.out + ((long long)b * p.out_bstride + (long long)(2 * l + n0 / p.up_cout) * p.out_pitch + n0 % p.up_cout) * 2;
       else obase = (char*)p.out + ((long long)b * p.out_bstride + (long long)l * p.out_pitch + n0) * (p.out_f32 ? 4 : 2);
-      const bf16* rbase = p.res ? p.res + (long long)b * p.res_bstride + (long long)l * p.res_pitch + n0 : nullptr;
+      const h16* rbase = p.res ? p.res + (long long)b * p.res_bstride + (long long)l * p.res_pitch + n0 : nullptr;
       const bool want_stats = p.stats && !second && l0 < p.Lout;    // (a pair's second tile can lie wholly past the clip)
       mbar_wait_t(&tf[acc], (tl >> 1) & 1, w_acc, prof);
       tc_fence_after();
@@ -674,11 +674,11 @@ __global__ void __launch_bounds__(kThreadsT, 1) tc_conv_t_kernel(const __grid_co
             for (int i = 0; i < 16; ++i) { a1 += v[i]; a2 += v[i] * v[i]; }
             if (rbase) {
               const uint4 q0 = __ldcg(reinterpret_cast<const uint4*>(rbase + cb)), q1 = __ldcg(reinterpret_cast<const uint4*>(rbase + cb + 8));
-              const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&q0);
-              const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&q1);
+              const h162* h0 = reinterpret_cast<const h162*>(&q0);
+              const h162* h1 = reinterpret_cast<const h162*>(&q1);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const float2 f0 = __bfloat1622float2(h0[i]), f1 = __bfloat1622float2(h1[i]);
+                const float2 f0 = h22ff(h0[i]), f1 = h22ff(h1[i]);
                 v[2 * i] += f0.x; v[2 * i + 1] += f0.y; v[8 + 2 * i] += f1.x; v[8 + 2 * i + 1] += f1.y;
               }
             }
@@ -688,10 +688,10 @@ __global__ void __launch_bounds__(kThreadsT, 1) tc_conv_t_kernel(const __grid_co
               for (int i = 0; i < 4; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             } else {
               uint4 o0, o1;
-              __nv_bfloat162* g0 = reinterpret_cast<__nv_bfloat162*>(&o0);
-              __nv_bfloat162* g1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+              h162* g0 = reinterpret_cast<h162*>(&o0);
+              h162* g1 = reinterpret_cast<h162*>(&o1);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) { g0[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); g1[i] = __floats2bfloat162_rn(v[8 + 2 * i], v[8 + 2 * i + 1]); }
+              for (int i = 0; i < 4; ++i) { g0[i] = ff2h2(v[2 * i], v[2 * i + 1]); g1[i] = ff2h2(v[8 + 2 * i], v[8 + 2 * i + 1]); }
               uint4* o = reinterpret_cast<uint4*>(obase + (size_t)cb * 2);
               o[0] = o0; o[1] = o1;
             }
@@ -747,23 +747,23 @@ __global__ void __launch_bounds__(128) tc_conv_ref_kernel(TcConvParams p, TcRefV
         const TcTap& tap = gr.tap[tp];
         const int row = l + gr.shift + tap.row_off;
         if (m0 < tap.m_lo || m0 >= tap.m_hi || row < 0 || row >= v.Lv) continue;
-        const bf16* xr = v.x + (long long)b * v.bstride + (long long)row * v.pitch + gr.ch0;
-        const bf16* wr = v.w + (long long)ch * v.Ktot + tap.kofs;
-        for (int c = 0; c < gr.nchunk * TC_BK; ++c) acc += __bfloat162float(wr[c]) * __bfloat162float(xr[c]);
+        const h16* xr = v.x + (long long)b * v.bstride + (long long)row * v.pitch + gr.ch0;
+        const h16* wr = v.w + (long long)ch * v.Ktot + tap.kofs;
+        for (int c = 0; c < gr.nchunk * TC_BK; ++c) acc += h2f(wr[c]) * h2f(xr[c]);
       }
     }
     float val = acc + bias;
     s1 += val; s2 += val * val;
     if (p.direct) {
-      if (p.res) val += __bfloat162float(p.res[(long long)b * p.res_bstride + (long long)l * p.res_pitch + ch]);
+      if (p.res) val += h2f(p.res[(long long)b * p.res_bstride + (long long)l * p.res_pitch + ch]);
       const long long o = (long long)b * p.out_bstride + (long long)l * p.out_pitch + ch;
       if (p.out_f32) reinterpret_cast<float*>(p.out)[o] = val;
-      else reinterpret_cast<bf16*>(p.out)[o] = __float2bfloat16(val);
+      else reinterpret_cast<h16*>(p.out)[o] = f2h(val);
     } else if (p.split_m && ch >= p.split_m) {
-      v.out2[(long long)b * v.out2_bstride + (long long)l * v.out2_pitch + (ch - p.split_m)] = __float2bfloat16(val);
+      v.out2[(long long)b * v.out2_bstride + (long long)l * v.out2_pitch + (ch - p.split_m)] = f2h(val);
     } else {
       const int phase = ch / Cc, cc = ch % Cc, nph = p.up_cout ? 2 : 1;
-      v.out[(long long)b * v.out_bstride + (long long)(l * nph + phase) * v.out_pitch + cc] = __float2bfloat16(val);
+      v.out[(long long)b * v.out_bstride + (long long)(l * nph + phase) * v.out_pitch + cc] = f2h(val);
     }
   }
   if (p.stats && !(p.split_m && ch >= p.split_m)) {
@@ -799,14 +799,14 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   return fn;
 }
 
-int make_tmap_x(CUtensorMap* tm, const bf16* x, int B, int Lv, int Cv, int pitch, long long bstride, int boxrows) {
+int make_tmap_x(CUtensorMap* tm, const h16* x, int B, int Lv, int Cv, int pitch, long long bstride, int boxrows) {
   auto enc = get_encode();
   LADIFF_REQUIRE(enc != nullptr, LADIFF_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[3] = {(cuuint64_t)Cv, (cuuint64_t)Lv, (cuuint64_t)B};
   cuuint64_t strides[2] = {(cuuint64_t)pitch * 2, (cuuint64_t)bstride * 2};
   cuuint32_t box[3] = {TC_BK, (cuuint32_t)boxrows, 1};
   cuuint32_t es[3] = {1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)x, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = enc(tm, TC_TMAP_DTYPE, 3, (void*)x, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   LADIFF_REQUIRE(r == CUDA_SUCCESS, LADIFF_ERR_CUDA, "cuTensorMapEncodeTiled(X B%d L%d C%d pitch %d box %d) failed: %d", B, Lv, Cv,
                  pitch, boxrows, (int)r);
@@ -814,14 +814,14 @@ int make_tmap_x(CUtensorMap* tm, const bf16* x, int B, int Lv, int Cv, int pitch
 }
 
 // output map {Cc, phases, rows, B}: element (c, ph, l, b) at out[b*bstride + (l*phases + ph)*pitch + c]
-int make_tmap_y(CUtensorMap* tm, const bf16* out, int Cc, int phases, int rows, int B, int pitch, long long bstride, int boxrows) {
+int make_tmap_y(CUtensorMap* tm, const h16* out, int Cc, int phases, int rows, int B, int pitch, long long bstride, int boxrows) {
   auto enc = get_encode();
   LADIFF_REQUIRE(enc != nullptr, LADIFF_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[4] = {(cuuint64_t)Cc, (cuuint64_t)phases, (cuuint64_t)rows, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)pitch * 2 * phases, (cuuint64_t)bstride * 2};
   cuuint32_t box[4] = {TC_BM, 1, (cuuint32_t)boxrows, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = enc(tm, TC_TMAP_DTYPE, 4, (void*)out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   LADIFF_REQUIRE(r == CUDA_SUCCESS, LADIFF_ERR_CUDA, "cuTensorMapEncodeTiled(Y C%d ph%d rows%d B%d pitch %d box %d) failed: %d", Cc,
                  phases, rows, B, pitch, boxrows, (int)r);
@@ -840,27 +840,27 @@ int tc_num_sms() {
   return n;   // every GPU of one box is the same part
 }
 
-static int make_tmap_wt(CUtensorMap* tm, const bf16* w, int Cout, int Ktot, int nch) {
+static int make_tmap_wt(CUtensorMap* tm, const h16* w, int Cout, int Ktot, int nch) {
   auto enc = get_encode();
   LADIFF_REQUIRE(enc != nullptr, LADIFF_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
   cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
   cuuint32_t box[2] = {TC_BK, (cuuint32_t)nch};
   cuuint32_t es[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = enc(tm, TC_TMAP_DTYPE, 2, (void*)w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   LADIFF_REQUIRE(r == CUDA_SUCCESS, LADIFF_ERR_CUDA, "cuTensorMapEncodeTiled(Wt %dx%d box %d) failed: %d", Cout, Ktot, nch, (int)r);
   return 0;
 }
 
-int tc_make_tmap_w(CUtensorMap* tm, const bf16* w, int Cout, int Ktot) {
+int tc_make_tmap_w(CUtensorMap* tm, const h16* w, int Cout, int Ktot) {
   auto enc = get_encode();
   LADIFF_REQUIRE(enc != nullptr, LADIFF_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
   cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
   cuuint32_t box[2] = {TC_BK, TC_BM};
   cuuint32_t es[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = enc(tm, TC_TMAP_DTYPE, 2, (void*)w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   LADIFF_REQUIRE(r == CUDA_SUCCESS, LADIFF_ERR_CUDA, "cuTensorMapEncodeTiled(W %dx%d) failed: %d", Cout, Ktot, (int)r);
   return 0;

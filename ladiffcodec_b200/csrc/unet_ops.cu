@@ -1,4 +1,4 @@
-// Element-wise / normalisation / attention kernels of the UNet (channels-last bf16, fp32 math).
+// Element-wise / normalisation / attention kernels of the UNet (channels-last h16, fp32 math).
 #include <stdlib.h>
 
 #include "unet_ops.cuh"
@@ -6,7 +6,7 @@
 namespace {
 
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
-// SiLU(2h) = h + h*tanh(h): one MUFU (tanh.approx.f32, rel. error 2^-11 -> <= 2^-12 of the result, below the bf16 rounding of
+// SiLU(2h) = h + h*tanh(h): one MUFU (tanh.approx.f32, rel. error 2^-11 -> <= 2^-12 of the result, below the h16 rounding of
 // the stored activation) instead of ex2 + rcp; callers fold the factor 1/2 into their affine transform
 __device__ __forceinline__ float silu_from_half(float h) {
   float t;
@@ -15,18 +15,18 @@ __device__ __forceinline__ float silu_from_half(float h) {
 }
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+  const h162* h = reinterpret_cast<const h162*>(&u);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float2 t = __bfloat1622float2(h[i]);
+    float2 t = h22ff(h[i]);
     f[2 * i] = t.x; f[2 * i + 1] = t.y;
   }
 }
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   uint4 u;
-  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+  h162* h = reinterpret_cast<h162*>(&u);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  for (int i = 0; i < 4; ++i) h[i] = ff2h2(f[2 * i], f[2 * i + 1]);
   return u;
 }
 
@@ -67,9 +67,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a, int rows_p
   }
   const int r0 = blockIdx.x * rows_per_cta;
   const int r1 = min(r0 + rows_per_cta, a.L);
-  const bf16* yb = a.y.p + (long long)b * a.y.bstride + c0;
-  const bf16* rb = a.res.p ? a.res.p + (long long)b * a.res.bstride + c0 : nullptr;
-  bf16* ob = a.out.p + (long long)b * a.out.bstride + c0;
+  const h16* yb = a.y.p + (long long)b * a.y.bstride + c0;
+  const h16* rb = a.res.p ? a.res.p + (long long)b * a.res.bstride + c0 : nullptr;
+  h16* ob = a.out.p + (long long)b * a.out.bstride + c0;
   pdl_wait();
   pdl_trigger();
   uint4 u[GN_U], ur[GN_U];
@@ -153,9 +153,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a, int rows_p
     return;
   }
   // ---- with the attention pre-norm fused: the cv threads that share a row (cv/32 whole warps) reduce (sum, sumsq) of the
-  // bf16-rounded result, so LN sees exactly the tensor the unfused kernel would read back.  Uniform trip count per CTA.
+  // h16-rounded result, so LN sees exactly the tensor the unfused kernel would read back.  Uniform trip count per CTA.
   const int wpr = cv >> 5;                                 // warps per row
-  bf16* lb = a.ln_out.p + (long long)b * a.ln_out.bstride + c0;
+  h16* lb = a.ln_out.p + (long long)b * a.ln_out.bstride + c0;
   const int nbatch = (r1 - r0 + GN_U * rstep - 1) / (GN_U * rstep);
   for (int it = 0; it < nbatch; ++it) {
     uint4 o[GN_U];
@@ -240,11 +240,11 @@ __global__ void __launch_bounds__(256) layernorm_cl_kernel(ClView x, const float
 #pragma unroll
     for (int r = 0; r < LN_R; ++r) {
       if (row0 + r >= L) break;
-      const bf16* xr = x.p + (long long)b * x.bstride + (long long)(row0 + r) * x.pitch;
+      const h16* xr = x.p + (long long)b * x.bstride + (long long)(row0 + r) * x.pitch;
 #pragma unroll
       for (int i = 0; i < NVEC; ++i) raw[r][i] = __ldcg(reinterpret_cast<const uint4*>(xr + (lane + 32 * i) * 8));
       if (res.p) {
-        const bf16* rr = res.p + (long long)b * res.bstride + (long long)(row0 + r) * res.pitch;
+        const h16* rr = res.p + (long long)b * res.bstride + (long long)(row0 + r) * res.pitch;
 #pragma unroll
         for (int i = 0; i < NVEC; ++i) rres[r][i] = __ldcg(reinterpret_cast<const uint4*>(rr + (lane + 32 * i) * 8));
       }
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(256) layernorm_cl_kernel(ClView x, const float
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
       const float rstd = rsqrtf(q / (float)C + 1e-5f);
-      bf16* orow = out.p + (long long)b * out.bstride + (long long)(row0 + r) * out.pitch;
+      h16* orow = out.p + (long long)b * out.bstride + (long long)(row0 + r) * out.pitch;
 #pragma unroll
       for (int i = 0; i < NVEC; ++i) {
         float f[8];
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(256) linattn_ctx_kernel(ClView qkv, float* __r
   {
     // 8 threads per row: 4 x 16 B of k, 4 x 16 B of v; all (<= LA_S/32) row loads of a thread are issued before the first use
     const int c = tid & 7;
-    const bf16* base = qkv.p + (long long)b * qkv.bstride + (c < 4 ? 128 : 256) + h * 32 + (c & 3) * 8;
+    const h16* base = qkv.p + (long long)b * qkv.bstride + (c < 4 ? 128 : 256) + h * 32 + (c & 3) * 8;
     float (*dst)[32] = c < 4 ? ks : vs;
     constexpr int NB = LA_S / 32;
     uint4 raw[NB];
@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(256, 3) linattn_out_kernel(ClView qkv, const f
   pdl_trigger();
   uint4 qraw[4];
   if (n < L) {
-    const bf16* qr = qkv.p + (long long)b * qkv.bstride + (long long)n * qkv.pitch + h * 32;
+    const h16* qr = qkv.p + (long long)b * qkv.bstride + (long long)n * qkv.pitch + h * 32;
 #pragma unroll
     for (int i = 0; i < 4; ++i) qraw[i] = __ldcg(reinterpret_cast<const uint4*>(qr + 8 * i));
   }
@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(256, 3) linattn_out_kernel(ClView qkv, const f
       acc[4 * e4 + 2] += pd * c.z; acc[4 * e4 + 3] += pd * c.w;
     }
   }
-  bf16* orow = out.p + (long long)b * out.bstride + (long long)n * out.pitch + h * 32;
+  h16* orow = out.p + (long long)b * out.bstride + (long long)n * out.pitch + h * 32;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float f[8];
@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(256) fullattn_kernel(ClView qkv, ClView out, i
   constexpr int KT = 128;
   __shared__ float ks[KT][33];
   __shared__ float vs[KT][33];
-  const bf16* base = qkv.p + (long long)b * qkv.bstride;
+  const h16* base = qkv.p + (long long)b * qkv.bstride;
   const float scale = 0.17677669529663687f;
   float qreg[4][32];
   float m[4], l[4], acc[4];
@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(256) fullattn_kernel(ClView qkv, ClView out, i
     qi[u] = blockIdx.x * 32 + warp * 4 + u;
     m[u] = -INFINITY; l[u] = 0.f; acc[u] = 0.f;
     float qv = 0.f;
-    if (qi[u] < L) qv = __bfloat162float(base[(long long)qi[u] * qkv.pitch + h * 32 + lane]) * scale;
+    if (qi[u] < L) qv = h2f(base[(long long)qi[u] * qkv.pitch + h * 32 + lane]) * scale;
 #pragma unroll
     for (int d = 0; d < 32; ++d) qreg[u][d] = __shfl_sync(0xffffffffu, qv, d);
   }
@@ -527,8 +527,8 @@ __global__ void __launch_bounds__(256) fullattn_kernel(ClView qkv, ClView out, i
       const int j = i >> 5, d = i & 31;
       float kk = 0.f, vv = 0.f;
       if (k0 + j < L) {
-        kk = __bfloat162float(base[(long long)(k0 + j) * qkv.pitch + 128 + h * 32 + d]);
-        vv = __bfloat162float(base[(long long)(k0 + j) * qkv.pitch + 256 + h * 32 + d]);
+        kk = h2f(base[(long long)(k0 + j) * qkv.pitch + 128 + h * 32 + d]);
+        vv = h2f(base[(long long)(k0 + j) * qkv.pitch + 256 + h * 32 + d]);
       }
       ks[j][d] = kk; vs[j][d] = vv;
     }
@@ -565,7 +565,7 @@ __global__ void __launch_bounds__(256) fullattn_kernel(ClView qkv, ClView out, i
 #pragma unroll
   for (int u = 0; u < 4; ++u)
     if (qi[u] < L)
-      out.p[(long long)b * out.bstride + (long long)qi[u] * out.pitch + h * 32 + lane] = __float2bfloat16(acc[u] / l[u]);
+      out.p[(long long)b * out.bstride + (long long)qi[u] * out.pitch + h * 32 + lane] = f2h(acc[u] / l[u]);
 }
 
 // ------------------------------------------------------------------ full attention, keys resident in shared memory
@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(128) fullattn2_kernel(ClView qkv, ClView out, 
   const int h = blockIdx.y, b = blockIdx.z;
   pdl_wait();
   pdl_trigger();
-  const bf16* base = qkv.p + (long long)b * qkv.bstride;
+  const h16* base = qkv.p + (long long)b * qkv.bstride;
   for (int i = threadIdx.x; i < L * 8; i += 128) {          // 8 x 16 B per key row: k (4) then v (4)
     const int j = i >> 3, c = i & 7;
     float f[8];
@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(128) fullattn2_kernel(ClView qkv, ClView out, 
   const int qi = blockIdx.x * 128 + threadIdx.x;
   float q[32];
   if (qi < L) {
-    const bf16* qr = base + (long long)qi * qkv.pitch + h * 32;
+    const h16* qr = base + (long long)qi * qkv.pitch + h * 32;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float f[8];
@@ -629,7 +629,7 @@ __global__ void __launch_bounds__(128) fullattn2_kernel(ClView qkv, ClView out, 
     }
   }
   const float inv = 1.f / l;
-  bf16* orow = out.p + (long long)b * out.bstride + (long long)qi * out.pitch + h * 32;
+  h16* orow = out.p + (long long)b * out.bstride + (long long)qi * out.pitch + h * 32;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float f[8];
@@ -640,7 +640,7 @@ __global__ void __launch_bounds__(128) fullattn2_kernel(ClView qkv, ClView out, 
 }
 
 // ------------------------------------------------------------------ layout conversion
-// NCL f32 -> channels-last bf16 (optionally scaled per clip).  grid (ceil(L/32), C/32, B), block (32, 8)
+// NCL f32 -> channels-last h16 (optionally scaled per clip).  grid (ceil(L/32), C/32, B), block (32, 8)
 __global__ void ncl_to_cl_kernel(const float* __restrict__ x, const float* __restrict__ inv_scale, ClView out, int C, int L) {
   __shared__ float t[32][33];
   const int b = blockIdx.z, c0 = blockIdx.y * 32, l0 = blockIdx.x * 32;
@@ -652,7 +652,7 @@ __global__ void ncl_to_cl_kernel(const float* __restrict__ x, const float* __res
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int l = l0 + i;
-    if (l < L) out.p[(long long)b * out.bstride + (long long)l * out.pitch + c0 + threadIdx.x] = __float2bfloat16(t[threadIdx.x][i]);
+    if (l < L) out.p[(long long)b * out.bstride + (long long)l * out.pitch + c0 + threadIdx.x] = f2h(t[threadIdx.x][i]);
   }
 }
 
@@ -715,7 +715,7 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, fl
 //   DDIM (mode 1): x <- (k0 x0 + k1 eps) + ks z          ddim_sample                        :296-300
 //   mode 2:        x <- x0                               ddim_sample's last pair (time_next < 0)  :289-291
 // Every product and sum is rounded separately (no FMA contraction): given the same eps the step reproduces the reference's
-// fp32 tensor algebra bit for bit.  Also writes the new x as bf16 into xin (channels-last view, the UNet's next input).
+// fp32 tensor algebra bit for bit.  Also writes the new x as h16 into xin (channels-last view, the UNet's next input).
 // In-kernel noise (noise == null, ks != 0): Philox4x32-10 keyed by the seed, counter = (global element index of the thread's first
 // element [clip_offset + b], absolute timestep t_abs): independent of how a trajectory is split into calls or a job over ranks.
 // grid (ceil(L/32), C/32, B), block (32, 8)
@@ -770,7 +770,7 @@ __global__ void ddpm_step_kernel(const float* __restrict__ eps, float* __restric
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int i = threadIdx.y + 8 * k, l = l0 + i;
-    if (l < L && xin.p) xin.p[(long long)b * xin.bstride + (long long)l * xin.pitch + c0 + threadIdx.x] = __float2bfloat16(t[i][threadIdx.x]);
+    if (l < L && xin.p) xin.p[(long long)b * xin.bstride + (long long)l * xin.pitch + c0 + threadIdx.x] = f2h(t[i][threadIdx.x]);
   }
 }
 

@@ -1,10 +1,10 @@
-// Element-wise / normalisation / attention kernels of the UNet on channels-last bf16 activations.
+// Element-wise / normalisation / attention kernels of the UNet on channels-last h16 activations.
 #pragma once
 #include "common.cuh"
 
-// channels-last bf16 view: element (b, l, c) at p[b*bstride + l*pitch + c]
+// channels-last h16 view: element (b, l, c) at p[b*bstride + l*pitch + c]
 struct ClView {
-  bf16* p;
+  h16* p;
   long long bstride;
   int pitch;
   int C;
@@ -12,7 +12,7 @@ struct ClView {
 
 // GroupNorm(8) + FiLM + SiLU (+ residual) (+ tanh)            unet.py:145-154, 183-192, 466-467
 struct GnApplyArgs {
-  ClView y;            // conv output (bf16)
+  ClView y;            // conv output (h16)
   const float2* stats; // [B][n_ntiles][C/32] partial (sum, sumsq)
   int n_ntiles;
   const float* gamma;  // [C]
@@ -34,7 +34,7 @@ int gn_apply_launch(const GnApplyArgs& a, int B, cudaStream_t st);
 int layernorm_cl_launch(ClView x, const float* g, ClView res, ClView out, int B, int L, cudaStream_t st);
 
 // LinearAttention core (between to_qkv and to_out)              unet.py:208-221
-// qkv [B][L][384] bf16 (q | k | v, each 4 heads x 32) -> out [B][L][128] bf16; ctx scratch [B][4][32][32] f32;
+// qkv [B][L][384] h16 (q | k | v, each 4 heads x 32) -> out [B][L][128] h16; ctx scratch [B][4][32][32] f32;
 // part scratch linattn_part_floats(B, L) f32; counters [4B] int32, zero before the first launch (the kernel re-zeroes them)
 int linattn_launch(ClView qkv, float* ctx, float* part, int* counters, ClView out, int B, int L, cudaStream_t st);
 size_t linattn_part_floats(int B, int L);
@@ -42,7 +42,7 @@ size_t linattn_part_floats(int B, int L);
 int fullattn_launch(ClView qkv, ClView out, int B, int L, cudaStream_t st);
 
 // layout conversion / DDPM
-// x NCL f32 [B][C][L] * scale[b] -> channels-last bf16 view (channel offset via out.p)
+// x NCL f32 [B][C][L] * scale[b] -> channels-last h16 view (channel offset via out.p)
 int ncl_to_cl_launch(const float* x, const float* inv_scale /*[B] or null*/, ClView out, int B, int C, int L, cudaStream_t st);
 // channels-last f32 [B][L][C] -> NCL f32
 int cl_to_ncl_f32_launch(const float* x, float* y, int B, int C, int L, cudaStream_t st);
@@ -60,7 +60,7 @@ struct DdpmTables {   // device pointers to the (1000,) fp32 buffers of Gaussian
 //   mode 0 (DDPM): x <- (k0 x0 + k1 x) + ks z;  mode 1 (DDIM): x <- (k0 x0 + k1 eps) + ks z;  mode 2: x <- x0.
 struct StepCoef { float a, b, k0, k1, ks; int mode; };
 // eps channels-last f32 [B][L][C]; x NCL f32 in place; noise NCL f32 (step slice) or null -> Philox(seed, t_abs, clip_offset + b);
-// also writes the new x as bf16 into xin (channels-last view, channel offset applied by caller; p null = skip).
+// also writes the new x as h16 into xin (channels-last view, channel offset applied by caller; p null = skip).
 int ddpm_step_launch(const float* eps, float* x, const float* noise, unsigned long long seed, int t_abs, unsigned long long clip_offset,
                      StepCoef cf, ClView xin, int B, int C, int L, cudaStream_t st);
 // x[0..n) <- N(0,1) (uniform = 0) or U[0,1) (uniform = 1) from Philox(seed, elem_offset + i)

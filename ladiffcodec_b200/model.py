@@ -38,6 +38,8 @@ def _on_device(fn):
     @functools.wraps(fn)
     def wrapper(self, *a, **k):
         owner = getattr(self, "_m", self)
+        if owner.device.type != "cuda":
+            raise _lib.LadiffError("no CUDA device: ladiffcodec_b200 has no CPU fallback")
         with torch.cuda.device(owner.device):
             return fn(self, *a, **k)
     return wrapper
@@ -258,6 +260,9 @@ class GaussianDiffusion1D(_Sub):
         torch.randn_like per step (the draws the reference makes, ddpm_loss.py:249); tensor [n,B,C,L] → consumed in loop order."""
         m = self._m
         B, C, L = x.shape
+        condition = _f32(condition, m.device)            # raw pointers below: fp32, contiguous [B,C,F]
+        if not (x.is_contiguous() and x.dtype == torch.float32 and x.device == m.device):
+            raise ValueError("x must be a contiguous fp32 tensor on the model's device (it is updated in place)")
         F = condition.shape[-1]
         ws = m._workspace(B, L * m.decoder.hop_length)
 

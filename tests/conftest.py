@@ -24,3 +24,19 @@ def load_golden(name):
 @pytest.fixture(scope="session")
 def golden_names():
     return ["A_3kbps", "B_3kbps", "A_1p5kbps"]
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Measured parity figures of the GPU tests -> gpurun_out/parity_report.json (the numbers DESIGN.md §2 quotes)."""
+    import json
+    try:
+        import parity_common as pc
+    except Exception:
+        return
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out) and pc.MEASURED:
+        path = os.path.join(out, "parity_report.json")
+        old = json.load(open(path)) if os.path.exists(path) else {}
+        old.update(pc.MEASURED)
+        with open(path, "w") as f:
+            json.dump(old, f, indent=1)

@@ -15,12 +15,41 @@ from ladiffcodec_b200.synthetic import make_state_dict, make_clips              
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
-# Stated tolerances.  fp32 SIMT codec stages: a few 1e-5 of the tensor's scale.
-# UNet: bf16 operands / bf16 activations with fp32 accumulation -> relative L2 per evaluation.
-TOL = dict(codec_abs=5e-5, upsample_abs=2e-5, unet_rel_l2=3e-2, unet_simt_vs_tc_rel_l2=3e-2, latent_rel_l2=2e-2,
-           wav_snr_db=25.0,
-           # long trajectories (N = 50 / 200 / 1000, other samplers): PROVISIONAL until measured on the B200 — see DESIGN.md §2
-           latent_rel_l2_long=0.2, wav_snr_db_long=15.0, latent_rel_l2_1000=0.5, wav_snr_db_1000=5.0, loss_abs=5e-3)
+# Stated tolerances: what was measured on the B200 (profiles/r2a/parity_report_*.json) times ~2.
+# fp32 SIMT codec stages: a few 1e-5 of the tensor's scale.  UNet: 16-bit tensor-core operands and stored activations with fp32
+# accumulation -> relative L2 per evaluation, and per trajectory at the step counts the benchmarks run.
+_TOL_F16 = dict(
+    codec_abs=5e-5, upsample_abs=2e-5,
+    unet_rel_l2=4e-3,               # one UNet evaluation vs the fp32 oracle: measured 1.4e-3 (config 2 full size), 1.3-1.6e-3 (goldens)
+    unet_simt_vs_tc_rel_l2=4e-3,    # tensor-core path vs SIMT check kernel on the same operands (summation order + rounding flips)
+    latent_rel_l2=2e-3, wav_snr_db=50.0,                 # 2-3 step trajectories (round-1 goldens, edge shapes, 5 s / 35 s utterances)
+    latent_rel_l2_long=2e-3, wav_snr_db_long=54.0,       # N = 50 / 200, first 20 steps from noise, infilling: measured <= 7.6e-4 / >= 60.5 dB
+    latent_rel_l2_1000=2.5e-3, wav_snr_db_1000=50.0,     # p_sample_loop, all 1000 steps: measured 1.2e-3 / 56.5 dB
+    latent_rel_l2_ddim=5e-2, wav_snr_db_ddim=26.0,       # ddim_sample 20 steps eta 0 / 10 steps eta .5: measured 2.5e-2 / 32.2 dB (no fresh
+                                                         # noise to wash errors out, 50-100 timestep jumps, x0 clamp flips at t ~ 999)
+    loss_abs=2e-3, pred_x0_rel_l2=1e-2)
+_TOL_BF16 = dict(_TOL_F16, unet_rel_l2=3e-2, unet_simt_vs_tc_rel_l2=3e-2, latent_rel_l2=2e-2, wav_snr_db=25.0, latent_rel_l2_long=1.5e-2,
+                 wav_snr_db_long=38.0, latent_rel_l2_1000=2e-2, wav_snr_db_1000=32.0, latent_rel_l2_ddim=0.3, wav_snr_db_ddim=12.0,
+                 loss_abs=1e-2, pred_x0_rel_l2=5e-2)
+
+
+class _Tol:
+    """Tolerances of the loaded build: fp16 (default) or the -DLADIFF_USE_BF16 A/B build."""
+    def _table(self):
+        from ladiffcodec_b200 import _lib
+        import torch as _t
+        return _TOL_F16 if _lib.act_dtype() == _t.float16 else _TOL_BF16
+
+    def __getitem__(self, k):
+        return self._table()[k]
+
+
+TOL = _Tol()
+MEASURED = {}          # test name -> figures; dumped to gpurun_out/parity_report.json by tests/conftest.py at session end
+
+
+def record(key, **vals):
+    MEASURED.setdefault(key, {}).update(vals)
 
 
 def ptr(t):

@@ -62,8 +62,10 @@ def test_unsupported_flags_fail_loudly(lib):
     with pytest.raises(NotImplementedError):
         DiffAudioTime()
     m = DiffAudioRep(**base)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(_lib.LadiffError):            # forward-only training loss exists now, but not without a GPU / loaded weights
         m(torch.zeros(1, 1, 640))
+    with pytest.raises(NotImplementedError):
+        m.diffusion.interpolate(None, None)
 
 
 def test_error_codes_and_messages(lib):

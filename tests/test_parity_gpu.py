@@ -87,6 +87,7 @@ def test_unet_forward_tcgen05(case):
     m.set_conv_impl(0)
     eps = m.diff_model(img.cuda(), tp.cuda(), fx["cond"].cuda()).cpu()
     assert torch.isfinite(eps).all()
+    pc.record("unet_eval_" + case["name"], rel_l2_vs_oracle=pc.rel_l2(eps, eps_o), rel_l2_vs_reference=pc.rel_l2(eps[:, ::4, ::4], fx["eps_sub"]))
     assert pc.rel_l2(eps, eps_o) <= pc.TOL["unet_rel_l2"]
     assert pc.rel_l2(eps[:, ::4, ::4], fx["eps_sub"]) <= pc.TOL["unet_rel_l2"]        # vs the real reference
     # the tcgen05 kernel and the SIMT check kernel consume identical packed operands
@@ -95,6 +96,7 @@ def test_unet_forward_tcgen05(case):
     m.set_conv_impl(2)          # tcgen05 with one activation tile per tap (no row-shifted descriptors)
     eps_u = m.diff_model(img.cuda(), tp.cuda(), fx["cond"].cuda()).cpu()
     m.set_conv_impl(0)
+    pc.record("unet_eval_" + case["name"], simt_vs_tc=pc.rel_l2(eps, eps_s), per_tap_vs_shared=pc.rel_l2(eps, eps_u))
     assert pc.rel_l2(eps, eps_s) <= pc.TOL["unet_simt_vs_tc_rel_l2"]
     assert pc.rel_l2(eps, eps_u) <= pc.TOL["unet_simt_vs_tc_rel_l2"]
     # per-sample time indices: a batch with mixed t equals the per-t evaluations
@@ -111,6 +113,8 @@ def test_ddpm_trajectory(case):
     with torch.no_grad():
         lat_o = O.halfway_sampling(img.clone(), fx["n_steps"], fx["cond"], case["sdm"], noise, pc.unet_kwargs(args))
     lat = m.diffusion.halfway_sampling(img=img.cuda(), t=fx["n_steps"], condition=fx["cond"].cuda(), noise=noise.cuda()).cpu()
+    pc.record("short_trajectory_" + case["name"], n_steps=fx["n_steps"], latent_rel_l2_vs_oracle=pc.rel_l2(lat, lat_o),
+              latent_rel_l2_vs_reference=pc.rel_l2(lat[:, ::4, ::4], fx["latent_sub"]))
     assert pc.rel_l2(lat, lat_o) <= pc.TOL["latent_rel_l2"]
     assert pc.rel_l2(lat[:, ::4, ::4], fx["latent_sub"]) <= pc.TOL["latent_rel_l2"]
     assert lat.abs().max().item() <= 1.0 + 1e-5           # last step is a clamp to [-1,1] scaled by coef1+coef2 = 1
@@ -165,6 +169,7 @@ def test_synthesize_matches_reference_waveform(case):
     from ladiffcodec_b200.sample import synthesize
     m, c, fx = case["m"], case["c"], case["fx"]
     out, lat = synthesize(m, c, case["wav"].cuda(), n_steps=fx["n_steps"], noise=case["noise"], return_latent=True)
+    pc.record("short_trajectory_" + case["name"], wav_snr_db_vs_reference=pc.snr_db(out, fx["wav_hat"]))
     assert pc.snr_db(out, fx["wav_hat"]) >= pc.TOL["wav_snr_db"]
     assert pc.rel_l2(lat.cpu()[:, ::4, ::4], fx["latent_sub"]) <= pc.TOL["latent_rel_l2"]
     assert out.abs().reshape(fx["B"], -1).max(1).values.sub(1.0).abs().max().item() < 1e-5   # sample.py:134
@@ -244,33 +249,35 @@ def test_strict_loader_errors():
 
 
 def test_tc_conv_operator_shapes():
-    """tcgen05 conv operator vs torch on bf16-rounded operands: ragged L (not a tile multiple), k in {1,3,7}, Cin up to 2048,
-    minimum size, several short clips packed per tile; fp32 (direct epilogue) and bf16 (smem-staged TMA-store epilogue)
+    """tcgen05 conv operator vs torch on 16-bit-rounded operands: ragged L (not a tile multiple), k in {1,3,7}, Cin up to 2048,
+    minimum size, several short clips packed per tile; fp32 (direct epilogue) and 16-bit (smem-staged TMA-store epilogue)
     outputs; tap-shared (impl 0) and per-tap (impl 2) activation tiles; the positions-on-M kernel with one CTA (impl 3) and a cta_group::2 CTA pair (impl 4) per tile."""
     import torch.nn.functional as F
     from ladiffcodec_b200 import _lib
     lib = _lib.get_lib()
+    h16 = _lib.act_dtype()                       # torch.float16 (default build) or torch.bfloat16
+    ulp = 2.0 ** -11 if h16 == torch.float16 else 2.0 ** -8
     P = ctypes.c_void_p
     for (B, L, Cin, Cout, k) in [(2, 75, 128, 128, 1), (1, 300, 1024, 1024, 3), (2, 640, 256, 256, 7), (5, 37, 2048, 1024, 3),
                                  (1, 4800, 512, 256, 3), (2, 16, 64, 128, 3), (1, 1201, 256, 384, 1), (7, 75, 1024, 1024, 3),
                                  (3, 150, 512, 512, 3)]:
         g = torch.Generator().manual_seed(L + Cin)
-        x = torch.randn(B, L, Cin, generator=g).to(torch.bfloat16)
+        x = torch.randn(B, L, Cin, generator=g).to(h16)
         w = torch.randn(Cout, Cin, k, generator=g) * (Cin * k) ** -0.5
         bias = torch.randn(Cout, generator=g) * 0.1
-        ref = F.conv1d(x.float().permute(0, 2, 1), w.to(torch.bfloat16).float(), bias, padding=(k - 1) // 2).permute(0, 2, 1)
+        ref = F.conv1d(x.float().permute(0, 2, 1), w.to(h16).float(), bias, padding=(k - 1) // 2).permute(0, 2, 1)
         s_ref = ref.reshape(B, L, Cout // 32, 32).sum(dim=(1, 3))
         xd, wd, bd = x.cuda(), w.cuda(), bias.cuda()
         for impl in (0, 2, 3, 4, 5):
             if impl == 5 and (k != 1 or L <= 120):      # two-CTAs-per-SM shape: small-K single-clip tiles only
                 continue
             for f32 in (1, 0):
-                y = torch.full((B, L, Cout), float("nan"), device="cuda", dtype=torch.float32 if f32 else torch.bfloat16)
+                y = torch.full((B, L, Cout), float("nan"), device="cuda", dtype=torch.float32 if f32 else h16)
                 st = torch.zeros(B, Cout // 32, 2, device="cuda")
                 rc = lib.ladiff_op_conv1d_cl(P(xd.data_ptr()), P(wd.data_ptr()), P(bd.data_ptr()), B, L, Cin, Cout, k, P(y.data_ptr()),
                                              f32, impl, P(st.data_ptr()))
                 assert rc == 0, lib.ladiff_last_error()
-                tol = 2e-4 if f32 else 2e-4 + ref.abs().max().item() * 2 ** -8       # bf16 output rounding
+                tol = 2e-4 if f32 else 2e-4 + ref.abs().max().item() * ulp          # 16-bit output rounding
                 assert (y.float().cpu() - ref).abs().max().item() < tol, (B, L, Cin, Cout, k, impl, f32)
                 assert (st[:, :, 0].cpu() - s_ref).abs().max().item() < 1e-2 * max(1.0, s_ref.abs().max().item())
 
@@ -303,7 +310,8 @@ def test_full_size_properties_config2():
     m.set_conv_impl(1)
     e_simt = m.diff_model(img, tt, cond)
     m.set_conv_impl(0)
-    assert pc.rel_l2(e_tc, e_simt) <= pc.TOL["unet_simt_vs_tc_rel_l2"]     # bf16 activations: rounding flips, not a bias
+    pc.record("config2_full_size", simt_vs_tc=pc.rel_l2(e_tc, e_simt))
+    assert pc.rel_l2(e_tc, e_simt) <= pc.TOL["unet_simt_vs_tc_rel_l2"]     # 16-bit activations: rounding flips, not a bias
     # whole path: permuting the clips permutes the outputs; a sub-batch reproduces its clips
     out = synthesize(m, c, wav.cuda(), n_steps=n_steps, noise=noise)
     assert out.shape == (B, 1, T) and bool(torch.isfinite(out).all())
@@ -341,6 +349,7 @@ def test_long_utterance_against_oracle():
         ref = O.synthesize(wav, sdm, sdc, n_steps=n_steps, noise=noise, cond_bandwidth=args.cond_bandwidth,
                            enc_ratios=args.enc_ratios, upsampling_ratios=args.upsampling_ratios, diff_dims=args.diff_dims,
                            unet_scale_cond=args.unet_scale_cond, fast_lstm=True, stages=stages)
+    pc.record("long_utterance_5s", latent_rel_l2=pc.rel_l2(lat, stages["latent"]), wav_snr_db=pc.snr_db(out, ref))
     assert pc.rel_l2(lat, stages["latent"]) <= pc.TOL["latent_rel_l2"]
     assert pc.snr_db(out, ref) >= pc.TOL["wav_snr_db"]
     del m, c
@@ -380,6 +389,7 @@ def test_edge_shapes_against_oracle(B, T, layout):
                            enc_ratios=args.enc_ratios, upsampling_ratios=args.upsampling_ratios, diff_dims=args.diff_dims,
                            unet_scale_cond=args.unet_scale_cond, fast_lstm=True, stages=stages)
     assert out.shape == (B, 1, T)
+    pc.record(f"edge_B{B}_T{T}_{layout}", latent_rel_l2=pc.rel_l2(lat, stages["latent"]), wav_snr_db=pc.snr_db(out, ref))
     assert pc.rel_l2(lat, stages["latent"]) <= pc.TOL["latent_rel_l2"]
     assert pc.snr_db(out, ref) >= pc.TOL["wav_snr_db"]
     del m, c

@@ -4,9 +4,6 @@
 
 Every measured figure is also appended to gpurun_out/parity_report.json (when that directory exists) — the per-step error-growth
 curves committed under profiles/ come from there.  Tolerances: tests/parity_common.py:TOL (stated in DESIGN.md §2)."""
-import json
-import os
-
 import pytest
 import torch
 
@@ -14,19 +11,7 @@ import parity_common as pc
 from oracle import ladiff_oracle as O
 
 pytestmark = pytest.mark.gpu
-REPORT = {}
-
-
-@pytest.fixture(scope="module", autouse=True)
-def _dump_report():
-    yield
-    out = os.path.join(pc.ROOT, "gpurun_out")
-    if os.path.isdir(out) and REPORT:
-        path = os.path.join(out, "parity_report.json")
-        old = json.load(open(path)) if os.path.exists(path) else {}
-        old.update(REPORT)
-        with open(path, "w") as f:
-            json.dump(old, f, indent=1)
+REPORT = pc.MEASURED
 
 
 def _models(args, sdm, sdc):
@@ -121,7 +106,7 @@ def test_sample_full_1000_steps():
     waveform (the oracle is pinned to the same chain segment-wise on CPU; 1000 CPU steps do not fit a test)."""
     fx, args, sdm, sdc, wav, L, d = pc.r2_setup("A_full1000")
     m, c = _models(args, sdm, sdc)
-    cond = fx["cond"].cuda()
+    cond = fx["cond"].cuda().contiguous()
     m.diffusion.seq_length = L
     lat = m.diffusion.sample(batch_size=fx["B"], condition=cond, noise=d["noise"], init=d["init"]).cpu()
     # intermediate states: run the chain in the same three pieces the fixture stores
@@ -138,10 +123,12 @@ def test_sample_full_1000_steps():
         x = m.diffusion._steps(x.clone(), cond, cur, n, nz, 0)
         cur -= n
         curve.append(pc.rel_l2(x.cpu()[:, ::8, ::8], fx["trace_sub"][j]))
-    assert torch.equal(x.cpu(), lat)                       # chunked == one call
+    lat2 = m.diffusion.sample(batch_size=fx["B"], condition=cond, noise=d["noise"], init=d["init"]).cpu()
+    rep["chunked_equals_one_call"] = [bool(torch.equal(x.cpu(), lat)), bool(torch.equal(x.cpu(), lat2)), bool(torch.equal(lat, lat2))]
     rep["rel_l2_every_20_steps"] = curve
     REPORT["sample_full1000"] = rep
     print({k: v for k, v in rep.items() if k != "rel_l2_every_20_steps"}, "max over chain", max(curve))
+    assert all(rep["chunked_equals_one_call"]), rep["chunked_equals_one_call"]     # chunked == one call, run to run
     assert rep["latent_rel_l2_vs_reference"] <= pc.TOL["latent_rel_l2_1000"]
     assert rep["wav_snr_db_vs_reference"] >= pc.TOL["wav_snr_db_1000"]
     del m, c
@@ -164,8 +151,9 @@ def test_ddim_sample(name):
                wav_snr_db_vs_reference=pc.snr_db(w, fx["wav_hat"]))
     REPORT["ddim_" + name] = rep
     print(name, rep)
-    assert rep["latent_rel_l2_vs_oracle"] <= pc.TOL["latent_rel_l2_long"]
-    assert rep["latent_rel_l2_vs_reference"] <= pc.TOL["latent_rel_l2_long"]
+    assert rep["latent_rel_l2_vs_oracle"] <= pc.TOL["latent_rel_l2_ddim"]
+    assert rep["latent_rel_l2_vs_reference"] <= pc.TOL["latent_rel_l2_ddim"]
+    assert rep["wav_snr_db_vs_reference"] >= pc.TOL["wav_snr_db_ddim"]
     # is_ddim_sampling routes sample() to ddim_sample like the reference (ddpm_loss.py:307-308)
     m.diffusion.is_ddim_sampling, m.diffusion.seq_length = True, L
     lat2 = m.diffusion.sample(batch_size=fx["B"], condition=cond, noise=d["noise"], init=d["init"]).cpu()
@@ -213,14 +201,17 @@ def test_training_loss_forward():
     t = torch.tensor(fx["case"]["t"], dtype=torch.long)
     m.diffusion.seq_length = L
     loss, pred, xt, t_out = m.diffusion(img.cuda(), cond, t=t.cuda(), noise=d["noise"])
-    assert torch.equal(xt.cpu(), fx["x_t"])                                         # q_sample: bit-exact
+    with torch.no_grad():
+        xt_o = O.q_sample(img, t, d["noise"], sdm)
+    assert torch.equal(xt.cpu(), xt_o)                                              # q_sample: bit-exact against the same-box oracle
+    assert torch.allclose(xt.cpu(), fx["x_t"], atol=2e-6, rtol=0)                   # … and the reference's, up to the CPU conv's ulps in img
     assert torch.equal(t_out.cpu(), t)
     rep = dict(loss=float(loss), loss_ref=float(fx["loss"]), pred_x_start_rel_l2=pc.rel_l2(pred, fx["pred_x_start"]))
     REPORT["p_losses"] = rep
     print(rep)
     assert abs(rep["loss"] - rep["loss_ref"]) <= pc.TOL["loss_abs"]
-    assert rep["pred_x_start_rel_l2"] <= pc.TOL["unet_rel_l2"]
-    assert torch.equal(m.diffusion.q_sample(img.cuda(), t.cuda(), d["noise"]).cpu(), fx["x_t"])
+    assert rep["pred_x_start_rel_l2"] <= pc.TOL["pred_x0_rel_l2"]
+    assert torch.equal(m.diffusion.q_sample(img.cuda(), t.cuda(), d["noise"]).cpu(), xt_o)
     # DiffAudioRep.forward against the oracle's composition of the same stages
     with torch.no_grad():
         x_rep = O.seanet_encoder(wav, sdm, list(args.enc_ratios)) / 18.0
@@ -231,7 +222,10 @@ def test_training_loss_forward():
     assert scale == 18.0 and qtz is None
     assert (x_rep_g.cpu() - x_rep).abs().max().item() <= pc.TOL["codec_abs"]
     assert abs(float(losses["diff_loss"]) - float(lo)) <= pc.TOL["loss_abs"]
-    assert pc.rel_l2(x_hat, xh_o) <= 2 * pc.TOL["unet_rel_l2"]
+    REPORT["p_losses"].update(diff_loss=float(losses["diff_loss"]), diff_loss_oracle=float(lo), neg_loss=float(losses["neg_loss"]),
+                              neg_loss_oracle=float(neg_o), x_hat_rel_l2=pc.rel_l2(x_hat, xh_o))
+    print(REPORT["p_losses"])
+    assert pc.rel_l2(x_hat, xh_o) <= 4 * pc.TOL["pred_x0_rel_l2"]
     assert abs(float(losses["neg_loss"]) - float(neg_o)) <= 0.3                     # dB
     # the codec's own forward (quantising model): eval-mode losses
     lc, xh_c = c(wav.cuda())
