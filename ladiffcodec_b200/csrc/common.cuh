@@ -191,9 +191,9 @@ struct TcConvDesc {
 struct TcConvParams {
   CUtensorMap tmW;   // weights  [Cout][Ktot] h16 row-major, box {64, 128}, SWIZZLE_128B
   CUtensorMap tmX;   // activations view [B][Lv][Cv] h16, box {64, BOXROWS, 1}, SWIZZLE_128B, OOB -> 0
-  CUtensorMap tmY;   // output {Cc, phases, rows, B} h16, box {128, 1, CR, 1}
+  CUtensorMap tmY;   // output {Cc, phases, rows, B} h16, box {32, 1, CR, 1} (one epilogue warp's channel slice)
   CUtensorMap tmYr;  // same, box rows = NT % CR (last chunk of a single-clip tile)
-  CUtensorMap tmY2;  // second output (channels m >= split_m), box {128, 1, CR, 1}
+  CUtensorMap tmY2;  // second output (channels m >= split_m), box {32, 1, CR, 1}
   CUtensorMap tmY2r;
   TcGroup grp[TC_MAX_GRP];
   int ngrp;

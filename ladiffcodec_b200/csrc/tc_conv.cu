@@ -294,9 +294,9 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
     // whose running index cc has (cc & 1) == wg, with its own pair of staging buffers, named barrier and TMA-store issuer
     const int q = warp & 3;
     const int wg = (warp - 2) >> 2;
-    const bool store_warp = ((warp - 2) & 3) == 0;   // its elected lane issues this group's TMA stores; bulk-group waits are warp-wide
     const int Cc = p.up_cout ? p.up_cout : (p.split_m ? p.split_m : p.Cout);
-    const uint32_t stage_wg = stage0 + (uint32_t)(wg * 2) * (uint32_t)p.CR * 256u;
+    // this warp's two staging buffers, [CR rows][32 channels] each; its elected lane issues the stores, bulk-group waits are warp-wide
+    const uint32_t stage_w = stage0 + (uint32_t)((wg * 4 + q) * 2) * (uint32_t)p.CR * 64u;
     int tl = 0, cc = 0, kk = 0;
     // bias of the NEXT tile is requested one tile ahead (an exposed L2 round trip per tile otherwise)
     float bias_next = (p.bias && (int)blockIdx.x < total_tiles) ? __ldg(p.bias + decode_tile(p, blockIdx.x).m0 + q * 32 + lane) : 0.f;
@@ -338,9 +338,9 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
           uint32_t stg = 0;
           const long long te0 = prof ? clock64() : 0;
           if (!p.direct) {
-            if (store_warp) bulk_wait_read_1();  // the store this group issued two chunks ago has finished reading its buffer
-            epi_bar(wg);
-            stg = stage_wg + (uint32_t)(kk & 1) * (uint32_t)p.CR * 256u + (uint32_t)(q * 32 + lane) * 2u;
+            bulk_wait_read_1();                  // the store this warp issued two chunks ago has finished reading its buffer
+            __syncwarp();
+            stg = stage_w + (uint32_t)(kk & 1) * (uint32_t)p.CR * 64u + (uint32_t)lane * 2u;
           }
           const long long te1 = prof ? clock64() : 0;
           const uint32_t tcol = tlane + (uint32_t)(j * p.NT + r0);
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
                   const float v = __uint_as_float(r[i]) + bias;
                   s1 += v; s2 += v * v;
                   const unsigned short hv = h16_bits(f2h(v));
-                  asm volatile("st.shared.u16 [%0], %1;" ::"r"(stg + (uint32_t)(c0 + i) * 256u), "h"(hv) : "memory");
+                  asm volatile("st.shared.u16 [%0], %1;" ::"r"(stg + (uint32_t)(c0 + i) * 64u), "h"(hv) : "memory");
                 }
               } else {
 #pragma unroll
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
                   const float v = __uint_as_float(r[i]) + bias;
                   if (r0 + c0 + i < vr) { s1 += v; s2 += v * v; }
                   const unsigned short hv = h16_bits(f2h(v));
-                  asm volatile("st.shared.u16 [%0], %1;" ::"r"(stg + (uint32_t)(c0 + i) * 256u), "h"(hv) : "memory");
+                  asm volatile("st.shared.u16 [%0], %1;" ::"r"(stg + (uint32_t)(c0 + i) * 64u), "h"(hv) : "memory");
                 }
               }
             } else {
@@ -398,13 +398,14 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
           const long long te2 = prof ? clock64() : 0;
           if (!p.direct) {
             fence_async_smem();
-            epi_bar(wg);
-            if (store_warp && !no_st && elect_one()) {
-              const uint32_t src = stage_wg + (uint32_t)(kk & 1) * (uint32_t)p.CR * 256u;
-              if (second) tma_store_4d(nrows == p.CR ? &p.tmY2 : &p.tmY2r, src, tc.m0 - p.split_m, 0, tc.l0 + r0, b);
-              else tma_store_4d(nrows == p.CR ? &p.tmY : &p.tmYr, src, tc.m0 % Cc, tc.m0 / Cc, tc.l0 + r0, b);
+            __syncwarp();
+            if (!no_st && elect_one()) {
+              const uint32_t src = stage_w + (uint32_t)(kk & 1) * (uint32_t)p.CR * 64u;
+              if (second) tma_store_4d(nrows == p.CR ? &p.tmY2 : &p.tmY2r, src, tc.m0 - p.split_m + q * 32, 0, tc.l0 + r0, b);
+              else tma_store_4d(nrows == p.CR ? &p.tmY : &p.tmYr, src, tc.m0 % Cc + q * 32, tc.m0 / Cc, tc.l0 + r0, b);
               bulk_commit();
             }
+            __syncwarp();
             ++kk;
           }
           if (prof) { const long long te3 = clock64(); w_e1 += te1 - te0; w_e2 += te2 - te1; w_e3 += te3 - te2; }
@@ -425,7 +426,7 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
     }
     // the staging buffers must outlive the stores' shared-memory reads; their global writes are covered by grid completion
     // (and by griddepcontrol.wait in the dependent kernel), so the CTA does not wait for them
-    if (store_warp) bulk_wait_read_0();
+    bulk_wait_read_0();
     if (prof && threadIdx.x == 64) { p.prof[blockIdx.x * 8 + 3] = (unsigned long long)w_acc; p.prof[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - t_begin);
       p.prof[blockIdx.x * 8 + 5] = (unsigned long long)w_e1; p.prof[blockIdx.x * 8 + 6] = (unsigned long long)w_e2; p.prof[blockIdx.x * 8 + 7] = (unsigned long long)w_e3; }
   }
@@ -819,7 +820,7 @@ int make_tmap_y(CUtensorMap* tm, const h16* out, int Cc, int phases, int rows, i
   LADIFF_REQUIRE(enc != nullptr, LADIFF_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[4] = {(cuuint64_t)Cc, (cuuint64_t)phases, (cuuint64_t)rows, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)pitch * 2 * phases, (cuuint64_t)bstride * 2};
-  cuuint32_t box[4] = {TC_BM, 1, (cuuint32_t)boxrows, 1};
+  cuuint32_t box[4] = {32, 1, (cuuint32_t)boxrows, 1};      // one epilogue warp's slice: 32 channels x boxrows rows
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, TC_TMAP_DTYPE, 4, (void*)out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
