@@ -219,6 +219,11 @@ int32_t ladiff_normalize_clips(float* x, int32_t B, int64_t n, int32_t mode, voi
 int32_t ladiff_op_conv1d_cl(const void* x_h16, const float* w, const float* bias, int32_t B, int32_t L,
                             int32_t Cin, int32_t Cout, int32_t k, void* y, int32_t y_f32, int32_t impl,
                             float* gn_stats /* [B,Cout/32,2] or NULL */);
+/* Operator-level timing of the same conv (kernel tuning, profiles/conv_sweep.py): one plan, `warm` untimed + `iters` timed launches
+ * between two CUDA events; ms_out[0] = mean ms per launch; want_* override the tile shape (0 = cost model); label receives the plan. */
+int32_t ladiff_op_conv1d_bench(const void* x_h16, const float* w, const float* bias, int32_t B, int32_t L, int32_t Cin, int32_t Cout,
+                               int32_t k, int32_t want_nt, int32_t want_nclip, int32_t want_two, int32_t want_t, int32_t stats_on,
+                               int32_t warm, int32_t iters, float* ms_out, char* label, int32_t label_cap);
 /* Selects the conv implementation used inside the UNet: 0 = tcgen05 (default), 1 = SIMT check kernel. */
 int32_t ladiff_set_conv_impl(LadiffHandle* h, int32_t impl);
 /* Profiling for bench.py's roofline: when on, CUDA events are recorded on the launching stream around every

@@ -63,6 +63,8 @@ SIGNATURES = {
     "ladiff_synthesize_codes": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_u64, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "ladiff_normalize_clips": (c_i32, [c_vp, c_i32, c_i64, c_i32, c_vp]),
     "ladiff_op_conv1d_cl": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp]),
+    "ladiff_op_conv1d_bench": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32,
+                                       ctypes.POINTER(ctypes.c_float), ctypes.c_char_p, c_i32]),
     "ladiff_set_conv_impl": (c_i32, [c_vp, c_i32]),
     "ladiff_take_launch_count": (c_i64, [c_vp]),
     "ladiff_set_profiling": (c_i32, [c_vp, c_i32]),

@@ -971,7 +971,9 @@ int tc_conv_plan(const TcConvDesc& d, TcConvParams* pp, TcRefView* rv) {
       a_cap = n > a_cap ? n : a_cap;
     }
   p.a_cap = a_cap;
-  (void)halo2;
+  // The tiling is decided on the conv's own halo (K - 1 rows), not on the halo one shared-memory tile happens to need: the
+  // tap-shared and the per-tap (check) variants of the same conv must cut the clips identically (same GroupNorm partials).
+  if (halo2 < tile_halo) halo2 = tile_halo;
   p.MT = d.CoutV / TC_BM;
   p.B = d.B; p.Lout = Lout; p.Cout = d.CoutV; p.bias = d.bias; p.stats = d.stats;
   p.up_cout = d.kind == TC_KIND_UP ? d.CoutV / 2 : 0;
@@ -1016,7 +1018,7 @@ int tc_conv_plan(const TcConvDesc& d, TcConvParams* pp, TcRefView* rv) {
     }
     return 0;
   }
-  pick_tiling(Lout, d.B, p.MT, tile_halo, d.want_nt, d.want_nclip, &p.NT, &p.NCLIP, &p.n_ptiles);
+  pick_tiling(Lout, d.B, p.MT, halo2, d.want_nt, d.want_nclip, &p.NT, &p.NCLIP, &p.n_ptiles);
   p.NMMA = p.NT * p.NCLIP;
   p.n_ntiles = p.NCLIP == 1 ? d.B * p.n_ptiles : cdiv(d.B, p.NCLIP);
   p.BOXROWS = p.NCLIP == 1 ? p.NT + (tile_halo ? 8 : 0) : p.NT;

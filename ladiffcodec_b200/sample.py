@@ -231,10 +231,11 @@ def _normalize(lib, x, mode, device):
     return x
 
 
-def synthesis(inp_args, noise_device=None):
+def synthesis(inp_args, noise_device=None, noise_seed=None):
     """sample.py:50-136, file for file.  The reference draws its per-step noise with torch.randn_like on the tensor's device;
     `noise_device="cpu"` (or LADIFF_NOISE_DEVICE=cpu) draws the same numbers from the CPU generator instead and copies them over,
-    which reproduces a CPU run of the reference under the same torch.manual_seed."""
+    which reproduces a CPU run of the reference under the same generator state.  `noise_seed`: torch.manual_seed(noise_seed) right
+    after each file is loaded, so a file's output depends neither on the order of the files nor on anything drawn before."""
     import torchaudio
     noise_device = noise_device or os.environ.get("LADIFF_NOISE_DEVICE", "cuda")
     model, model_for_cond = build_models(inp_args)
@@ -248,6 +249,8 @@ def synthesis(inp_args, noise_device=None):
             if output_folder and not os.path.exists(output_folder):
                 os.makedirs(output_folder)
             wav, sr = _load_wav(wav_file)
+            if noise_seed is not None:
+                torch.manual_seed(noise_seed)
             wav = torchaudio.functional.resample(wav, orig_freq=sr, new_freq=16000)
             wav = wav.unsqueeze(1).to(torch.float).to(device)
             length = wav.shape[-1] // 640 * 640

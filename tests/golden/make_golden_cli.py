@@ -5,7 +5,8 @@ midway_t = 100 — and commits what it saves.  tests/test_cli_gpu.py runs `ladif
 Run in the build container only:   python tests/golden/make_golden_cli.py
 Shims: the sys.modules stubs of oracle/ref_import.py, and torchaudio.load / torchaudio.save (TorchCodec is not
 in this image) replaced by scipy.io.wavfile equivalents: load → (float32 [1,T] in [-1,1), sr) for 16-bit PCM; save captured in
-memory.  One synthesis() call per file with torch.manual_seed(SEED) before it, so a file's noise does not depend on glob order.
+memory.  The load shim also seeds the global generator (torch.manual_seed(SEED) per file, right where the loop starts on a
+file), so a file's noise depends neither on glob order nor on the random initialisation of the modules the script builds first.
 """
 import argparse
 import os
@@ -54,6 +55,9 @@ def main():
     def load(path):
         sr, data = wavfile.read(path)
         assert data.dtype == np.int16
+        # synthesis() builds its models (random init = generator draws) before the file loop: seed HERE, at the first thing
+        # the loop does per file, so that the only draws after the seed are halfway_sampling's randn_like per step
+        torch.manual_seed(SEED_NOISE)
         return torch.from_numpy(data.astype(np.float32) / 32768.0)[None], sr
 
     def save(path, wav, sr):
@@ -73,7 +77,6 @@ def main():
         shutil.copy(os.path.join(cli, "in", rel), os.path.join(one, rel))
         ns = argparse.Namespace(**{**vars(args), "input_dir": one, "output_dir": os.path.join(tmp, "out")})
         saved.clear()
-        torch.manual_seed(SEED_NOISE)
         ref_sample.synthesis(ns)
         assert len(saved) == 1, list(saved)
         (path, (wav, sr)), = saved.items()

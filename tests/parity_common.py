@@ -22,7 +22,7 @@ _TOL_F16 = dict(
     codec_abs=5e-5, upsample_abs=2e-5,
     unet_rel_l2=4e-3,               # one UNet evaluation vs the fp32 oracle: measured 1.4e-3 (config 2 full size), 1.3-1.6e-3 (goldens)
     unet_simt_vs_tc_rel_l2=4e-3,    # tensor-core path vs SIMT check kernel on the same operands (summation order + rounding flips)
-    latent_rel_l2=2e-3, wav_snr_db=50.0,                 # 2-3 step trajectories (round-1 goldens, edge shapes, 5 s / 35 s utterances)
+    latent_rel_l2=3e-4, wav_snr_db=70.0,                 # 2-3 step trajectories (round-1 goldens, edge shapes, 5 s utterance): measured <= 8.3e-5 / >= 78.7 dB
     latent_rel_l2_long=2e-3, wav_snr_db_long=54.0,       # N = 50 / 200, first 20 steps from noise, infilling: measured <= 7.6e-4 / >= 60.5 dB
     latent_rel_l2_1000=2.5e-3, wav_snr_db_1000=50.0,     # p_sample_loop, all 1000 steps: measured 1.2e-3 / 56.5 dB
     latent_rel_l2_ddim=5e-2, wav_snr_db_ddim=26.0,       # ddim_sample 20 steps eta 0 / 10 steps eta .5: measured 2.5e-2 / 32.2 dB (no fresh

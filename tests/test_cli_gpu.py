@@ -35,8 +35,7 @@ def test_synthesis_on_wav_files_matches_the_reference_script(tmp_path):
         shutil.copy(os.path.join(CLI, "in", rel), one / rel)
         out_dir = str(tmp_path / "out")
         ns = argparse.Namespace(**{**vars(args), "input_dir": str(one), "output_dir": out_dir})
-        torch.manual_seed(fx["seeds"]["noise"])
-        synthesis(ns, noise_device="cpu")                     # the reference ran on CPU: same generator, same draw order
+        synthesis(ns, noise_device="cpu", noise_seed=fx["seeds"]["noise"])    # the reference ran on CPU: same generator, same draw order
         path = out_dir + "/" + rel                           # sample.py:75-76: output_dir + path below input_dir
         assert os.path.exists(path), path
         sr, data = wavfile.read(path)

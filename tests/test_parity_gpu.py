@@ -410,3 +410,30 @@ def test_pipeline_two_batches_in_flight(case):
     for i, (o, r) in enumerate(zip(outs, ref)):
         assert (o.device.type == "cuda") == (i % 2 == 0)
         assert pc.snr_db(o, r) > 55.0, i
+
+
+@pytest.mark.parametrize("L", [240, 480, 960, 1920])
+def test_unet_lengths_around_the_multi_clip_tile_boundary(L):
+    """Latent lengths whose resolution levels straddle the 120-row limit of the several-clips-per-tile mode (a level with exactly
+    120 rows used to make the tap-shared and the per-tap tilings of one conv disagree): one UNet evaluation against the oracle, and
+    the SIMT / per-tap check variants on the same plan."""
+    from ladiffcodec_b200.config import readme_args
+    args = readme_args()
+    sdm = pc.make_state_dict(seed=11, **pc.ladiff_model_kwargs(args))
+    sdc = pc.make_state_dict(seed=12, **pc.cond_model_kwargs(args))
+    m, c = pc.cuda_models(args, sdm, sdc)
+    F = L // 40                      # upsampling ratios 5, 4, 2; level j of the UNet has L / 2^j rows -> one of them has exactly 120
+    g = torch.Generator().manual_seed(L)
+    cond = torch.randn(2, 128, F, generator=g) * 0.3
+    x = torch.randn(2, 128, L, generator=g)
+    t = torch.tensor([5, 700])
+    with torch.no_grad():
+        eo = O.unet_forward(x, t, cond, sdm, **pc.unet_kwargs(args))
+    e = m.diff_model(x.cuda(), t.cuda(), cond.cuda()).cpu()
+    assert pc.rel_l2(e, eo) <= pc.TOL["unet_rel_l2"]
+    for impl in (1, 2):
+        m.set_conv_impl(impl)
+        assert pc.rel_l2(m.diff_model(x.cuda(), t.cuda(), cond.cuda()).cpu(), e) <= pc.TOL["unet_simt_vs_tc_rel_l2"]
+    m.set_conv_impl(0)
+    del m, c
+    torch.cuda.empty_cache()
