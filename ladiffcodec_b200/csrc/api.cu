@@ -603,7 +603,30 @@ int conv_out_len(int Lin, int K, int stride) {   // conv.py:56-63 with padding_t
   return (Lin - K + pt + stride - 1) / stride + 1;
 }
 
+// LADIFF_CODEC_PROF=1: every codec launch is bracketed by CUDA events on its stream and printed (serialises the stage; debugging aid)
+struct CodecProf {
+  cudaStream_t st; cudaEvent_t e0 = nullptr, e1 = nullptr; char label[160]; bool on;
+  CodecProf(cudaStream_t s, const char* fmt, int a, int b, int c, int d, int e) : st(s) {
+    static const bool env = getenv("LADIFF_CODEC_PROF") != nullptr;
+    on = env;
+    if (!on) return;
+    snprintf(label, sizeof(label), fmt, a, b, c, d, e);
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+  }
+  ~CodecProf() {
+    if (!on) return;
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    fprintf(stderr, "[codec_prof] %8.1f us  %s\n", ms * 1e3f, label);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
+};
+
 int run_conv(H* h, const ConvW& cw, const float* x, int Lin, float* y, int act_in, const float* res, int B, cudaStream_t st) {
+  CodecProf cp(st, "conv Cin=%d Cout=%d K=%d stride=%d Lin=%d", cw.Cin, cw.Cout, cw.K, cw.stride, Lin);
   ConvF32Args a;
   memset(&a, 0, sizeof(a));
   a.x = x; a.Cin = cw.Cin; a.Lin = Lin; a.w = cw.w; a.wt = cw.wt; a.bias = cw.bias; a.y = y; a.CoutV = cw.Cout;
@@ -614,6 +637,7 @@ int run_conv(H* h, const ConvW& cw, const float* x, int Lin, float* y, int act_i
 }
 // SConvTranspose1d (conv.py:252-274): y [B][Cout][Lin*s]; causal -> trim right only, else left = ceil((k-s)/2)
 int run_convtr(H* h, const ConvTrW& cw, const float* x, int Lin, float* y, int act_in, bool causal, int B, cudaStream_t st) {
+  CodecProf cp(st, "convtr Cin=%d Cout=%d s=%d Lin=%d causal=%d", cw.Cin, cw.Cout, cw.s, Lin, causal ? 1 : 0);
   ConvF32Args a;
   memset(&a, 0, sizeof(a));
   a.x = x; a.Cin = cw.Cin; a.Lin = Lin; a.w = cw.w2; a.wt = cw.wt; a.bias = cw.bias; a.y = y; a.CoutV = cw.s * cw.Cout; a.LoutV = Lin + 1;
@@ -625,6 +649,17 @@ int run_convtr(H* h, const ConvTrW& cw, const float* x, int Lin, float* y, int a
   return conv1d_f32_launch(a, B, st);
 }
 int run_resblock(H* h, const ResBlockW& rb, float*& x, int L, Pool& pool, int B, cudaStream_t st) {
+  if (rb.c1.wt && rb.sc.wt && rb.c2.wt) {      // one fused kernel where the channel count has one (C = 32, 64)
+    float* yf = pool.get();
+    int rc;
+    {
+      CodecProf cp(st, "fused resblock C=%d L=%d B=%d%c%c", rb.sc.Cout, L, B, ' ', ' ');
+      rc = seanet_resblock_launch(x, yf, rb.c1.wt, rb.c1.bias, rb.sc.wt, rb.sc.bias, rb.c2.wt, rb.c2.bias, rb.sc.Cout, B, L, st);
+    }
+    if (rc == 0) { h->launches++; pool.put(x); x = yf; return 0; }
+    pool.put(yf);
+    if (rc < 0) return rc;
+  }
   float* hbuf = pool.get(); float* s = pool.get(); float* y = pool.get();
   TRY(run_conv(h, rb.c1, x, L, hbuf, 1, nullptr, B, st));
   TRY(run_conv(h, rb.sc, x, L, s, 0, nullptr, B, st));
@@ -643,6 +678,7 @@ int run_lstm(H* h, const LstmW& lw, float*& x, int T, Pool& pool, float* hbuf, f
     TRY(run_conv(h, ip, in, T, pre, 0, nullptr, B, st));
     y = pool.get();
     const float* skip = (l == lw.layers - 1) ? x : nullptr;
+    CodecProf cp(st, "lstm recurrence H=%d T=%d layer=%d B=%d%c", lw.H, T, l, B, ' ');
     if (lw.H == 64 || lw.H == 128) {
       TRY(lstm_seq_launch(pre, lw.whh[l], skip, y, B, lw.H, T, st));
       h->launches++;

@@ -1,6 +1,7 @@
 // fp32 NCL kernels of the SEANet codec path (HBM/latency-bound side of the pipeline; plain SIMT fp32 so that the
 // encoder output feeding the RVQ argmax keeps fp32 fidelity).
 #include <stdlib.h>
+#include <string.h>
 
 #include "codec_ops.cuh"
 
@@ -266,6 +267,145 @@ __global__ void __launch_bounds__(256, RC >= 8 ? 2 : 3) conv1d_f32_v2_kernel(Con
   }
 }
 
+// ------------------------------------------------------------------ fused SEANet residual block (seanet.py:45-63), C = 32 / 64
+//   y = conv1x1_shortcut(x) + conv_k1(ELU(conv_k3(ELU(x))))        hidden = C/2, causal reflect padding 2 for the k3 (conv.py:217-232)
+// One read of x and one write of y per element (the three-launch form moves x three times, the hidden tensor twice and the shortcut
+// twice).  CTA = NTH threads (8 warps for C = 32, 16 for C = 64), TT positions of one clip; shared memory holds raw x, ELU(x) with its 2-sample halo, ELU(hidden) and
+// all three weight matrices (K-major).  Thread tile: (channels of its warp) x (groups of 4 consecutive positions, 128 apart):
+// activations as LDS.128/.64 (lanes 16 B apart: conflict-free), weights as warp-broadcast vector loads.
+template <int C, int TT, int NTH>
+__global__ void __launch_bounds__(NTH) seanet_resblock_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ w1t,
+                                                               const float* __restrict__ b1, const float* __restrict__ wsct,
+                                                               const float* __restrict__ bsc, const float* __restrict__ w2t,
+                                                               const float* __restrict__ b2, int L) {
+  constexpr int HID = C / 2, XP = TT + 8, NG = TT / 128, NW = NTH / 32, R1 = HID / NW, R2 = C / NW;
+  extern __shared__ __align__(16) float rsm[];
+  float* xe = rsm;                          // [C][XP]   ELU(x), element t0 + i at index i + 2
+  float* xraw = xe + C * XP;                // [C][TT]
+  float* he = xraw + C * TT;                // [HID][TT] ELU(hidden)
+  float* w1s = he + HID * TT;               // [C*3][HID]
+  float* wss = w1s + C * 3 * HID;           // [C][C]
+  float* w2s = wss + C * C;                 // [HID][C]
+  const int b = blockIdx.y, t0 = blockIdx.x * TT, tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const float* xb = x + (long long)b * C * L;
+  // ---- stage 0: weights and the x tile
+  for (int i = tid; i < C * 3 * HID / 4; i += NTH) reinterpret_cast<float4*>(w1s)[i] = __ldg(reinterpret_cast<const float4*>(w1t) + i);
+  for (int i = tid; i < C * C / 4; i += NTH) reinterpret_cast<float4*>(wss)[i] = __ldg(reinterpret_cast<const float4*>(wsct) + i);
+  for (int i = tid; i < HID * C / 4; i += NTH) reinterpret_cast<float4*>(w2s)[i] = __ldg(reinterpret_cast<const float4*>(w2t) + i);
+  for (int i = tid; i < C * (TT / 4); i += NTH) {
+    const int c = i / (TT / 4), p4 = (i - c * (TT / 4)) * 4, t = t0 + p4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t + 3 < L) v = __ldg(reinterpret_cast<const float4*>(xb + (long long)c * L + t));
+    else {
+      if (t < L) v.x = __ldg(xb + (long long)c * L + t);
+      if (t + 1 < L) v.y = __ldg(xb + (long long)c * L + t + 1);
+      if (t + 2 < L) v.z = __ldg(xb + (long long)c * L + t + 2);
+    }
+    *reinterpret_cast<float4*>(xraw + c * TT + p4) = v;
+    float* e = xe + c * XP + p4 + 2;
+    e[0] = v.x > 0.f ? v.x : expm1f(v.x); e[1] = v.y > 0.f ? v.y : expm1f(v.y);
+    e[2] = v.z > 0.f ? v.z : expm1f(v.z); e[3] = v.w > 0.f ? v.w : expm1f(v.w);
+  }
+  if (tid < 2 * C) {                        // halo: x[t0-2], x[t0-1]; reflect at the clip start (x[-1] = x[1], x[-2] = x[2])
+    const int c = tid >> 1, hh = tid & 1;   // hh = 0 -> offset -2, 1 -> offset -1
+    int t = t0 - 2 + hh;
+    if (t < 0) t = -t;
+    float v = t < L ? __ldg(xb + (long long)c * L + t) : 0.f;
+    xe[c * XP + hh] = v > 0.f ? v : expm1f(v);
+  }
+  __syncthreads();
+  // ---- stage 1: hidden = conv_k3(ELU(x)) + b1 -> ELU -> he
+  {
+    float acc[R1][NG * 4];
+#pragma unroll
+    for (int r = 0; r < R1; ++r) {
+      const float bb = __ldg(b1 + ty * R1 + r);
+#pragma unroll
+      for (int j = 0; j < NG * 4; ++j) acc[r][j] = bb;
+    }
+    for (int ci = 0; ci < C; ++ci) {
+      float xv[NG][6];
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        const float* xr = xe + ci * XP + 4 * tx + 128 * g;
+        const float4 a4 = *reinterpret_cast<const float4*>(xr);
+        const float2 a2 = *reinterpret_cast<const float2*>(xr + 4);
+        xv[g][0] = a4.x; xv[g][1] = a4.y; xv[g][2] = a4.z; xv[g][3] = a4.w; xv[g][4] = a2.x; xv[g][5] = a2.y;
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float wv[R1];
+        const float* wr = w1s + (ci * 3 + k) * HID + ty * R1;
+        if (R1 == 2) { const float2 t2 = *reinterpret_cast<const float2*>(wr); wv[0] = t2.x; wv[1] = t2.y; }
+        else {
+#pragma unroll
+          for (int r4 = 0; r4 < R1 / 4; ++r4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(wr + 4 * r4);
+            wv[4 * r4] = t4.x; wv[4 * r4 + 1] = t4.y; wv[4 * r4 + 2] = t4.z; wv[4 * r4 + 3] = t4.w;
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < R1; ++r)
+#pragma unroll
+          for (int g = 0; g < NG; ++g)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[r][g * 4 + j] = fmaf(wv[r], xv[g][j + k], acc[r][g * 4 + j]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R1; ++r)
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        float4 o;
+        o.x = acc[r][g * 4 + 0]; o.y = acc[r][g * 4 + 1]; o.z = acc[r][g * 4 + 2]; o.w = acc[r][g * 4 + 3];
+        o.x = o.x > 0.f ? o.x : expm1f(o.x); o.y = o.y > 0.f ? o.y : expm1f(o.y);
+        o.z = o.z > 0.f ? o.z : expm1f(o.z); o.w = o.w > 0.f ? o.w : expm1f(o.w);
+        *reinterpret_cast<float4*>(he + (ty * R1 + r) * TT + 4 * tx + 128 * g) = o;
+      }
+  }
+  __syncthreads();
+  // ---- stage 2: y = W_sc x + b_sc + W_2 ELU(hidden) + b_2
+  float acc[R2][NG * 4];
+#pragma unroll
+  for (int r = 0; r < R2; ++r) {
+    const float bb = __ldg(bsc + ty * R2 + r) + __ldg(b2 + ty * R2 + r);
+#pragma unroll
+    for (int j = 0; j < NG * 4; ++j) acc[r][j] = bb;
+  }
+  auto accumulate = [&](const float* act, const float* wrow) {      // one input channel: act [TT], wrow [C]
+    float wv[R2];
+#pragma unroll
+    for (int r4 = 0; r4 < R2 / 4; ++r4) {
+      const float4 t4 = *reinterpret_cast<const float4*>(wrow + ty * R2 + 4 * r4);
+      wv[4 * r4] = t4.x; wv[4 * r4 + 1] = t4.y; wv[4 * r4 + 2] = t4.z; wv[4 * r4 + 3] = t4.w;
+    }
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      const float4 a4 = *reinterpret_cast<const float4*>(act + 4 * tx + 128 * g);
+#pragma unroll
+      for (int r = 0; r < R2; ++r) {
+        acc[r][g * 4 + 0] = fmaf(wv[r], a4.x, acc[r][g * 4 + 0]); acc[r][g * 4 + 1] = fmaf(wv[r], a4.y, acc[r][g * 4 + 1]);
+        acc[r][g * 4 + 2] = fmaf(wv[r], a4.z, acc[r][g * 4 + 2]); acc[r][g * 4 + 3] = fmaf(wv[r], a4.w, acc[r][g * 4 + 3]);
+      }
+    }
+  };
+  for (int ci = 0; ci < C; ++ci) accumulate(xraw + ci * TT, wss + ci * C);
+  for (int hc = 0; hc < HID; ++hc) accumulate(he + hc * TT, w2s + hc * C);
+  float* yb = y + (long long)b * C * L;
+#pragma unroll
+  for (int r = 0; r < R2; ++r)
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      const int t = t0 + 4 * tx + 128 * g;
+      float* yr = yb + (long long)(ty * R2 + r) * L + t;
+      if (t + 3 < L) *reinterpret_cast<float4*>(yr) = make_float4(acc[r][g * 4 + 0], acc[r][g * 4 + 1], acc[r][g * 4 + 2], acc[r][g * 4 + 3]);
+      else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (t + j < L) yr[j] = acc[r][g * 4 + j];
+      }
+    }
+}
+
 __global__ void conv_w_transpose_kernel(const float* __restrict__ w, float* __restrict__ wt, int CoutV, int Cin, int K, int S, int perm_s,
                                         int perm_cout) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -338,6 +478,110 @@ __global__ void __launch_bounds__(4 * H) lstm_seq_kernel(const float* __restrict
       }
     }
   }
+}
+
+// ------------------------------------------------------------------ LSTM, small H: a CTA CLUSTER per clip (gate rows split over SMs)
+// The recurrence is serial in time, so its speed is the latency of ONE step.  A cluster of CL = H/32 CTAs (128 threads each) owns a
+// clip; CTA r owns hidden units [32r, 32r+32) = 128 gate rows, one row per thread (thread = 4*unit + gate), the row's H recurrent
+// weights live in REGISTERS, h_{t-1} in the CTA's shared memory (double-buffered).  Per step: 4-chain dot product against
+// broadcast LDS.128 reads of h, quad shuffle -> the four gates of a unit, cell update (every lane of the quad keeps c), then lane q of
+// the quad sends h_t[unit] to CTA q with ONE one-way message: st.async into the peer's shared memory that also completes 4 bytes
+// on the peer's mbarrier (tx-count), the same mechanism TMA uses.  Every thread then waits for the step's H*4 bytes.  Two
+// barriers alternate by step parity, so a fast peer's message for step t+1 can never be counted in step t; a peer only gets to
+// step t+1 after it has received THIS CTA's step-t values, i.e. after all of this CTA's warps finished reading the h buffer that
+// step t+1 overwrites.  No __syncthreads, no cluster barrier and no release fence inside the loop.
+__device__ __forceinline__ uint32_t lc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lc_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+// gates with MUFU-based exp (rel. error ~2^-21): far below the decoder's 5e-5 tolerance; the ENCODER's LSTM (whose output feeds
+// the RVQ argmax) runs lstm_persist_kernel with expf / tanhf
+__device__ __forceinline__ float lc_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float lc_tanh(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
+
+template <int H>
+__global__ void __launch_bounds__(128, 1) lstm_cluster_kernel(const float* __restrict__ pre, const float* __restrict__ whh,
+                                                              const float* __restrict__ skip, float* __restrict__ y, int T) {
+  constexpr int CL = H / 32;
+  __shared__ __align__(16) float hs[2][H];
+  __shared__ __align__(8) uint64_t bar[2];
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int b = blockIdx.x / CL, tid = threadIdx.x;
+  const int q = tid & 3, u = tid >> 2, j = 32 * (int)rank + u, row = q * H + j;
+  float w[H];
+#pragma unroll
+  for (int k = 0; k < H; k += 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(whh + (long long)row * H + k));
+    w[k] = v.x; w[k + 1] = v.y; w[k + 2] = v.z; w[k + 3] = v.w;
+  }
+  for (int i = tid; i < 2 * H; i += 128) (&hs[0][0])[i] = 0.f;
+  const uint32_t bar0 = lc_smem_u32(&bar[0]), bar1 = lc_smem_u32(&bar[1]);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // steps 0 and 1 expect H*4 bytes each (posted before any peer can send)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0), "r"(H * 4) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar1), "r"(H * 4) : "memory");
+  }
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");   // peers' barriers and hs are ready
+  const bool sender = q < CL;          // lane q of a unit's quad feeds CTA q of the cluster
+  const uint32_t r_bar0 = sender ? lc_mapa(bar0, (uint32_t)q) : 0u, r_bar1 = sender ? lc_mapa(bar1, (uint32_t)q) : 0u;
+  const uint32_t r_hs0 = sender ? lc_mapa(lc_smem_u32(&hs[0][j]), (uint32_t)q) : 0u;
+  const uint32_t r_hs1 = sender ? lc_mapa(lc_smem_u32(&hs[1][j]), (uint32_t)q) : 0u;
+  float c = 0.f;
+  const float* prow = pre + ((long long)b * 4 * H + row) * T;
+  const long long ybase = ((long long)b * H + j) * T;
+  for (int t0 = 0; t0 < T; t0 += 8) {
+    float pbuf[8], sbuf[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      pbuf[i] = (t0 + i < T) ? __ldg(prow + t0 + i) : 0.f;
+      sbuf[i] = (skip && q == 3 && t0 + i < T) ? __ldg(skip + ybase + t0 + i) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int t = t0 + i;
+      if (t >= T) break;            // uniform
+      const int cur = t & 1;        // step t reads hs[cur], fills hs[cur ^ 1] and completes bar[cur]
+      float a0 = pbuf[i], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      const float4* h4 = reinterpret_cast<const float4*>(hs[cur]);
+#pragma unroll
+      for (int k4 = 0; k4 < H / 4; ++k4) {
+        const float4 hv = h4[k4];
+        a0 = fmaf(w[4 * k4 + 0], hv.x, a0); a1 = fmaf(w[4 * k4 + 1], hv.y, a1);
+        a2 = fmaf(w[4 * k4 + 2], hv.z, a2); a3 = fmaf(w[4 * k4 + 3], hv.w, a3);
+      }
+      const float acc = (a0 + a1) + (a2 + a3);
+      const int base = (tid & 31) & ~3;
+      const float gi = __shfl_sync(0xffffffffu, acc, base + 0);
+      const float gf = __shfl_sync(0xffffffffu, acc, base + 1);
+      const float gg = __shfl_sync(0xffffffffu, acc, base + 2);
+      const float go = __shfl_sync(0xffffffffu, acc, base + 3);
+      c = lc_sigmoid(gf) * c + lc_sigmoid(gi) * lc_tanh(gg);
+      const float h = lc_sigmoid(go) * lc_tanh(c);
+      if (sender)
+        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                     ::"r"(cur ? r_hs0 : r_hs1), "r"(__float_as_uint(h)), "r"(cur ? r_bar1 : r_bar0) : "memory");
+      if (q == 3) y[ybase + t] = skip ? h + sbuf[i] : h;
+      // wait for h_t of every unit of the clip: H*4 bytes on bar[cur]; phase parity = (t >> 1) & 1
+      const uint32_t bar_c = cur ? bar1 : bar0, parity = (uint32_t)(t >> 1) & 1u;
+      uint32_t ok = 0;
+      while (!ok) {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok) : "r"(bar_c), "r"(parity) : "memory");
+      }
+      // re-arm this barrier for step t + 2 (its phase just completed; nobody sends step t + 2 data before receiving OUR step t + 1)
+      if (tid == 0 && t + 2 < T) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_c), "r"(H * 4) : "memory");
+    }
+  }
+  // no CTA may exit while a peer can still write into its shared memory
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // ------------------------------------------------------------------ LSTM, any H: one launch per time step
@@ -723,6 +967,28 @@ static int conv1d_v2_dispatch(const ConvF32Args& a, int KT, int S, int B, cudaSt
   return 0;
 }
 
+template <int C, int TT, int NTH>
+static int seanet_resblock_launch_t(const float* x, float* y, const float* w1t, const float* b1, const float* wsct, const float* bsc,
+                                    const float* w2t, const float* b2, int B, int L, cudaStream_t st) {
+  constexpr int HID = C / 2, XP = TT + 8;
+  const size_t smem = (size_t)(C * XP + C * TT + HID * TT + C * 3 * HID + C * C + HID * C) * sizeof(float);
+  static unsigned long long attr = 0;
+  if (ladiff_first_on_device(&attr))
+    LADIFF_CUDA_OK(cudaFuncSetAttribute(seanet_resblock_kernel<C, TT, NTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  seanet_resblock_kernel<C, TT, NTH><<<dim3(cdiv(L, TT), B), NTH, smem, st>>>(x, y, w1t, b1, wsct, bsc, w2t, b2, L);
+  LADIFF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+// Fused residual block; returns 1 if this shape has no fused kernel (caller falls back to the three-launch form).
+int seanet_resblock_launch(const float* x, float* y, const float* w1t, const float* b1, const float* wsct, const float* bsc, const float* w2t,
+                           const float* b2, int C, int B, int L, cudaStream_t st) {
+  static const bool off = getenv("LADIFF_NO_FUSED_RESBLOCK") != nullptr;
+  if (off || L % 4 != 0 || L < 4 || ((uintptr_t)x % 16) != 0 || ((uintptr_t)y % 16) != 0) return 1;
+  if (C == 32) return seanet_resblock_launch_t<32, 256, 256>(x, y, w1t, b1, wsct, bsc, w2t, b2, B, L, st);
+  if (C == 64) return seanet_resblock_launch_t<64, 256, 512>(x, y, w1t, b1, wsct, bsc, w2t, b2, B, L, st);
+  return 1;
+}
+
 int conv1d_f32_launch(const ConvF32Args& a, int B, cudaStream_t st) {
   LADIFF_REQUIRE(a.K >= 1 && a.K <= 64 && a.stride >= 1, LADIFF_ERR_ARG, "conv1d_f32: K=%d stride=%d", a.K, a.stride);
   static const bool no_v2 = getenv("LADIFF_CODEC_V1") != nullptr;
@@ -755,7 +1021,24 @@ int conv1d_f32_launch(const ConvF32Args& a, int B, cudaStream_t st) {
   return 0;
 }
 
+template <int H>
+static int lstm_cluster_launch(const float* pre, const float* whh, const float* skip, float* y, int B, int T, cudaStream_t st) {
+  constexpr int CL = H / 32;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(B * CL); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  LADIFF_CUDA_OK(cudaLaunchKernelEx(&cfg, lstm_cluster_kernel<H>, pre, whh, skip, y, T));
+  return 0;
+}
+
 int lstm_seq_launch(const float* pre, const float* whh, const float* skip, float* y, int B, int H, int T, cudaStream_t st) {
+  static const bool no_cluster = getenv("LADIFF_LSTM_NO_CLUSTER") != nullptr;
+  if (!no_cluster && H == 64) return lstm_cluster_launch<64>(pre, whh, skip, y, B, T, st);
+  if (!no_cluster && H == 128) return lstm_cluster_launch<128>(pre, whh, skip, y, B, T, st);
   if (H == 64) {
     lstm_seq_kernel<64, 64><<<B, 256, 0, st>>>(pre, whh, skip, y, T);
   } else if (H == 128) {

@@ -21,6 +21,11 @@ struct ConvF32Args {
   int il_s, il_cout, il_trim, il_lout;
 };
 int conv1d_f32_launch(const ConvF32Args& a, int B, cudaStream_t st);
+// Fused SEANet residual block (seanet.py:45-63) for C = 32 / 64: y = shortcut_1x1(x) + conv_k1(ELU(conv_k3(ELU(x)))), causal reflect
+// padding; w1t [C*3][C/2], wsct [C][C], w2t [C/2][C] are the K-major copies (conv_w_transpose_launch).  Returns 0 when launched,
+// 1 when the shape has no fused kernel (caller uses three conv launches), < 0 on error.
+int seanet_resblock_launch(const float* x, float* y, const float* w1t, const float* b1, const float* wsct, const float* bsc, const float* w2t,
+                           const float* b2, int C, int B, int L, cudaStream_t st);
 // wt[((ci*S + p)*KT + kt)][col(co)] = w[co][ci][kt*S + p], S = stride phases (K = KT*S), for the register-tiled kernel.
 // perm_s > 0 (transposed-conv virtual channels co = ph*perm_cout + cr): col = cr*perm_s + ph (phase fastest), else col = co.
 int conv_w_transpose_launch(const float* w, float* wt, int CoutV, int Cin, int K, int S, int perm_s, int perm_cout, cudaStream_t st);
