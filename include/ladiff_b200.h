@@ -219,6 +219,9 @@ int32_t ladiff_normalize_clips(float* x, int32_t B, int64_t n, int32_t mode, voi
 int32_t ladiff_op_conv1d_cl(const void* x_h16, const float* w, const float* bias, int32_t B, int32_t L,
                             int32_t Cin, int32_t Cout, int32_t k, void* y, int32_t y_f32, int32_t impl,
                             float* gn_stats /* [B,Cout/32,2] or NULL */);
+/* Attention core of the mid block (srcs/modules/unet.py:238-245) on channels-last 16-bit qkv [B,L,384] (q | k | v, 4 heads x 32) →
+ * out [B,L,128].  impl 0 = the UNet's choice, 1 = tiled SIMT, 2 = SIMT with keys in shared memory (L <= 512), 3 = tcgen05 (QK^T, PV). */
+int32_t ladiff_op_fullattn(const void* qkv_h16, void* out_h16, int32_t B, int32_t L, int32_t impl);
 /* Operator-level timing of the same conv (kernel tuning, profiles/conv_sweep.py): one plan, `warm` untimed + `iters` timed launches
  * between two CUDA events; ms_out[0] = mean ms per launch; want_* override the tile shape (0 = cost model); label receives the plan. */
 int32_t ladiff_op_conv1d_bench(const void* x_h16, const float* w, const float* bias, int32_t B, int32_t L, int32_t Cin, int32_t Cout,
@@ -226,6 +229,10 @@ int32_t ladiff_op_conv1d_bench(const void* x_h16, const float* w, const float* b
                                int32_t warm, int32_t iters, float* ms_out, char* label, int32_t label_cap);
 /* Selects the conv implementation used inside the UNet: 0 = tcgen05 (default), 1 = SIMT check kernel. */
 int32_t ladiff_set_conv_impl(LadiffHandle* h, int32_t impl);
+/* Timing ablation for bench.py's roofline: UNet evaluations of this handle skip the kernel classes in `mask` (1 GroupNorm-apply,
+ * 2 LayerNorm, 4 attention cores, 8 1x1 convs, 16 all other convs) — results are garbage while mask != 0.  The difference between
+ * the replay time with and without a class is that class's time inside the CUDA-graph replay (PDL overlap included). */
+int32_t ladiff_set_skip_ops(LadiffHandle* h, int32_t mask);
 /* Profiling for bench.py's roofline: when on, CUDA events are recorded on the launching stream around every
  * tcgen05 conv launch of a UNet evaluation.  ladiff_profile_report (synchronises) returns for the most recent
  * evaluation: out4 = {conv ms, conv algorithmic FLOPs, conv launches, whole-evaluation ms}. */

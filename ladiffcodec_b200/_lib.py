@@ -65,8 +65,10 @@ SIGNATURES = {
     "ladiff_op_conv1d_cl": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp]),
     "ladiff_op_conv1d_bench": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32,
                                        ctypes.POINTER(ctypes.c_float), ctypes.c_char_p, c_i32]),
+    "ladiff_op_fullattn": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32]),
     "ladiff_set_conv_impl": (c_i32, [c_vp, c_i32]),
     "ladiff_take_launch_count": (c_i64, [c_vp]),
+    "ladiff_set_skip_ops": (c_i32, [c_vp, c_i32]),
     "ladiff_set_profiling": (c_i32, [c_vp, c_i32]),
     "ladiff_profile_report": (c_i32, [c_vp, ctypes.POINTER(ctypes.c_double)]),
     "ladiff_profile_dump": (c_i32, [c_vp, ctypes.c_char_p, c_i64]),

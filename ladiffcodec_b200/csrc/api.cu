@@ -132,6 +132,7 @@ struct LadiffHandle {
   std::vector<void*> owned;
   bool finalized = false;
   int conv_impl = 0;
+  int skip_ops = 0;
   int profiling = 0;
   Plan* last_plan = nullptr;
   long long launches = 0;
@@ -801,6 +802,12 @@ ClView view(h16* p, int L, int pitch, int C, int ch0 = 0) {
   ClView v; v.p = p + ch0; v.bstride = (long long)L * pitch; v.pitch = pitch; v.C = C; return v;
 }
 
+// Timing ablations (ladiff_set_skip_ops / LADIFF_SKIP_OPS; results are garbage while a bit is set): 1 GroupNorm-apply, 2 LayerNorm,
+// 4 attention cores, 8 1x1 convs, 16 all other convs.  bench.py uses it to attribute the CUDA-graph replay's time to kernel classes.
+static int g_skip_env() {
+  static const int m = getenv("LADIFF_SKIP_OPS") ? atoi(getenv("LADIFF_SKIP_OPS")) : 0;
+  return m;
+}
 struct PlanBuilder {
   H* h; Plan* pl; int B;
   bool tune_stream_ok; cudaStream_t tune_stream; cudaEvent_t tune_ev[2];
@@ -895,7 +902,9 @@ struct PlanBuilder {
       LADIFF_REQUIRE(ps.n_ptiles * ps.stat_parts * ps.stat_slots <= pl->bufs.stats_slots, LADIFF_ERR_WORKSPACE, "plan: stats buffer too small");
     if (n_ntiles) *n_ntiles = ps.n_ptiles * ps.stat_parts;
     H* hh = h;
-    pl->ops.push_back([hh, ps, pu, rv](cudaStream_t st) {
+    const int skip_bit = pc.K == 1 ? 8 : 16;
+    pl->ops.push_back([hh, ps, pu, rv, skip_bit](cudaStream_t st) {
+      if ((hh->skip_ops | g_skip_env()) & skip_bit) return 0;
       if (hh->conv_impl == 1) return tc_conv_ref_launch(ps, rv, st);
       return tc_conv_launch(hh->conv_impl == 2 ? pu : ps, st);
     });
@@ -921,7 +930,8 @@ struct PlanBuilder {
     a.y = y; a.stats = pl->bufs.stats; a.n_ntiles = n_ntiles; a.gamma = g; a.beta = b; a.film = film;
     a.film_stride = h->un.film_stride; a.t_dev = pl->bufs.t_dev; a.res = res; a.out = out; a.L = L; a.do_tanh = do_tanh ? 1 : 0;
     const int BB = B;
-    pl->ops.push_back([a, BB](cudaStream_t st) { return gn_apply_launch(a, BB, st); });
+    H* hg = h;
+    pl->ops.push_back([a, BB, hg](cudaStream_t st) { return ((hg->skip_ops | g_skip_env()) & 1) ? 0 : gn_apply_launch(a, BB, st); });
     label("gn_apply C=%d L=%d film=%d res=%d", y.C, L, film ? 1 : 0, res.p ? 1 : 0);
     pl->launches_per_run++;
     return 0;
@@ -948,7 +958,8 @@ struct PlanBuilder {
   }
   int layernorm(ClView x, const float* g, ClView res, ClView out, int L) {
     const int BB = B;
-    pl->ops.push_back([x, g, res, out, BB, L](cudaStream_t st) { return layernorm_cl_launch(x, g, res, out, BB, L, st); });
+    H* hg = h;
+    pl->ops.push_back([x, g, res, out, BB, L, hg](cudaStream_t st) { return ((hg->skip_ops | g_skip_env()) & 2) ? 0 : layernorm_cl_launch(x, g, res, out, BB, L, st); });
     label("layernorm C=%d L=%d res=%d", x.C, L, res.p ? 1 : 0, 0);
     pl->launches_per_run++;
     return 0;
@@ -963,14 +974,16 @@ struct PlanBuilder {
     TRY(conv(a.qkv, ln, L, qkv, nullptr, false, nullptr, none));
     const int BB = B; float* ctx = u.ctx; float* lap = u.la_part; int* lac = u.la_cnt;
     if (linear) {
-      pl->ops.push_back([qkv, ctx, lap, lac, ao, BB, L](cudaStream_t st) { return linattn_launch(qkv, ctx, lap, lac, ao, BB, L, st); });
+      H* hg = h;
+      pl->ops.push_back([qkv, ctx, lap, lac, ao, BB, L, hg](cudaStream_t st) { return ((hg->skip_ops | g_skip_env()) & 4) ? 0 : linattn_launch(qkv, ctx, lap, lac, ao, BB, L, st); });
       label("linattn(ctx+out) L=%d", L, 0, 0, 0);
       pl->launches_per_run += 2;
       ClView yo = view(u.tY, L, a.C, a.C);
       TRY(conv(a.out, ao, L, yo, nullptr, false, nullptr, none));
       TRY(layernorm(yo, a.out_g, x, out, L));
     } else {
-      pl->ops.push_back([qkv, ao, BB, L](cudaStream_t st) { return fullattn_launch(qkv, ao, BB, L, st); });
+      H* hg = h;
+      pl->ops.push_back([qkv, ao, BB, L, hg](cudaStream_t st) { return ((hg->skip_ops | g_skip_env()) & 4) ? 0 : fullattn_launch(qkv, ao, BB, L, st); });
       label("fullattn L=%d", L, 0, 0, 0);
       pl->launches_per_run++;
       TRY(conv(a.out, ao, L, out, nullptr, false, nullptr, x));
@@ -1619,6 +1632,16 @@ extern "C" int32_t ladiff_set_conv_impl(LadiffHandle* h, int32_t impl) {
   h->conv_impl = impl;
   return 0;
 }
+extern "C" int32_t ladiff_set_skip_ops(LadiffHandle* h, int32_t mask) {
+  LADIFF_REQUIRE(h && mask >= 0 && mask < 32, LADIFF_ERR_ARG, "ladiff_set_skip_ops: mask=%d", mask);
+  if (mask != h->skip_ops) {
+    LADIFF_CUDA_OK(cudaDeviceSynchronize());
+    for (Plan* p : h->plans)
+      if (p->gexec) { cudaGraphExecDestroy(p->gexec); p->gexec = nullptr; }       // re-captured with the new op set on the next run
+  }
+  h->skip_ops = mask;
+  return 0;
+}
 extern "C" int32_t ladiff_set_profiling(LadiffHandle* h, int32_t on) {
   LADIFF_REQUIRE(h, LADIFF_ERR_ARG, "null handle");
   h->profiling = on < 0 ? 0 : (on > 2 ? 2 : on);   // 1: events around conv launches; 2: around every op of the evaluation
@@ -1766,5 +1789,16 @@ extern "C" int32_t ladiff_op_conv1d_bench(const void* x_h16, const float* w, con
   cudaDeviceSynchronize();
   cudaFree(wp); cudaFree(y);
   if (stats) cudaFree(stats);
+  return rc;
+}
+
+// Operator-level entry for the mid-block attention core (tests): qkv [B][L][384] 16-bit (q | k | v, 4 heads x 32) -> out [B][L][128].
+// impl 0 = what the UNet would pick, 1 = tiled SIMT, 2 = SIMT with keys in shared memory, 3 = tcgen05.  Synchronises.
+extern "C" int32_t ladiff_op_fullattn(const void* qkv_h16, void* out_h16, int32_t B, int32_t L, int32_t impl) {
+  LADIFF_REQUIRE(qkv_h16 && out_h16 && B > 0 && L > 0 && impl >= 0 && impl <= 3, LADIFF_ERR_ARG, "ladiff_op_fullattn: bad argument");
+  ClView q = view((h16*)qkv_h16, L, 384, 384), o = view((h16*)out_h16, L, 128, 128);
+  int rc = impl == 0 ? fullattn_launch(q, o, B, L, 0) : fullattn_launch_impl(q, o, B, L, impl, 0);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (!rc && e != cudaSuccess) { ladiff_set_error("ladiff_op_fullattn: %s", cudaGetErrorString(e)); rc = LADIFF_ERR_CUDA; }
   return rc;
 }

@@ -1,0 +1,254 @@
+// tcgen05 full attention for the UNet's bottleneck block (reference srcs/modules/unet.py:234-246: sim = q k^T, softmax over keys,
+// out = attn v; 4 heads x 32) when the bottleneck is long (whole utterances: n = L/16 in the thousands).
+//
+// One CTA per (clip, head, 128-query tile), flash-attention style over 128-key tiles:
+//   S[128 q, 128 k] = Q K^T      tcgen05.mma kind::f16, M = 128, N = 128, K = 32 (2 instructions), fp32 in TMEM
+//   online softmax               thread = query row (tcgen05.ld 32x32b gives a thread its row), running max / sum in registers
+//   O_tile[128 q, 32 d] = P V    tcgen05.mma M = 128, N = 32, K = 128 (8 instructions); P written by the row threads as the
+//                                16-bit A operand, V^T staged as the B operand; the tile's result is folded into fp32 registers
+// Operands live in shared memory in the K-major SWIZZLE_128B layout the conv kernel uses (128-byte rows, 16-byte chunk index XOR
+// row%8); they are written by ordinary stores (rows of 64 bytes: half of every 128-byte row is unused), made visible to the tensor
+// core with fence.proxy.async.  Warps 0-3: loads / softmax / epilogue (TMEM lane quadrant = warp), warp 4: TMEM allocation + MMA issue.
+#include "unet_ops.cuh"
+
+namespace {
+
+__device__ __forceinline__ uint32_t a_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool a_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void a_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void a_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = a_smem_u32(bar);
+  long long t0 = 0;
+  for (uint32_t spins = 0;; ++spins) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) return;
+    if (spins == 64) t0 = clock64();
+    if (spins > 64 && (spins & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();     // protocol bug -> launch error, not a hang
+  }
+}
+__device__ __forceinline__ void a_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(a_smem_u32(bar)) : "memory");
+}
+// K-major SWIZZLE_128B matrix descriptor (SBO = 1024 B: 8 rows x 128 B), as in tc_conv.cu
+__device__ __forceinline__ uint64_t a_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void a_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void a_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr));
+}
+// byte offset of 16-byte chunk `c` (0..7) of row `r` inside a [rows][128 B] SWIZZLE_128B tile (tile base 1024-byte aligned)
+__device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t c) { return r * 128u + ((c ^ (r & 7u)) << 4); }
+
+constexpr int FT_THREADS = 160;
+constexpr uint32_t FT_Q = 0, FT_K = 16384, FT_VT = 32768, FT_P = 40960, FT_SMEM = 73728 + 1024;
+
+__global__ void __launch_bounds__(FT_THREADS) fullattn_tc_kernel(ClView qkv, ClView out, int L) {
+  extern __shared__ uint8_t fa_raw[];
+  __shared__ __align__(8) uint64_t s_bar, o_bar;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int h = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * 128;
+  const uint32_t sbase = (a_smem_u32(fa_raw) + 1023u) & ~1023u;
+  if (tid == 0) {
+    a_mbar_init(&s_bar, 1); a_mbar_init(&o_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(a_smem_u32(&tmem_base_s)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  pdl_wait();
+  pdl_trigger();
+  const h16* base = qkv.p + (long long)b * qkv.bstride;
+  const float scale = 0.17677669529663687f;          // q * 32^-0.5 (unet.py:238)
+  // ---- Q tile: thread r owns query q0 + r; zero row beyond the clip
+  if (warp < 4) {
+    const int qi = q0 + tid;
+    uint4 v[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[c] = make_uint4(0u, 0u, 0u, 0u);
+    if (qi < L) {
+      const h16* qr = base + (long long)qi * qkv.pitch + h * 32;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 raw = __ldcg(reinterpret_cast<const uint4*>(qr + 8 * c));
+        h162* hp = reinterpret_cast<h162*>(&raw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 f = h22ff(hp[i]); hp[i] = ff2h2(f.x * scale, f.y * scale); }
+        v[c] = raw;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + FT_Q + sw128(tid, c)), "r"(v[c].x), "r"(v[c].y), "r"(v[c].z), "r"(v[c].w) : "memory");
+  }
+  // instruction descriptors: fp32 accumulate, 16-bit A/B (K-major), N >> 3 at bit 17, M >> 4 at bit 24
+  const uint32_t idesc_s = (1u << 4) | (TC_IDESC_AB_FMT << 7) | (TC_IDESC_AB_FMT << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+  const uint32_t idesc_o = (1u << 4) | (TC_IDESC_AB_FMT << 7) | (TC_IDESC_AB_FMT << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+  float m_run = -INFINITY, l_run = 0.f, o[32];
+#pragma unroll
+  for (int d = 0; d < 32; ++d) o[d] = 0.f;
+  const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+  uint32_t ph = 0;
+  for (int k0 = 0; k0 < L; k0 += 128, ph ^= 1u) {
+    if (warp < 4) {
+      // ---- K tile (row = key, 32 d) and V^T tile (row = d, 128 keys = 2 atoms of 64)
+      const int kj = k0 + tid;
+      uint4 kv[4], vv[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { kv[c] = make_uint4(0u, 0u, 0u, 0u); vv[c] = make_uint4(0u, 0u, 0u, 0u); }
+      if (kj < L) {
+        const h16* kr = base + (long long)kj * qkv.pitch + 128 + h * 32;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { kv[c] = __ldcg(reinterpret_cast<const uint4*>(kr + 8 * c)); vv[c] = __ldcg(reinterpret_cast<const uint4*>(kr + 128 + 8 * c)); }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + FT_K + sw128(tid, c)), "r"(kv[c].x), "r"(kv[c].y), "r"(kv[c].z), "r"(kv[c].w) : "memory");
+      const uint32_t atom = (uint32_t)tid >> 6, kc = (uint32_t)tid & 63u;          // key column inside its 64-key atom
+      const unsigned short* ve = reinterpret_cast<const unsigned short*>(vv);
+#pragma unroll
+      for (int d = 0; d < 32; ++d)
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(sbase + FT_VT + atom * 4096u + sw128((uint32_t)d, kc >> 3) + (kc & 7u) * 2u), "h"(ve[d]) : "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 4) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (a_elect_one()) {
+        const uint64_t ad = a_desc(sbase + FT_Q), bd = a_desc(sbase + FT_K);
+        a_mma(tmem, ad, bd, idesc_s, 0u);
+        a_mma(tmem, ad + 2, bd + 2, idesc_s, 1u);
+        a_commit(&s_bar);
+      }
+      __syncwarp();
+    } else {
+      a_mbar_wait(&s_bar, ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // ---- online softmax over this tile's 128 scores of the thread's query row
+      const int nvalid = min(128, L - k0);
+      float mx = m_run;
+#pragma unroll
+      for (int cb = 0; cb < 128; cb += 32) {
+        uint32_t r0[16], r1[16];
+        a_ld16(tlane + (uint32_t)cb, r0); a_ld16(tlane + (uint32_t)cb + 16u, r1);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (cb + i < nvalid) mx = fmaxf(mx, __uint_as_float(r0[i]));
+          if (cb + 16 + i < nvalid) mx = fmaxf(mx, __uint_as_float(r1[i]));
+        }
+      }
+      const float corr = __expf(m_run - mx);          // exp(-inf) = 0 on the first tile
+      float psum = 0.f;
+#pragma unroll
+      for (int cb = 0; cb < 128; cb += 32) {
+        uint32_t r0[16], r1[16];
+        a_ld16(tlane + (uint32_t)cb, r0); a_ld16(tlane + (uint32_t)cb + 16u, r1);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float p[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          p[i] = cb + i < nvalid ? __expf(__uint_as_float(r0[i]) - mx) : 0.f;
+          p[16 + i] = cb + 16 + i < nvalid ? __expf(__uint_as_float(r1[i]) - mx) : 0.f;
+        }
+        // the sum uses the values the tensor core will see (rounded to 16 bits), like a softmax computed in that precision would
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const h162 pr = ff2h2(p[8 * c + 2 * i], p[8 * c + 2 * i + 1]);
+            const float2 back = h22ff(pr);
+            psum += back.x + back.y;
+            w[i] = *reinterpret_cast<const uint32_t*>(&pr);
+          }
+          const uint32_t chunk = (uint32_t)(cb >> 3) + (uint32_t)c;       // 16-byte chunk (8 keys) of the 128-key row
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                       ::"r"(sbase + FT_P + (chunk >> 3) * 16384u + sw128((uint32_t)tid, chunk & 7u)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+        }
+      }
+      l_run = l_run * corr + psum;
+      m_run = mx;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) o[d] *= corr;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 4) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (a_elect_one()) {
+#pragma unroll
+        for (int at = 0; at < 2; ++at) {
+          const uint64_t ad = a_desc(sbase + FT_P + (uint32_t)at * 16384u), bd = a_desc(sbase + FT_VT + (uint32_t)at * 4096u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) a_mma(tmem + 128u, ad + 2 * k, bd + 2 * k, idesc_o, (at | k) ? 1u : 0u);
+        }
+        a_commit(&o_bar);
+      }
+      __syncwarp();
+    } else {
+      a_mbar_wait(&o_bar, ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t r0[16], r1[16];
+      a_ld16(tlane + 128u, r0); a_ld16(tlane + 144u, r1);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { o[i] += __uint_as_float(r0[i]); o[16 + i] += __uint_as_float(r1[i]); }
+    }
+    // the next iteration's stores into K / V^T / P happen after every row thread passed o_bar (all MMAs of this tile are complete)
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+  }
+  if (warp < 4) {
+    const int qi = q0 + tid;
+    if (qi < L) {
+      const float inv = 1.f / l_run;
+      h16* orow = out.p + (long long)b * out.bstride + (long long)qi * out.pitch + h * 32;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 w;
+        h162* hp = reinterpret_cast<h162*>(&w);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) hp[i] = ff2h2(o[8 * c + 2 * i] * inv, o[8 * c + 2 * i + 1] * inv);
+        *reinterpret_cast<uint4*>(orow + 8 * c) = w;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+}
+
+}  // namespace
+
+int fullattn_tc_launch(ClView qkv, ClView out, int B, int L, cudaStream_t st) {
+  static unsigned long long attr = 0;
+  if (ladiff_first_on_device(&attr)) {
+    LADIFF_CUDA_OK(cudaFuncSetAttribute(fullattn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
+    prefer_max_smem_carveout(fullattn_tc_kernel);
+  }
+  LADIFF_CUDA_OK(launch_pdl(fullattn_tc_kernel, dim3(cdiv(L, 128), 4, B), dim3(FT_THREADS), (size_t)FT_SMEM, st, qkv, out, L));
+  return 0;
+}

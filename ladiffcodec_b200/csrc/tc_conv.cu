@@ -1030,8 +1030,11 @@ int tc_conv_plan(const TcConvDesc& d, TcConvParams* pp, TcRefView* rv) {
   p.stage_bytes = p.a_cap * (int)A_BYTES + p.b_slot_bytes;
   // shared-memory budget: S pipeline stages + 2 epilogue staging chunks per epilogue warpgroup + 1 KB alignment + 1 KB tap over-read.
   // Smaller staging chunks (32 rows) are used when they buy another pipeline stage.
+  // LADIFF_TC_SMEM_KB caps a conv CTA's shared memory: what it leaves free lets the small kernels of ANOTHER stream (a second batch
+  // in flight) become resident next to a running conv CTA instead of waiting for the conv to drain
+  static const long smem_cap = getenv("LADIFF_TC_SMEM_KB") ? atol(getenv("LADIFF_TC_SMEM_KB")) * 1024 : (long)kSmemLimit;
   auto stages_for = [&](int cr) {
-    const long rest = (long)(d.want_two_per_sm ? kSmemLimit2 : kSmemLimit) - 2048 - (p.direct ? (d.res ? (long)p.NMMA * 256 : 0) : (long)2 * kEpiGroups * cr * 256);
+    const long rest = (long)(d.want_two_per_sm ? kSmemLimit2 : (smem_cap < (long)kSmemLimit ? smem_cap : (long)kSmemLimit)) - 2048 - (p.direct ? (d.res ? (long)p.NMMA * 256 : 0) : (long)2 * kEpiGroups * cr * 256);
     const int s2 = (int)(rest / p.stage_bytes);
     return s2 > kMaxStages ? kMaxStages : s2;
   };

@@ -1000,7 +1000,24 @@ int linattn_launch(ClView qkv, float* ctx, float* part, int* counters, ClView ou
   return 0;
 }
 
+// impl: 1 tiled SIMT (online softmax), 2 SIMT with the keys resident in shared memory (L <= FA2_MAX_KEYS), 3 tcgen05
+int fullattn_launch_impl(ClView qkv, ClView out, int B, int L, int impl, cudaStream_t st) {
+  if (impl == 3) return fullattn_tc_launch(qkv, out, B, L, st);
+  if (impl == 2) {
+    LADIFF_REQUIRE(L <= FA2_MAX_KEYS, LADIFF_ERR_ARG, "fullattn2: L=%d > %d", L, FA2_MAX_KEYS);
+    const size_t smem = (size_t)L * 64 * sizeof(float);
+    LADIFF_CUDA_OK(cudaFuncSetAttribute(fullattn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA2_MAX_KEYS * 64 * (int)sizeof(float)));
+    LADIFF_CUDA_OK(launch_pdl(fullattn2_kernel, dim3(cdiv(L, 128), 4, B), dim3(128), smem, st, qkv, out, L));
+    return 0;
+  }
+  LADIFF_CUDA_OK(launch_pdl(fullattn_kernel, dim3(cdiv(L, 32), 4, B), dim3(256), 0, st, qkv, out, L));
+  return 0;
+}
+
 int fullattn_launch(ClView qkv, ClView out, int B, int L, cudaStream_t st) {
+  // LADIFF_ATTN_TC_MIN: bottleneck length from which QK^T / PV run on tcgen05 (default: beyond what the keys-in-smem SIMT kernel holds)
+  static const int tc_min = getenv("LADIFF_ATTN_TC_MIN") ? atoi(getenv("LADIFF_ATTN_TC_MIN")) : FA2_MAX_KEYS + 1;
+  if (L >= tc_min && qkv.pitch % 8 == 0 && out.pitch % 8 == 0) return fullattn_tc_launch(qkv, out, B, L, st);
   static const bool no_fa2 = getenv("LADIFF_NO_FA2") != nullptr;
   if (L <= FA2_MAX_KEYS && !no_fa2) {
     const size_t smem = (size_t)L * 64 * sizeof(float);

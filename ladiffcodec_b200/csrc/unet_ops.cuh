@@ -40,6 +40,9 @@ int linattn_launch(ClView qkv, float* ctx, float* part, int* counters, ClView ou
 size_t linattn_part_floats(int B, int L);
 // Attention core (mid block)                                    unet.py:234-245
 int fullattn_launch(ClView qkv, ClView out, int B, int L, cudaStream_t st);
+int fullattn_launch_impl(ClView qkv, ClView out, int B, int L, int impl, cudaStream_t st);
+// the same on the tensor cores (csrc/attn_tc.cu: tcgen05 QK^T and PV, flash-attention style); fullattn_launch picks it for long bottlenecks
+int fullattn_tc_launch(ClView qkv, ClView out, int B, int L, cudaStream_t st);
 
 // layout conversion / DDPM
 // x NCL f32 [B][C][L] * scale[b] -> channels-last h16 view (channel offset via out.p)

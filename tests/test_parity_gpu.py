@@ -437,3 +437,58 @@ def test_unet_lengths_around_the_multi_clip_tile_boundary(L):
     m.set_conv_impl(0)
     del m, c
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("B,L", [(2, 75), (1, 300), (3, 129), (1, 1000), (1, 4375), (2, 17)])
+def test_full_attention_operator_tcgen05_and_simt(B, L):
+    """Mid-block attention core (unet.py:238-245) on the tensor cores (tcgen05 QK^T and PV) and on the two SIMT kernels against torch
+    on the same 16-bit-rounded q, k, v: ragged lengths, several clips, the 35 s utterance's bottleneck (n = 4375)."""
+    from ladiffcodec_b200 import _lib
+    lib = _lib.get_lib()
+    h16 = _lib.act_dtype()
+    g = torch.Generator().manual_seed(B * 1000 + L)
+    qkv = (torch.randn(B, L, 384, generator=g) * 1.5).to(h16)
+    q, k, v = [t.float().reshape(B, L, 4, 32).permute(0, 2, 1, 3) for t in qkv.split(128, dim=2)]      # [B, h, L, d]
+    sim = torch.einsum("bhid,bhjd->bhij", q * 32 ** -0.5, k)
+    ref = torch.einsum("bhij,bhjd->bhid", sim.softmax(dim=-1), v).permute(0, 2, 1, 3).reshape(B, L, 128)
+    qd = qkv.cuda()
+    P = ctypes.c_void_p
+    for impl in (3, 1, 2, 0):
+        if impl == 2 and L > 512:
+            continue
+        out = torch.full((B, L, 128), float("nan"), dtype=h16, device="cuda")
+        rc = lib.ladiff_op_fullattn(P(qd.data_ptr()), P(out.data_ptr()), B, L, impl)
+        assert rc == 0, lib.ladiff_last_error()
+        err = (out.float().cpu() - ref).abs().max().item()
+        tol = (4e-3 if h16 == torch.float16 else 3e-2) * max(1.0, ref.abs().max().item())
+        assert err < tol, (B, L, impl, err)
+
+
+def test_35s_utterance_against_oracle():
+    """SURVEY §8f rank 1 at the length the reference's script meets on real LibriSpeech files: a 35 s utterance (T = 560 000 samples,
+    Layout-A latent L = 70 000, bottleneck attention over n = 4375 positions -> the tcgen05 attention kernel; encoder LSTM over 1750
+    frames, decoder LSTM over 70 000 steps) through the one-call entry, against the oracle."""
+    from ladiffcodec_b200.config import readme_args
+    from ladiffcodec_b200.sample import synthesize
+    args = readme_args()
+    sdm = pc.make_state_dict(seed=11, **pc.ladiff_model_kwargs(args))
+    sdc = pc.make_state_dict(seed=12, **pc.cond_model_kwargs(args))
+    m, c = pc.cuda_models(args, sdm, sdc)
+    T, n_steps = 640 * 875, 2
+    wav = pc.make_clips(1, T, seed=35)
+    L = T // 8
+    noise = torch.randn(n_steps - 1, 1, 128, L, generator=torch.Generator().manual_seed(4))
+    out, lat = synthesize(m, c, wav.cuda(), n_steps=n_steps, noise=noise, return_latent=True)
+    ws_gb = m._lib.ladiff_synthesize_workspace_bytes(m._h, c._h, 1, T) / 2 ** 30
+    stages = {}
+    with torch.no_grad():
+        ref = O.synthesize(wav, sdm, sdc, n_steps=n_steps, noise=noise, cond_bandwidth=args.cond_bandwidth,
+                           enc_ratios=args.enc_ratios, upsampling_ratios=args.upsampling_ratios, diff_dims=args.diff_dims,
+                           unet_scale_cond=args.unet_scale_cond, fast_lstm=True, stages=stages)
+    pc.record("long_utterance_35s", latent_rel_l2=pc.rel_l2(lat, stages["latent"]), wav_snr_db=pc.snr_db(out, ref), workspace_gib=ws_gb,
+              bottleneck_n=L // 16)
+    assert out.shape == (1, 1, T)
+    assert pc.rel_l2(lat, stages["latent"]) <= pc.TOL["latent_rel_l2"]
+    assert pc.snr_db(out, ref) >= pc.TOL["wav_snr_db"]
+    del m, c
+    torch.cuda.empty_cache()
