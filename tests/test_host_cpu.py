@@ -107,3 +107,31 @@ def test_product_does_not_import_the_oracle():
         if f.endswith(".py"):
             src = open(os.path.join(pkg, f)).read()
             assert "oracle" not in src.replace("# oracle", ""), f
+
+
+def test_ddim_time_grid_equals_the_references(lib):
+    """ladiff_ddim_times restates torch.linspace(-1, T-1, S+1).int() reversed (ddpm_loss.py:273-274) in C: every S in 1..1000."""
+    for S in list(range(1, 200)) + [250, 333, 500, 999, 1000]:
+        out = (ctypes.c_int32 * (S + 1))()
+        assert lib.ladiff_ddim_times(1000, S, out) == 0
+        ref = list(reversed(torch.linspace(-1, 999, steps=S + 1).int().tolist()))
+        assert list(out) == ref, S
+
+
+def test_sampler_surface_exists_and_refuses_what_the_reference_cannot_run():
+    from ladiffcodec_b200.model import GaussianDiffusion1D
+    for name in ("p_sample", "p_sample_loop", "sample", "ddim_sample", "infilling", "halfway_sampling", "q_sample", "p_losses", "forward"):
+        assert callable(getattr(GaussianDiffusion1D, name)), name
+    import inspect
+    sig = inspect.signature(GaussianDiffusion1D.infilling)
+    for arg in ("infill_img", "condition", "midway_t", "noise", "offset", "lam"):          # ddpm_loss.py:331
+        assert arg in sig.parameters, arg
+
+
+def test_bench_refuses_a_gpu_count_it_was_not_launched_with():
+    import subprocess, sys
+    env = dict(os.environ, WORLD_SIZE="1", RANK="0", LOCAL_RANK="0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--gpus", "2", "--steps", "1"], capture_output=True, text=True,
+                       timeout=300, cwd=ROOT, env=env)
+    assert r.returncode != 0
+    assert ("--gpus 2 but WORLD_SIZE=1" in (r.stderr + r.stdout)) or ("no CUDA device" in (r.stderr + r.stdout))
