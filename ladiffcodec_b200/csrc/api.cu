@@ -973,7 +973,23 @@ struct PlanBuilder {
     if (!pre_normed) TRY(layernorm(x, a.norm_g, none, ln, L));
     TRY(conv(a.qkv, ln, L, qkv, nullptr, false, nullptr, none));
     const int BB = B; float* ctx = u.ctx; float* lap = u.la_part; int* lac = u.la_cnt;
-    if (linear) {
+    // opt-in (LADIFF_ATTN_TAIL=1): parity-green but 15 % SLOWER per DDPM step at config 2 than the three kernels it replaces — one
+    // 123 KB CTA per SM runs its phases (SIMT context product, weight staging, MMA, two LayerNorm sweeps) back to back with nothing
+    // to overlap them
+    static const bool fuse_tail = getenv("LADIFF_ATTN_TAIL") != nullptr;
+    if (linear && fuse_tail && a.C % 256 == 0 && a.C <= 1024) {
+      // context, then ONE kernel for ctx^T softmax(q) -> to_out 1x1 (tcgen05) -> LayerNorm -> + x
+      H* hg = h;
+      pl->ops.push_back([qkv, ctx, lap, lac, BB, L, hg](cudaStream_t st) { return ((hg->skip_ops | g_skip_env()) & 4) ? 0 : linattn_ctx_launch(qkv, ctx, lap, lac, BB, L, st); });
+      label("linattn ctx L=%d", L, 0, 0, 0);
+      const h16* wout = a.out.w; const float* bo = a.out.bias; const float* go = a.out_g; const int C = a.C;
+      pl->ops.push_back([qkv, ctx, wout, bo, go, x, out, BB, L, C, hg](cudaStream_t st) {
+        return ((hg->skip_ops | g_skip_env()) & 4) ? 0 : linattn_tail_launch(qkv, ctx, wout, bo, go, x, out, BB, L, C, st);
+      });
+      label("linattn tail (out + to_out 1x1 + LN + res) C=%d L=%d", a.C, L, 0, 0);
+      pl->op_flops.resize(pl->ops.size(), 0.0);
+      pl->launches_per_run += 2;
+    } else if (linear) {
       H* hg = h;
       pl->ops.push_back([qkv, ctx, lap, lac, ao, BB, L, hg](cudaStream_t st) { return ((hg->skip_ops | g_skip_env()) & 4) ? 0 : linattn_launch(qkv, ctx, lap, lac, ao, BB, L, st); });
       label("linattn(ctx+out) L=%d", L, 0, 0, 0);

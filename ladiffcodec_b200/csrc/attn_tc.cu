@@ -241,6 +241,202 @@ __global__ void __launch_bounds__(FT_THREADS) fullattn_tc_kernel(ClView qkv, ClV
   if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
 }
 
+// ================================================================================================ linear-attention tail
+// Everything of Residual(PreNorm(LinearAttention)) (unet.py:208-222, 50-56) after the context matrix, in ONE kernel:
+//   out[e, n] = sum_d ctx[h][d][e] softmax_d(q[h, :, n])[d]      (SIMT: thread = (head, position), ctx broadcast from shared memory)
+//   y = W_out out + b                                            (tcgen05: D[128 positions, C] = A[128, 128] W^T, K = 128)
+//   z = LayerNorm_c(y) g + x                                     (row-owning epilogue threads: statistics and the write from TMEM)
+// replacing three launches (linattn_out_kernel, the 1x1 to_out conv, layernorm_cl_kernel) and the y / out round trips.
+// CTA = 128 positions of one clip; 16 warps: warp w -> head w >> 2, rows 32 (w & 3) + lane; warps 0-3 also run the epilogue
+// (TMEM lane quadrant = warp & 3); warp 16 allocates TMEM and issues the MMAs.  C output channels in chunks of 256 (one MMA N);
+// C <= 512 stays resident in TMEM for the two LayerNorm sweeps, C = 1024 is computed twice (K is only 128).
+constexpr int LT_THREADS = 544;
+constexpr uint32_t LT_CTX = 0, LT_A = 16384, LT_W = 49152, LT_PAR = 114688, LT_SMEM = 114688 + 8192 + 1024;
+
+__global__ void __launch_bounds__(LT_THREADS) linattn_tail_kernel(ClView qkv, const float* __restrict__ ctx, const h16* __restrict__ wout,
+                                                                   const float* __restrict__ bias, const float* __restrict__ gain, ClView xres,
+                                                                   ClView out, int L, int C) {
+  extern __shared__ uint8_t lt_raw[];
+  __shared__ __align__(8) uint64_t m_bar;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int b = blockIdx.y, n0 = blockIdx.x * 128;
+  const uint32_t sbase = (a_smem_u32(lt_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = lt_raw + (sbase - a_smem_u32(lt_raw));
+  float* cs = reinterpret_cast<float*>(sgen + LT_CTX);              // [4][32][32]
+  float* s_bias = reinterpret_cast<float*>(sgen + LT_PAR);           // [C]
+  float* s_gain = s_bias + 1024;                                     // [C]
+  if (tid == 0) {
+    a_mbar_init(&m_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 16) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(a_smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = tid; i < C; i += LT_THREADS) { s_bias[i] = bias ? __ldg(bias + i) : 0.f; s_gain[i] = __ldg(gain + i); }   // parameters: before the wait
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  pdl_wait();
+  pdl_trigger();
+  // ---- phase A: context to shared memory, out = ctx^T softmax(q) as the 16-bit A operand
+  if (warp < 16) {
+    const float4* src = reinterpret_cast<const float4*>(ctx + (long long)b * 4096);
+    float4* dst = reinterpret_cast<float4*>(cs);
+    for (int i = tid; i < 1024; i += 512) dst[i] = __ldcg(src + i);
+  }
+  const int h = warp >> 2, r = (warp & 3) * 32 + lane, n = n0 + r;
+  uint4 qraw[4];
+  if (warp < 16 && n < L) {
+    const h16* qr = qkv.p + (long long)b * qkv.bstride + (long long)n * qkv.pitch + h * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) qraw[i] = __ldcg(reinterpret_cast<const uint4*>(qr + 8 * i));
+  }
+  __syncthreads();
+  if (warp < 16) {
+    uint4 w4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w4[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (n < L) {
+      float q[32];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const h162* hp = reinterpret_cast<const h162*>(&qraw[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 f = h22ff(hp[j]); q[8 * i + 2 * j] = f.x; q[8 * i + 2 * j + 1] = f.y; }
+      }
+      float mx = q[0];
+#pragma unroll
+      for (int i = 1; i < 32; ++i) mx = fmaxf(mx, q[i]);
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { q[i] = __expf(q[i] - mx); sum += q[i]; }
+      const float inv = 1.f / sum;
+      float acc[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) acc[e] = 0.f;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) {
+        const float pd = q[d] * inv;
+        const float4* c4 = reinterpret_cast<const float4*>(cs + (h * 32 + d) * 32);
+#pragma unroll
+        for (int e4 = 0; e4 < 8; ++e4) {
+          const float4 c = c4[e4];
+          acc[4 * e4 + 0] += pd * c.x; acc[4 * e4 + 1] += pd * c.y;
+          acc[4 * e4 + 2] += pd * c.z; acc[4 * e4 + 3] += pd * c.w;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        h162* hp = reinterpret_cast<h162*>(&w4[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hp[j] = ff2h2(acc[8 * i + 2 * j], acc[8 * i + 2 * j + 1]);
+      }
+    }
+    // channels h*32 .. +31 of row r: atom h >> 1 (64 channels each), 16-byte chunks (h & 1) * 4 + i
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                   ::"r"(sbase + LT_A + (uint32_t)(h >> 1) * 16384u + sw128((uint32_t)r, (uint32_t)((h & 1) * 4 + i))), "r"(w4[i].x), "r"(w4[i].y),
+                     "r"(w4[i].z), "r"(w4[i].w) : "memory");
+  }
+  // ---- phase B: y = W_out out (+ b), LayerNorm statistics, normalise + residual, per half of <= 512 channels
+  const uint32_t idesc = (1u << 4) | (TC_IDESC_AB_FMT << 7) | (TC_IDESC_AB_FMT << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+  const int nchunk = C / 256, nhalf = nchunk > 2 ? nchunk / 2 : 1, cph = nchunk / nhalf;     // chunks per half (1 or 2)
+  const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  float s1 = 0.f, s2 = 0.f, mean = 0.f, rstd = 0.f;
+  uint32_t ph = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int hf = 0; hf < nhalf; ++hf) {
+      if (pass == 0 || nhalf > 1) {
+        for (int cc = 0; cc < cph; ++cc) {
+          const int ch0 = (hf * cph + cc) * 256;
+          if (warp < 16) {        // W chunk: rows ch0 .. +255, K = 128 as two 64-wide atoms
+            for (int i = tid; i < 4096; i += 512) {
+              const int row = i >> 4, c16 = i & 15;
+              const uint4 v = __ldg(reinterpret_cast<const uint4*>(wout + (long long)(ch0 + row) * 128 + c16 * 8));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                           ::"r"(sbase + LT_W + (uint32_t)(c16 >> 3) * 32768u + sw128((uint32_t)row, (uint32_t)(c16 & 7))), "r"(v.x), "r"(v.y), "r"(v.z),
+                             "r"(v.w) : "memory");
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          }
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncthreads();
+          if (warp == 16) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (a_elect_one()) {
+#pragma unroll
+              for (int at = 0; at < 2; ++at) {
+                const uint64_t ad = a_desc(sbase + LT_A + (uint32_t)at * 16384u), bd = a_desc(sbase + LT_W + (uint32_t)at * 32768u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) a_mma(tmem + (uint32_t)cc * 256u, ad + 2 * k, bd + 2 * k, idesc, (at | k) ? 1u : 0u);
+              }
+              a_commit(&m_bar);
+            }
+            __syncwarp();
+          }
+          a_mbar_wait(&m_bar, ph);      // every thread: the W buffer may be refilled, the accumulator read
+          ph ^= 1u;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+      }
+      if (warp < 4) {
+        for (int cc = 0; cc < cph; ++cc) {
+          const int ch0 = (hf * cph + cc) * 256;
+          for (int c0 = 0; c0 < 256; c0 += 32) {
+            uint32_t r0[16], r1[16];
+            a_ld16(tlane + (uint32_t)(cc * 256 + c0), r0); a_ld16(tlane + (uint32_t)(cc * 256 + c0 + 16), r1);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (pass == 0) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float v0 = __uint_as_float(r0[i]) + s_bias[ch0 + c0 + i], v1 = __uint_as_float(r1[i]) + s_bias[ch0 + c0 + 16 + i];
+                s1 += v0 + v1; s2 = fmaf(v0, v0, fmaf(v1, v1, s2));
+              }
+            } else if (n0 + (int)tid < L) {
+              const long long rowoff = (long long)(n0 + (int)tid);
+              const h16* xr = xres.p + (long long)b * xres.bstride + rowoff * xres.pitch + ch0 + c0;
+              h16* orow = out.p + (long long)b * out.bstride + rowoff * out.pitch + ch0 + c0;
+#pragma unroll
+              for (int g8 = 0; g8 < 4; ++g8) {
+                const uint4 xv = __ldcg(reinterpret_cast<const uint4*>(xr + 8 * g8));
+                const h162* xh = reinterpret_cast<const h162*>(&xv);
+                uint4 ov;
+                h162* oh = reinterpret_cast<h162*>(&ov);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int i0 = 8 * g8 + 2 * j;
+                  const float a0 = __uint_as_float(i0 < 16 ? r0[i0 & 15] : r1[i0 & 15]) + s_bias[ch0 + c0 + i0];
+                  const float a1 = __uint_as_float(i0 + 1 < 16 ? r0[(i0 + 1) & 15] : r1[(i0 + 1) & 15]) + s_bias[ch0 + c0 + i0 + 1];
+                  const float2 xf = h22ff(xh[j]);
+                  oh[j] = ff2h2((a0 - mean) * rstd * s_gain[ch0 + c0 + i0] + xf.x, (a1 - mean) * rstd * s_gain[ch0 + c0 + i0 + 1] + xf.y);
+                }
+                *reinterpret_cast<uint4*>(orow + 8 * g8) = ov;
+              }
+            }
+          }
+        }
+      }
+      if (nhalf > 1) {          // the next half's MMAs overwrite the accumulator: all reads of this half are done
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+      }
+    }
+    if (pass == 0) {
+      mean = s1 / (float)C;
+      float var = s2 / (float)C - mean * mean;
+      var = var < 0.f ? 0.f : var;
+      rstd = rsqrtf(var + 1e-5f);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 16) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
 }  // namespace
 
 int fullattn_tc_launch(ClView qkv, ClView out, int B, int L, cudaStream_t st) {
@@ -250,5 +446,20 @@ int fullattn_tc_launch(ClView qkv, ClView out, int B, int L, cudaStream_t st) {
     prefer_max_smem_carveout(fullattn_tc_kernel);
   }
   LADIFF_CUDA_OK(launch_pdl(fullattn_tc_kernel, dim3(cdiv(L, 128), 4, B), dim3(FT_THREADS), (size_t)FT_SMEM, st, qkv, out, L));
+  return 0;
+}
+
+// wout: the to_out 1x1 conv's packed 16-bit weights [C][128]; bias [C] or null; gain [C] = to_out.1.g
+int linattn_tail_launch(ClView qkv, const float* ctx, const h16* wout, const float* bias, const float* gain, ClView xres, ClView out, int B,
+                        int L, int C, cudaStream_t st) {
+  LADIFF_REQUIRE(C % 256 == 0 && C <= 1024 && qkv.pitch % 8 == 0 && xres.pitch % 8 == 0 && out.pitch % 8 == 0, LADIFF_ERR_ARG,
+                 "linattn_tail: C=%d", C);
+  static unsigned long long attr = 0;
+  if (ladiff_first_on_device(&attr)) {
+    LADIFF_CUDA_OK(cudaFuncSetAttribute(linattn_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM));
+    prefer_max_smem_carveout(linattn_tail_kernel);
+  }
+  LADIFF_CUDA_OK(launch_pdl(linattn_tail_kernel, dim3(cdiv(L, 128), B), dim3(LT_THREADS), (size_t)LT_SMEM, st, qkv, ctx, wout, bias, gain, xres,
+                            out, L, C));
   return 0;
 }

@@ -1000,6 +1000,14 @@ int linattn_launch(ClView qkv, float* ctx, float* part, int* counters, ClView ou
   return 0;
 }
 
+int linattn_ctx_launch(ClView qkv, float* ctx, float* part, int* counters, int B, int L, cudaStream_t st) {
+  int S, ns;
+  linattn_split(B, L, &S, &ns);
+  LADIFF_CARVEOUT_ONCE(linattn_ctx_kernel);
+  LADIFF_CUDA_OK(launch_pdl(linattn_ctx_kernel, dim3(ns, 4, B), dim3(256), 0, st, qkv, ctx, part, counters, L, S, ns));
+  return 0;
+}
+
 // impl: 1 tiled SIMT (online softmax), 2 SIMT with the keys resident in shared memory (L <= FA2_MAX_KEYS), 3 tcgen05
 int fullattn_launch_impl(ClView qkv, ClView out, int B, int L, int impl, cudaStream_t st) {
   if (impl == 3) return fullattn_tc_launch(qkv, out, B, L, st);

@@ -38,6 +38,11 @@ int layernorm_cl_launch(ClView x, const float* g, ClView res, ClView out, int B,
 // part scratch linattn_part_floats(B, L) f32; counters [4B] int32, zero before the first launch (the kernel re-zeroes them)
 int linattn_launch(ClView qkv, float* ctx, float* part, int* counters, ClView out, int B, int L, cudaStream_t st);
 size_t linattn_part_floats(int B, int L);
+// the two halves separately: context only, and (csrc/attn_tc.cu) everything after it in one kernel — ctx^T softmax(q), the to_out 1x1
+// conv on tcgen05, channel LayerNorm and the residual:  out = LN(W_out (ctx^T q~) + b) g + xres
+int linattn_ctx_launch(ClView qkv, float* ctx, float* part, int* counters, int B, int L, cudaStream_t st);
+int linattn_tail_launch(ClView qkv, const float* ctx, const h16* wout, const float* bias, const float* gain, ClView xres, ClView out, int B,
+                        int L, int C, cudaStream_t st);
 // Attention core (mid block)                                    unet.py:234-245
 int fullattn_launch(ClView qkv, ClView out, int B, int L, cudaStream_t st);
 int fullattn_launch_impl(ClView qkv, ClView out, int B, int L, int impl, cudaStream_t st);

@@ -492,3 +492,26 @@ def test_35s_utterance_against_oracle():
     assert pc.snr_db(out, ref) >= pc.TOL["wav_snr_db"]
     del m, c
     torch.cuda.empty_cache()
+
+
+def test_fused_linear_attention_tail_operator_level():
+    """The opt-in fused tail of the linear-attention block (ctx^T softmax(q) -> to_out 1x1 on tcgen05 -> LayerNorm -> + x in one kernel,
+    LADIFF_ATTN_TAIL=1) against the default three-kernel form: run in a subprocess so that the environment switch is seen at plan time."""
+    import os, subprocess, sys
+    code = (
+        "import sys, torch; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import parity_common as pc\n"
+        "fx, args, sdm, sdc, wav, noise = pc.case_setup('B_3kbps')\n"
+        "m, c = pc.cuda_models(args, sdm, sdc)\n"
+        "from oracle import ladiff_oracle as O\n"
+        "B = fx['B']\n"
+        "img = pc.normalized_img(fx['cond'], sdm, args)\n"
+        "tp = torch.full((B,), fx['t_probe'], dtype=torch.long)\n"
+        "with torch.no_grad(): eo = O.unet_forward(img, tp, fx['cond'], sdm, **pc.unet_kwargs(args))\n"
+        "e = m.diff_model(img.cuda(), tp.cuda(), fx['cond'].cuda()).cpu()\n"
+        "print('REL', pc.rel_l2(e, eo))\n"
+    ) % (pc.ROOT, os.path.join(pc.ROOT, "tests"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=dict(os.environ, LADIFF_ATTN_TAIL="1"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    rel = float([l for l in r.stdout.splitlines() if l.startswith("REL")][0].split()[1])
+    assert rel <= pc.TOL["unet_rel_l2"], rel
