@@ -215,7 +215,8 @@ int32_t ladiff_normalize_clips(float* x, int32_t B, int64_t n, int32_t mode, voi
  * layout), zero padding (k-1)/2, stride 1 → y [B,L,Cout] (f16, or fp32 if y_f32).  impl 0 = tcgen05,
  * 1 = SIMT check kernel (same packed operands), 2 = tcgen05 with per-tap activation tiles, 3 = tcgen05 positions-on-M
  * kernel, 4 = the same with a cta_group::2 CTA pair per tile,
- * 5 = channels-on-M kernel shaped for two CTAs per SM (small-K convs only).  Allocates and frees its own scratch; synchronises. */
+ * 5 = channels-on-M kernel shaped for two CTAs per SM (small-K convs only), 6 = channels-on-M kernel as CTA pairs along N that
+ * share every weight tile through TMA multicast.  Allocates and frees its own scratch; synchronises. */
 int32_t ladiff_op_conv1d_cl(const void* x_h16, const float* w, const float* bias, int32_t B, int32_t L,
                             int32_t Cin, int32_t Cout, int32_t k, void* y, int32_t y_f32, int32_t impl,
                             float* gn_stats /* [B,Cout/32,2] or NULL */);

@@ -844,7 +844,7 @@ struct PlanBuilder {
     if (tuned_it != h->tuned.end() && h->conv_impl == 0) {        // an earlier plan of this handle already timed this conv
       const std::vector<int>& c = tuned_it->second;
       TcConvDesc dc = d;
-      dc.want_nt = c[0]; dc.want_nclip = c[1]; dc.want_two_per_sm = c[2]; dc.want_transposed = c[3];
+      dc.want_nt = c[0]; dc.want_nclip = c[1]; dc.want_two_per_sm = c[2]; dc.want_transposed = c[3]; dc.want_pair = c[4];
       TcConvParams pc2; TcRefView rv2;
       if (tc_conv_plan(dc, &pc2, &rv2) == 0) { ps = pc2; rv = rv2; }
     } else
@@ -887,8 +887,21 @@ struct PlanBuilder {
         if (force_t && pc2.transposed == force_t) { best_ms = 0.f; best = pc2; best_rv = rv2; continue; }
         if (ms < best_ms && ms < 0.97f * base_ms) { best_ms = ms; best = pc2; best_rv = rv2; }
       }
+      static const bool no_pair = getenv("LADIFF_NO_PAIR") != nullptr;
+      if (!no_pair && !best.transposed && best.minb == 1 && best.n_ntiles >= 2) {
+        // the chosen shape as CTA pairs along N that share every weight tile through TMA multicast (half the weight bytes per SM)
+        TcConvDesc dc = d;
+        dc.want_nt = best.NCLIP == 1 ? best.NT : 0; dc.want_nclip = best.NCLIP > 1 ? best.NCLIP : 0; dc.want_pair = 1;
+        TcConvParams pc2; TcRefView rv2;
+        if (tc_conv_plan(dc, &pc2, &rv2) == 0 && pc2.NT == best.NT && pc2.NCLIP == best.NCLIP) {
+          float ms = 0.f;
+          TRY(time_one(pc2, &ms));
+          static const bool force_pair = getenv("LADIFF_FORCE_PAIR") != nullptr;
+          if (force_pair || ms < 0.97f * best_ms) { best_ms = ms; best = pc2; best_rv = rv2; }
+        }
+      }
       ps = best; rv = best_rv;
-      h->tuned[tkey] = std::vector<int>{ps.transposed ? 0 : (ps.NCLIP == 1 ? ps.NT : 0), ps.NCLIP > 1 ? ps.NCLIP : 0, ps.minb == 2 ? 1 : 0, ps.transposed};
+      h->tuned[tkey] = std::vector<int>{ps.transposed ? 0 : (ps.NCLIP == 1 ? ps.NT : 0), ps.NCLIP > 1 ? ps.NCLIP : 0, ps.minb == 2 ? 1 : 0, ps.transposed, ps.pair};
     }
     d.tap_share = 0;
     d.want_nt = (ps.NCLIP == 1 && !ps.transposed) ? ps.NT : 0; d.want_nclip = ps.NCLIP > 1 ? ps.NCLIP : 0;
@@ -914,9 +927,9 @@ struct PlanBuilder {
     pl->op_label.resize(pl->ops.size());
     {
       char buf[200];
-      snprintf(buf, sizeof(buf), "conv kind=%d Cout=%d Cin=%d k=%d Lout=%d NT=%d nclip=%d tiles=%d S=%d taps/stage=%d stats=%d direct=%d posM=%d perSM=%d", pc.kind,
+      snprintf(buf, sizeof(buf), "conv kind=%d Cout=%d Cin=%d k=%d Lout=%d NT=%d nclip=%d tiles=%d S=%d taps/stage=%d stats=%d direct=%d posM=%d perSM=%d pair=%d", pc.kind,
                pc.CoutV, pc.Cin, pc.K, ps.Lout, ps.NT, ps.NCLIP, ps.transposed ? ps.n_chtiles * ps.n_ntiles : ps.MT * ps.n_ntiles, ps.S, ps.a_cap,
-               want_stats ? 1 : 0, ps.direct, ps.transposed ? ps.NCH : 0, ps.transposed ? 1 : ps.minb);
+               want_stats ? 1 : 0, ps.direct, ps.transposed ? ps.NCH : 0, ps.transposed ? 1 : ps.minb, ps.pair);
       pl->op_label.back() = buf;
     }
     pl->launches_per_run++;
@@ -1713,7 +1726,7 @@ extern "C" int32_t ladiff_op_conv1d_cl(const void* x_h16, const float* w, const 
                                        int32_t Cout, int32_t k, void* y, int32_t y_f32, int32_t impl, float* gn_stats) {
   LADIFF_REQUIRE(x_h16 && w && y && Cin % 64 == 0 && Cout % 128 == 0 && k >= 1 && k <= TC_MAX_TAPS && (k & 1), LADIFF_ERR_ARG,
                  "ladiff_op_conv1d_cl: Cin %% 64, Cout %% 128, odd k <= %d required", TC_MAX_TAPS);
-  LADIFF_REQUIRE(impl >= 0 && impl <= 5, LADIFF_ERR_ARG, "ladiff_op_conv1d_cl: impl=%d", impl);
+  LADIFF_REQUIRE(impl >= 0 && impl <= 6, LADIFF_ERR_ARG, "ladiff_op_conv1d_cl: impl=%d", impl);
   h16* wp = nullptr; float2* stats = nullptr;
   LADIFF_CUDA_OK(cudaMalloc((void**)&wp, sizeof(h16) * (size_t)Cout * Cin * k));
   int rc = pack_conv_launch(w, wp, Cout, Cin, k, 0, 0);
@@ -1727,6 +1740,7 @@ extern "C" int32_t ladiff_op_conv1d_cl(const void* x_h16, const float* w, const 
   else { d.out = (h16*)y; d.out_bstride = (long long)L * Cout; d.out_pitch = Cout; }
   d.B = B; d.tap_share = impl == 2 ? 0 : 1; d.want_transposed = impl == 3 ? 1 : (impl == 4 ? 2 : 0);
   if (impl == 5) { d.want_two_per_sm = 1; d.want_nt = 128; }
+  if (impl == 6) d.want_pair = 1;           // CTA pairs along N, weight tiles by TMA multicast
   TcConvParams p;
   TcRefView rv;
   if (!rc) rc = tc_conv_plan(d, &p, &rv);
@@ -1776,7 +1790,8 @@ extern "C" int32_t ladiff_op_conv1d_bench(const void* x_h16, const float* w, con
   d.kind = TC_KIND_PLAIN; d.Cin = Cin; d.K = k; d.CoutV = Cout; d.w = wp; d.tmW = &tmW; d.Ktot = Cin * k; d.bias = bias;
   d.x = (const h16*)x_h16; d.x_bstride = (long long)L * Cin; d.x_pitch = Cin; d.Lin = L;
   d.out = y; d.out_bstride = (long long)L * Cout; d.out_pitch = Cout;
-  d.B = B; d.tap_share = 1; d.want_nt = want_nt; d.want_nclip = want_nclip; d.want_two_per_sm = want_two; d.want_transposed = want_t;
+  d.B = B; d.tap_share = 1; d.want_nt = want_nt; d.want_nclip = want_nclip; d.want_two_per_sm = want_two == 1 ? 1 : 0; d.want_transposed = want_t;
+  d.want_pair = want_two == 2 ? 1 : 0;      // want_two: 1 = two CTAs per SM, 2 = multicast CTA pairs
   TcConvParams p;
   if (!rc) rc = tc_conv_plan(d, &p, nullptr);
   if (!rc && stats_on) {
@@ -1798,8 +1813,8 @@ extern "C" int32_t ladiff_op_conv1d_bench(const void* x_h16, const float* w, con
     ms_out[0] = ms / (float)(iters > 0 ? iters : 1);
   }
   if (label && label_cap > 0)
-    snprintf(label, (size_t)label_cap, "NT=%d nclip=%d tiles=%d S=%d a_cap=%d CR=%d minb=%d posM=%d NCH=%d", p.NT, p.NCLIP,
-             p.transposed ? p.n_chtiles * p.n_ntiles : p.MT * p.n_ntiles, p.S, p.a_cap, p.CR, p.minb, p.transposed, p.NCH);
+    snprintf(label, (size_t)label_cap, "NT=%d nclip=%d tiles=%d S=%d a_cap=%d CR=%d minb=%d posM=%d NCH=%d pair=%d", p.NT, p.NCLIP,
+             p.transposed ? p.n_chtiles * p.n_ntiles : p.MT * p.n_ntiles, p.S, p.a_cap, p.CR, p.minb, p.transposed, p.NCH, p.pair);
   if (e0) cudaEventDestroy(e0);
   if (e1) cudaEventDestroy(e1);
   cudaDeviceSynchronize();

@@ -185,6 +185,7 @@ struct TcConvDesc {
   int tap_share;            // 1: all taps of a chunk read one shared activation tile; 0: one tile load per tap
   int want_nt, want_nclip;  // > 0: force the tile shape (rows per clip region / clip regions per tile); 0: cost model
   int want_two_per_sm;      // 1: shape the launch so that two CTAs share an SM (<= 112 KB shared memory, <= 256 TMEM columns)
+  int want_pair;            // 1: CTA pairs along N share every weight tile (each CTA loads half of it and multicasts to both)
   int want_transposed;      // 1: positions-on-M kernel (tc_conv_t_kernel): 128-row position tiles x <= 256-channel tiles
 };
 
@@ -224,6 +225,9 @@ struct TcConvParams {
   const h16* res;
   long long res_bstride;
   int res_pitch;
+  int pair;                   // 1: launched as clusters of 2 CTAs that take neighbouring position tiles of the same output-channel tile;
+                              // each CTA TMA-loads half (64 rows) of every weight tile with .multicast::cluster into both CTAs
+  CUtensorMap tmWh;           // weights, box {64, 64} (half a weight tile)
   int minb;                   // CTAs per SM the launch is shaped for (1 or 2): selects the kernel instantiation and the grid
   // positions-on-M variant (tc_conv_t_kernel): D[position, channel]; rows = 128 positions of one clip, columns = NCH channels
   int transposed;

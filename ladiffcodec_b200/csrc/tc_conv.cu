@@ -92,6 +92,13 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// half a weight tile to the same shared-memory offset of BOTH CTAs of the pair; each CTA's own barrier (same offset) gets the bytes
+__device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
@@ -110,6 +117,12 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// the same, arriving on the barrier at this offset in both CTAs of the pair (a stage is refilled by multicast writes into both
+// CTAs' shared memory, so it is free only when both CTAs' MMAs have read it)
+__device__ __forceinline__ void tc_commit_both(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
 // start>>4 | LBO(=1, ignored for swizzled K-major)<<16 | SBO(=1024 B: 8 rows x 128 B)>>4 <<32 | version 1 <<46 | layout 2 <<61
@@ -135,9 +148,21 @@ __device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct TileCoord { int m0, b0, l0, pt; };
-__device__ __forceinline__ TileCoord decode_tile(const TcConvParams& p, int t) {
+// Tile schedule.  Single CTAs: CTA x takes tiles x, x + grid, ... of mt-fastest order.  Pairs: pair q = blockIdx.x / 2 takes "pair
+// tiles" q, q + npairs, ...; pair tile u = (mt = u % MT, j = u / MT) covers position tiles 2j (rank 0) and 2j + 1 (rank 1); a rank
+// whose position tile does not exist (odd count) is a dummy: it still loads and multicasts its weight halves and releases stages.
+__device__ __forceinline__ int tsched_first(const TcConvParams& p) { return p.pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x; }
+__device__ __forceinline__ int tsched_step(const TcConvParams& p) { return p.pair ? (int)(gridDim.x >> 1) : (int)gridDim.x; }
+__device__ __forceinline__ int tsched_count(const TcConvParams& p) { return p.pair ? p.MT * ((p.n_ntiles + 1) >> 1) : p.MT * p.n_ntiles; }
+__device__ __forceinline__ TileCoord decode_tile(const TcConvParams& p, int t, uint32_t rank, bool* dummy) {
   TileCoord c;
-  const int mt = t % p.MT, nt = t / p.MT;
+  const int mt = t % p.MT;
+  int nt = t / p.MT;
+  *dummy = false;
+  if (p.pair) {
+    nt = 2 * nt + (int)rank;
+    if (nt >= p.n_ntiles) { *dummy = true; nt = p.n_ntiles - 1; }
+  }
   c.m0 = mt * TC_BM;
   if (p.NCLIP == 1) { c.pt = nt % p.n_ptiles; c.b0 = nt / p.n_ptiles; c.l0 = c.pt * p.NT; }
   else { c.pt = 0; c.b0 = nt * p.NCLIP; c.l0 = 0; }
@@ -162,12 +187,14 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
   uint32_t acc_stride = 32;
   while ((int)acc_stride < p.NMMA) acc_stride <<= 1;
   const uint32_t tmem_cols = 2 * acc_stride;
-  const int total_tiles = p.MT * p.n_ntiles;
+  const int total_tiles = tsched_count(p), t_first = tsched_first(p), t_step = tsched_step(p);
+  uint32_t rank = 0;
+  if (p.pair) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   const bool prof = p.prof != nullptr;
   const long long t_begin = prof ? clock64() : 0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < p.S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], p.pair ? 2 : 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4 * kEpiGroups); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmW) : "memory");
@@ -181,6 +208,8 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
   }
   tc_fence_before();
   __syncthreads();
+  if (p.pair)          // the peer's barriers are initialised before any multicast write / remote arrive can reach them
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel's tail
@@ -198,8 +227,10 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
       const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
       int st = 0, issued = 0; uint32_t ph = 0;
       long long w_empty = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile(p, t);
+      const bool pair = p.pair != 0;
+      for (int t = t_first; t < total_tiles; t += t_step) {
+        bool dummy;
+        const TileCoord tc = decode_tile(p, t, rank, &dummy);
         for (int g = 0; g < p.ngrp; ++g) {
           const TcGroup& gr = p.grp[g];
           int n_a = 0, k0 = 0, k1 = 0, k2 = 0;
@@ -210,7 +241,7 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
             ++n_a;
           }
           const int nchunk = gr.nchunk, ch0 = gr.ch0, row = tc.l0 + gr.shift;
-          const uint32_t tx_bytes = b_bytes + (uint32_t)n_a * A_BYTES;
+          const uint32_t tx_bytes = (dummy ? 0u : b_bytes) + (uint32_t)n_a * A_BYTES;
           for (int c = 0; c < nchunk; ++c) {
             mbar_wait_t(&empty_bar[st], ph ^ 1, w_empty, prof);
             if ((p.dbg & 1) && issued >= S) { mbar_arrive(&full_bar[st]); if (++st == S) { st = 0; ph ^= 1; } continue; }
@@ -219,11 +250,21 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
             mbar_expect_tx(fb, tx_bytes);
             const uint32_t a_dst = smem_base + (uint32_t)st * stage_bytes;
             const int kc = c * TC_BK;
-            tma_load_3d(a_dst + b_off, &p.tmX, fb, ch0 + kc, row, tc.b0);
-            for (int j = 1; j < nclip; ++j) tma_load_3d(a_dst + b_off + (uint32_t)j * box_bytes, &p.tmX, fb, ch0 + kc, row, tc.b0 + j);
-            if (n_a > 0) tma_load_2d(a_dst, &p.tmW, fb, k0 + kc, tc.m0);
-            if (n_a > 1) tma_load_2d(a_dst + A_BYTES, &p.tmW, fb, k1 + kc, tc.m0);
-            if (n_a > 2) tma_load_2d(a_dst + 2 * A_BYTES, &p.tmW, fb, k2 + kc, tc.m0);
+            if (!dummy) {
+              tma_load_3d(a_dst + b_off, &p.tmX, fb, ch0 + kc, row, tc.b0);
+              for (int j = 1; j < nclip; ++j) tma_load_3d(a_dst + b_off + (uint32_t)j * box_bytes, &p.tmX, fb, ch0 + kc, row, tc.b0 + j);
+            }
+            if (!pair) {
+              if (n_a > 0) tma_load_2d(a_dst, &p.tmW, fb, k0 + kc, tc.m0);
+              if (n_a > 1) tma_load_2d(a_dst + A_BYTES, &p.tmW, fb, k1 + kc, tc.m0);
+              if (n_a > 2) tma_load_2d(a_dst + 2 * A_BYTES, &p.tmW, fb, k2 + kc, tc.m0);
+            } else {     // this CTA's half (rows 64 rank .. +63) of every weight tile goes to both CTAs of the pair
+              const uint32_t hoff = rank * (A_BYTES / 2);
+              const int mrow = tc.m0 + 64 * (int)rank;
+              if (n_a > 0) tma_load_2d_mcast(a_dst + hoff, &p.tmWh, fb, k0 + kc, mrow, 3);
+              if (n_a > 1) tma_load_2d_mcast(a_dst + A_BYTES + hoff, &p.tmWh, fb, k1 + kc, mrow, 3);
+              if (n_a > 2) tma_load_2d_mcast(a_dst + 2 * A_BYTES + hoff, &p.tmWh, fb, k2 + kc, mrow, 3);
+            }
             if (++st == S) { st = 0; ph ^= 1; }
           }
         }
@@ -241,8 +282,10 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
       const bool no_mma = (p.dbg & 4) != 0;
       int st = 0, tl = 0; uint32_t ph = 0;
       long long w_full = 0, w_tmem = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
-        const TileCoord tc = decode_tile(p, t);
+      const bool pair = p.pair != 0;
+      for (int t = t_first; t < total_tiles; t += t_step, ++tl) {
+        bool dummy;
+        const TileCoord tc = decode_tile(p, t, rank, &dummy);
         const int acc = tl & 1;
         mbar_wait_t(&tmem_empty[acc], ((tl >> 1) & 1) ^ 1, w_tmem, prof);     // the epilogue has drained this accumulator stage
         tc_fence_after();
@@ -266,7 +309,7 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
             const uint32_t a_base = smem_base + (uint32_t)st * stage_bytes;
             const uint64_t adesc = umma_desc(a_base);
             const uint64_t bdesc = umma_desc(a_base + b_off);
-            if (!no_mma) {
+            if (!no_mma && !dummy) {
               if (n_a > 0) {
 #pragma unroll
                 for (int k = 0; k < TC_BK / 16; ++k) { umma_bf16(d_tmem, adesc + 2 * k, bdesc + r0 + 2 * k, idesc, accumulate); accumulate = 1; }
@@ -280,7 +323,7 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
                 for (int k = 0; k < TC_BK / 16; ++k) umma_bf16(d_tmem, adesc + 2 * (A_BYTES >> 4) + 2 * k, bdesc + r2 + 2 * k, idesc, 1u);
               }
             }
-            tc_commit(&empty_bar[st]);     // frees the stage once these MMAs have read it
+            if (pair) tc_commit_both(&empty_bar[st]); else tc_commit(&empty_bar[st]);     // frees the stage once these MMAs have read it
             if (++st == S) { st = 0; ph ^= 1; }
           }
         }
@@ -299,14 +342,16 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
     const uint32_t stage_w = stage0 + (uint32_t)((wg * 4 + q) * 2) * (uint32_t)p.CR * 64u;
     int tl = 0, cc = 0, kk = 0;
     // bias of the NEXT tile is requested one tile ahead (an exposed L2 round trip per tile otherwise)
-    float bias_next = (p.bias && (int)blockIdx.x < total_tiles) ? __ldg(p.bias + decode_tile(p, blockIdx.x).m0 + q * 32 + lane) : 0.f;
+    bool dmy0;
+    float bias_next = (p.bias && t_first < total_tiles) ? __ldg(p.bias + decode_tile(p, t_first, rank, &dmy0).m0 + q * 32 + lane) : 0.f;
     long long w_acc = 0, w_e1 = 0, w_e2 = 0, w_e3 = 0;   // profiling: chunk entry (store drain + barrier), body, fence + barrier + store issue
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
-      const TileCoord tc = decode_tile(p, t);
+    for (int t = t_first; t < total_tiles; t += t_step, ++tl) {
+      bool dummy;
+      const TileCoord tc = decode_tile(p, t, rank, &dummy);
       const int acc = tl & 1;
       const int ch = tc.m0 + q * 32 + lane;
       const float bias = bias_next;
-      if (p.bias && t + (int)gridDim.x < total_tiles) bias_next = __ldg(p.bias + decode_tile(p, t + gridDim.x).m0 + q * 32 + lane);
+      if (p.bias && t + t_step < total_tiles) bias_next = __ldg(p.bias + decode_tile(p, t + t_step, rank, &dmy0).m0 + q * 32 + lane);
       const bool second = p.split_m && tc.m0 >= p.split_m;
       if (p.res) {
         // direct epilogue with a residual: its tile ([clip region][row][128 channels] h16) is staged in shared memory by all
@@ -326,7 +371,7 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
       mbar_wait_t(&tmem_full[acc], (tl >> 1) & 1, w_acc, prof);
       tc_fence_after();
       const uint32_t tlane = tmem_base + (uint32_t)acc * acc_stride + ((uint32_t)(q * 32) << 16);
-      for (int j = 0; j < p.NCLIP; ++j) {
+      for (int j = 0; j < (dummy ? 0 : p.NCLIP); ++j) {
         const int b = tc.b0 + j;
         int vr = p.Lout - tc.l0;                 // valid rows of this clip region
         vr = vr > p.NT ? p.NT : vr;
@@ -432,6 +477,8 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
   }
   tc_fence_before();
   __syncthreads();
+  if (p.pair)          // neither CTA exits while the peer can still multicast into its shared memory or arrive on its barriers
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
@@ -1050,6 +1097,12 @@ int tc_conv_plan(const TcConvDesc& d, TcConvParams* pp, TcRefView* rv) {
   p.tmW = *d.tmW;
   int rc = make_tmap_x(&p.tmX, d.x, d.B, Lv, Cv, pitch_v, d.x_bstride, p.BOXROWS);
   if (rc) return rc;
+  if (d.want_pair) {
+    LADIFF_REQUIRE(!d.want_two_per_sm && p.n_ntiles >= 2, LADIFF_ERR_ARG, "tc_conv: pair mode needs one CTA per SM and >= 2 position tiles");
+    p.pair = 1;
+    rc = make_tmap_wt(&p.tmWh, d.w, d.CoutV, d.Ktot, 64);
+    if (rc) return rc;
+  }
   if (p.direct) {
     if (d.out32) { p.out = d.out32; p.out_f32 = 1; p.out_pitch = d.CoutV; p.out_bstride = (long long)Lout * d.CoutV; }
     else { p.out = d.out; p.out_f32 = 0; p.out_pitch = d.out_pitch; p.out_bstride = d.out_bstride; }
@@ -1146,13 +1199,31 @@ static int tc_conv_launch_minb(const TcConvParams& p, cudaStream_t st) {
   if (ladiff_first_on_device(&attr_set)) {
     LADIFF_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
   }
-  const int tiles = p.MT * p.n_ntiles, slots = tc_num_sms() * MINB;
-  const int grid = tiles < slots ? tiles : slots;
+  const int tiles = p.pair ? p.MT * ((p.n_ntiles + 1) / 2) : p.MT * p.n_ntiles, slots = p.pair ? tc_num_sms() / 2 : tc_num_sms() * MINB;
+  const int grid = (tiles < slots ? tiles : slots) * (p.pair ? 2 : 1);
   static const bool want_prof = getenv("LADIFF_TC_PROF") != nullptr;   // debug aid: per-role mbarrier wait cycles, printed per launch
+  if (!want_prof && p.pair) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    int na = 1;
+    if (ladiff_pdl_enabled()) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    LADIFF_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_conv_kernel<MINB>, p));
+    return 0;
+  }
   if (!want_prof) {
     LADIFF_CUDA_OK(launch_pdl(tc_conv_kernel<MINB>, dim3(grid), dim3(kThreads), smem, st, p));
     return 0;
   }
+  LADIFF_REQUIRE(!p.pair, LADIFF_ERR_ARG, "LADIFF_TC_PROF does not cover the pair mode");
   TcConvParams q = p;
   q.dbg = getenv("LADIFF_TC_DBG") ? atoi(getenv("LADIFF_TC_DBG")) : 0;   // 1: no TMA after ring fill, 2: no epilogue, 4: no MMA, 8: epilogue without tcgen05.ld, 16: epilogue without smem/TMA stores
   unsigned long long* dprof = nullptr;

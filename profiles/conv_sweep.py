@@ -21,6 +21,7 @@ SHAPES = [  # (L, Cin, Cout, k) of config 2 (Layout-B); Cout doubled where res_c
 if len(sys.argv) > 1 and sys.argv[1] == "quick":
     SHAPES = SHAPES[:2] + [SHAPES[8], SHAPES[13]]
 VARIANTS = [("model", dict()), ("NT256", dict(nt=256)), ("NT208", dict(nt=208)), ("NT160", dict(nt=160)), ("NT128", dict(nt=128)),
+            ("pair", dict(two=2)), ("pair NT208", dict(nt=208, two=2)), ("pair NT160", dict(nt=160, two=2)), ("pair NT256", dict(nt=256, two=2)),
             ("two/SM NT128", dict(nt=128, two=1)), ("two/SM NT96", dict(nt=96, two=1)), ("posM", dict(t=1)), ("posM pair", dict(t=2))]
 for (L, Cin, Cout, k) in SHAPES:
     g = torch.Generator().manual_seed(L + Cin)

@@ -268,14 +268,17 @@ def test_tc_conv_operator_shapes():
         ref = F.conv1d(x.float().permute(0, 2, 1), w.to(h16).float(), bias, padding=(k - 1) // 2).permute(0, 2, 1)
         s_ref = ref.reshape(B, L, Cout // 32, 32).sum(dim=(1, 3))
         xd, wd, bd = x.cuda(), w.cuda(), bias.cuda()
-        for impl in (0, 2, 3, 4, 5):
+        for impl in (0, 2, 3, 4, 5, 6):
             if impl == 5 and (k != 1 or L <= 120):      # two-CTAs-per-SM shape: small-K single-clip tiles only
                 continue
+
             for f32 in (1, 0):
                 y = torch.full((B, L, Cout), float("nan"), device="cuda", dtype=torch.float32 if f32 else h16)
                 st = torch.zeros(B, Cout // 32, 2, device="cuda")
                 rc = lib.ladiff_op_conv1d_cl(P(xd.data_ptr()), P(wd.data_ptr()), P(bd.data_ptr()), B, L, Cin, Cout, k, P(y.data_ptr()),
                                              f32, impl, P(st.data_ptr()))
+                if impl == 6 and rc != 0 and b"pair mode needs" in lib.ladiff_last_error():
+                    continue                            # a single position tile: nothing to pair
                 assert rc == 0, lib.ladiff_last_error()
                 tol = 2e-4 if f32 else 2e-4 + ref.abs().max().item() * ulp          # 16-bit output rounding
                 assert (y.float().cpu() - ref).abs().max().item() < tol, (B, L, Cin, Cout, k, impl, f32)
