@@ -887,8 +887,10 @@ struct PlanBuilder {
         if (force_t && pc2.transposed == force_t) { best_ms = 0.f; best = pc2; best_rv = rv2; continue; }
         if (ms < best_ms && ms < 0.97f * base_ms) { best_ms = ms; best = pc2; best_rv = rv2; }
       }
-      static const bool no_pair = getenv("LADIFF_NO_PAIR") != nullptr;
-      if (!no_pair && !best.transposed && best.minb == 1 && best.n_ntiles >= 2) {
+      // opt-in (LADIFF_TRY_PAIR=1): measured within +-2 % of the single-CTA form on every conv shape of config 2
+      // (profiles/r2c/conv_sweep_with_multicast_pairs.txt) — the main loop is MMA-issue-bound, not L2->SM-bound
+      static const bool try_pair = getenv("LADIFF_TRY_PAIR") != nullptr || getenv("LADIFF_FORCE_PAIR") != nullptr;
+      if (try_pair && !best.transposed && best.minb == 1 && best.n_ntiles >= 2) {
         // the chosen shape as CTA pairs along N that share every weight tile through TMA multicast (half the weight bytes per SM)
         TcConvDesc dc = d;
         dc.want_nt = best.NCLIP == 1 ? best.NT : 0; dc.want_nclip = best.NCLIP > 1 ? best.NCLIP : 0; dc.want_pair = 1;
