@@ -406,6 +406,56 @@ __global__ void __launch_bounds__(NTH) seanet_resblock_kernel(const float* __res
     }
 }
 
+// ------------------------------------------------------------------ SEANet output conv: C -> 1 channel, k = 7, causal reflect pad
+// (seanet.py:236; conv.py:217-232).  HBM-bound: every input element is read once; thread = 4 consecutive output samples, the
+// ELU'd input tile of the CTA lives in shared memory, weights in registers via broadcast loads.
+template <int C>
+__global__ void __launch_bounds__(128) conv_out1_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                        float* __restrict__ y, int L, int act_in) {
+  constexpr int TT = 512, XP = TT + 8;         // 6 halo samples on the left, stored at index i + 6 - t0... (row pitch keeps 16-byte alignment)
+  extern __shared__ __align__(16) float osm[];
+  float* xs = osm;                               // [C][XP]: sample t0 - 8 + i at index i  (two unused slots keep float4 alignment)
+  float* ws = osm + C * XP;                      // [C][8]
+  const int b = blockIdx.y, t0 = blockIdx.x * TT, tid = threadIdx.x;
+  const float* xb = x + (long long)b * C * L;
+  for (int i = tid; i < C * 7; i += 128) ws[(i / 7) * 8 + i % 7] = __ldg(w + i);
+  for (int i = tid; i < C * (XP / 4); i += 128) {
+    const int c = i / (XP / 4), p4 = (i - c * (XP / 4)) * 4;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int t = t0 - 8 + p4 + j;
+      if (t < 0) t = -t;                          // reflect (only the first tile; |t| <= 8 < L)
+      float u = t < L ? __ldg(xb + (long long)c * L + t) : 0.f;
+      if (act_in == 1) u = u > 0.f ? u : expm1f(u);
+      v[j] = u;
+    }
+    *reinterpret_cast<float4*>(xs + c * XP + p4) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  __syncthreads();
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = 0; c < C; ++c) {
+    // outputs t0 + 4 tid + j (j < 4) read samples t - 6 .. t  ->  indices 4 tid + 2 + j .. 4 tid + 8 + j: 12 floats from 4 tid
+    const float* xr = xs + c * XP + 4 * tid;
+    const float4 a0 = *reinterpret_cast<const float4*>(xr), a1 = *reinterpret_cast<const float4*>(xr + 4), a2 = *reinterpret_cast<const float4*>(xr + 8);
+    const float xv[12] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
+    const float4 w0 = *reinterpret_cast<const float4*>(ws + c * 8), w1 = *reinterpret_cast<const float4*>(ws + c * 8 + 4);
+    const float wv[7] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z};
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(wv[k], xv[2 + j + k], acc[j]);
+  }
+  const float bb = bias ? __ldg(bias) : 0.f;
+  const int t = t0 + 4 * tid;
+  float* yr = y + (long long)b * L + t;
+  if (t + 3 < L && (((uintptr_t)yr) & 15) == 0) *reinterpret_cast<float4*>(yr) = make_float4(acc[0] + bb, acc[1] + bb, acc[2] + bb, acc[3] + bb);
+  else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (t + j < L) yr[j] = acc[j] + bb;
+  }
+}
+
 __global__ void conv_w_transpose_kernel(const float* __restrict__ w, float* __restrict__ wt, int CoutV, int Cin, int K, int S, int perm_s,
                                         int perm_cout) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -991,14 +1041,33 @@ int seanet_resblock_launch(const float* x, float* y, const float* w1t, const flo
 
 int conv1d_f32_launch(const ConvF32Args& a, int B, cudaStream_t st) {
   LADIFF_REQUIRE(a.K >= 1 && a.K <= 64 && a.stride >= 1, LADIFF_ERR_ARG, "conv1d_f32: K=%d stride=%d", a.K, a.stride);
+  static const bool no_out1 = getenv("LADIFF_CODEC_NO_OUT1") != nullptr;
+  if (!no_out1 && a.CoutV == 1 && a.K == 7 && a.stride == 1 && a.pad_reflect && a.padL == 6 && a.il_s == 0 && !a.res && a.Cin == 32 &&
+      a.LoutV == a.Lin && a.Lin > 8) {          // the decoder's output conv
+    const size_t smem = (size_t)(32 * (512 + 8) + 32 * 8) * sizeof(float);
+    static unsigned long long attr = 0;
+    if (ladiff_first_on_device(&attr))
+      LADIFF_CUDA_OK(cudaFuncSetAttribute(conv_out1_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_out1_kernel<32><<<dim3(cdiv(a.Lin, 512), B), 128, smem, st>>>(a.x, a.w, a.bias, a.y, a.Lin, a.act_in);
+    LADIFF_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   static const bool no_v2 = getenv("LADIFF_CODEC_V1") != nullptr;
   if (a.wt && !no_v2 && a.K % a.stride == 0) {
     const int S = a.stride, KT = a.K / S;
     const bool il_ok = a.il_s == 0 || (a.il_s <= 8 && (8 % a.il_s) == 0);     // phases of one channel live in one thread tile / pass
     if ((KT == 1 || KT == 2 || KT == 3 || KT == 7) && S <= 8 && il_ok) {
-      if (a.CoutV >= 128) return conv1d_v2_dispatch<8>(a, KT, S, B, st);
-      if (a.CoutV >= 64) return conv1d_v2_dispatch<4>(a, KT, S, B, st);
-      if (a.CoutV >= 32 && a.il_s <= 4) return conv1d_v2_dispatch<2>(a, KT, S, B, st);
+      // channels per thread (RC; CTA = 16 RC channels x 128 positions): the widest tile the channel count allows, narrowed while the
+      // grid would leave SMs idle (short time axes: the 120-frame layers of the encoder launch 32-128 CTAs with RC = 8)
+      int rc = a.CoutV >= 128 ? 8 : (a.CoutV >= 64 ? 4 : (a.CoutV >= 32 && a.il_s <= 4 ? 2 : 1));
+      static const bool no_narrow = getenv("LADIFF_CODEC_NO_NARROW") != nullptr;
+      const long tiles_t = cdiv(a.LoutV, 128);
+      // (stride-1 convs only: a strided conv's phase-channel fill is repeated by every channel tile and dominates when narrowed)
+      while (!no_narrow && S == 1 && rc > 2 && tiles_t * cdiv(a.CoutV, 16 * rc) * B < 2L * tc_num_sms()) rc >>= 1;
+      if (rc == 2 && !(a.CoutV >= 32 && a.il_s <= 4)) rc = 4;
+      if (rc == 8) return conv1d_v2_dispatch<8>(a, KT, S, B, st);
+      if (rc == 4) return conv1d_v2_dispatch<4>(a, KT, S, B, st);
+      if (rc == 2) return conv1d_v2_dispatch<2>(a, KT, S, B, st);
       if (a.il_s <= 1) return conv1d_v2_dispatch<1>(a, KT, S, B, st);
     }
   }
