@@ -151,15 +151,17 @@ struct TileCoord { int m0, b0, l0, pt; };
 // Tile schedule.  Single CTAs: CTA x takes tiles x, x + grid, ... of mt-fastest order.  Pairs: pair q = blockIdx.x / 2 takes "pair
 // tiles" q, q + npairs, ...; pair tile u = (mt = u % MT, j = u / MT) covers position tiles 2j (rank 0) and 2j + 1 (rank 1); a rank
 // whose position tile does not exist (odd count) is a dummy: it still loads and multicasts its weight halves and releases stages.
-__device__ __forceinline__ int tsched_first(const TcConvParams& p) { return p.pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x; }
-__device__ __forceinline__ int tsched_step(const TcConvParams& p) { return p.pair ? (int)(gridDim.x >> 1) : (int)gridDim.x; }
-__device__ __forceinline__ int tsched_count(const TcConvParams& p) { return p.pair ? p.MT * ((p.n_ntiles + 1) >> 1) : p.MT * p.n_ntiles; }
+// PAIR is a template parameter: the single-CTA instantiation carries none of the pair logic.
+template <int PAIR> __device__ __forceinline__ int tsched_first() { return PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x; }
+template <int PAIR> __device__ __forceinline__ int tsched_step() { return PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x; }
+template <int PAIR> __device__ __forceinline__ int tsched_count(const TcConvParams& p) { return PAIR ? p.MT * ((p.n_ntiles + 1) >> 1) : p.MT * p.n_ntiles; }
+template <int PAIR>
 __device__ __forceinline__ TileCoord decode_tile(const TcConvParams& p, int t, uint32_t rank, bool* dummy) {
   TileCoord c;
   const int mt = t % p.MT;
   int nt = t / p.MT;
   *dummy = false;
-  if (p.pair) {
+  if (PAIR) {
     nt = 2 * nt + (int)rank;
     if (nt >= p.n_ntiles) { *dummy = true; nt = p.n_ntiles - 1; }
   }
@@ -171,7 +173,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcConvParams& p, int t, u
 
 // MINB = 2: the same code compiled to <= 102 registers so that two CTAs of a small-footprint launch (<= 112 KB shared memory, <= 256
 // TMEM columns) share an SM: one CTA's prologue / epilogue then overlaps the other's main loop.
-template <int MINB>
+template <int MINB, int PAIR>
 __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_constant__ TcConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
@@ -187,14 +189,14 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
   uint32_t acc_stride = 32;
   while ((int)acc_stride < p.NMMA) acc_stride <<= 1;
   const uint32_t tmem_cols = 2 * acc_stride;
-  const int total_tiles = tsched_count(p), t_first = tsched_first(p), t_step = tsched_step(p);
+  const int total_tiles = tsched_count<PAIR>(p), t_first = tsched_first<PAIR>(), t_step = tsched_step<PAIR>();
   uint32_t rank = 0;
-  if (p.pair) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  if (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   const bool prof = p.prof != nullptr;
   const long long t_begin = prof ? clock64() : 0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], p.pair ? 2 : 1); }
+    for (int s = 0; s < p.S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], PAIR ? 2 : 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4 * kEpiGroups); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmW) : "memory");
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
   }
   tc_fence_before();
   __syncthreads();
-  if (p.pair)          // the peer's barriers are initialised before any multicast write / remote arrive can reach them
+  if (PAIR)            // the peer's barriers are initialised before any multicast write / remote arrive can reach them
     asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
@@ -227,10 +229,10 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
       const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
       int st = 0, issued = 0; uint32_t ph = 0;
       long long w_empty = 0;
-      const bool pair = p.pair != 0;
+      constexpr bool pair = PAIR != 0;
       for (int t = t_first; t < total_tiles; t += t_step) {
         bool dummy;
-        const TileCoord tc = decode_tile(p, t, rank, &dummy);
+        const TileCoord tc = decode_tile<PAIR>(p, t, rank, &dummy);
         for (int g = 0; g < p.ngrp; ++g) {
           const TcGroup& gr = p.grp[g];
           int n_a = 0, k0 = 0, k1 = 0, k2 = 0;
@@ -282,10 +284,10 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
       const bool no_mma = (p.dbg & 4) != 0;
       int st = 0, tl = 0; uint32_t ph = 0;
       long long w_full = 0, w_tmem = 0;
-      const bool pair = p.pair != 0;
+      constexpr bool pair = PAIR != 0;
       for (int t = t_first; t < total_tiles; t += t_step, ++tl) {
         bool dummy;
-        const TileCoord tc = decode_tile(p, t, rank, &dummy);
+        const TileCoord tc = decode_tile<PAIR>(p, t, rank, &dummy);
         const int acc = tl & 1;
         mbar_wait_t(&tmem_empty[acc], ((tl >> 1) & 1) ^ 1, w_tmem, prof);     // the epilogue has drained this accumulator stage
         tc_fence_after();
@@ -343,15 +345,15 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
     int tl = 0, cc = 0, kk = 0;
     // bias of the NEXT tile is requested one tile ahead (an exposed L2 round trip per tile otherwise)
     bool dmy0;
-    float bias_next = (p.bias && t_first < total_tiles) ? __ldg(p.bias + decode_tile(p, t_first, rank, &dmy0).m0 + q * 32 + lane) : 0.f;
+    float bias_next = (p.bias && t_first < total_tiles) ? __ldg(p.bias + decode_tile<PAIR>(p, t_first, rank, &dmy0).m0 + q * 32 + lane) : 0.f;
     long long w_acc = 0, w_e1 = 0, w_e2 = 0, w_e3 = 0;   // profiling: chunk entry (store drain + barrier), body, fence + barrier + store issue
     for (int t = t_first; t < total_tiles; t += t_step, ++tl) {
       bool dummy;
-      const TileCoord tc = decode_tile(p, t, rank, &dummy);
+      const TileCoord tc = decode_tile<PAIR>(p, t, rank, &dummy);
       const int acc = tl & 1;
       const int ch = tc.m0 + q * 32 + lane;
       const float bias = bias_next;
-      if (p.bias && t + t_step < total_tiles) bias_next = __ldg(p.bias + decode_tile(p, t + t_step, rank, &dmy0).m0 + q * 32 + lane);
+      if (p.bias && t + t_step < total_tiles) bias_next = __ldg(p.bias + decode_tile<PAIR>(p, t + t_step, rank, &dmy0).m0 + q * 32 + lane);
       const bool second = p.split_m && tc.m0 >= p.split_m;
       if (p.res) {
         // direct epilogue with a residual: its tile ([clip region][row][128 channels] h16) is staged in shared memory by all
@@ -477,7 +479,7 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
   }
   tc_fence_before();
   __syncthreads();
-  if (p.pair)          // neither CTA exits while the peer can still multicast into its shared memory or arrive on its barriers
+  if (PAIR)            // neither CTA exits while the peer can still multicast into its shared memory or arrive on its barriers
     asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
@@ -1197,7 +1199,8 @@ static int tc_conv_launch_minb(const TcConvParams& p, cudaStream_t st) {
   LADIFF_REQUIRE(smem <= limit, LADIFF_ERR_ARG, "tc_conv: smem %zu too large", smem);
   static unsigned long long attr_set = 0;     // opt in to the dynamic shared memory once per device
   if (ladiff_first_on_device(&attr_set)) {
-    LADIFF_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+    LADIFF_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel<MINB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+    LADIFF_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel<MINB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
   }
   const int tiles = p.pair ? p.MT * ((p.n_ntiles + 1) / 2) : p.MT * p.n_ntiles, slots = p.pair ? tc_num_sms() / 2 : tc_num_sms() * MINB;
   const int grid = (tiles < slots ? tiles : slots) * (p.pair ? 2 : 1);
@@ -1216,11 +1219,11 @@ static int tc_conv_launch_minb(const TcConvParams& p, cudaStream_t st) {
       ++na;
     }
     cfg.attrs = attr; cfg.numAttrs = na;
-    LADIFF_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_conv_kernel<MINB>, p));
+    LADIFF_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_conv_kernel<MINB, 1>, p));
     return 0;
   }
   if (!want_prof) {
-    LADIFF_CUDA_OK(launch_pdl(tc_conv_kernel<MINB>, dim3(grid), dim3(kThreads), smem, st, p));
+    LADIFF_CUDA_OK(launch_pdl(tc_conv_kernel<MINB, 0>, dim3(grid), dim3(kThreads), smem, st, p));
     return 0;
   }
   LADIFF_REQUIRE(!p.pair, LADIFF_ERR_ARG, "LADIFF_TC_PROF does not cover the pair mode");
@@ -1230,7 +1233,7 @@ static int tc_conv_launch_minb(const TcConvParams& p, cudaStream_t st) {
   LADIFF_CUDA_OK(cudaMalloc((void**)&dprof, sizeof(unsigned long long) * 8 * grid));
   LADIFF_CUDA_OK(cudaMemset(dprof, 0, sizeof(unsigned long long) * 8 * grid));
   q.prof = dprof;
-  tc_conv_kernel<MINB><<<grid, kThreads, smem, st>>>(q);
+  tc_conv_kernel<MINB, 0><<<grid, kThreads, smem, st>>>(q);
   LADIFF_CUDA_OK(cudaGetLastError());
   LADIFF_CUDA_OK(cudaStreamSynchronize(st));
   std::vector<unsigned long long> hp((size_t)8 * grid);
