@@ -173,7 +173,8 @@ __device__ __forceinline__ TileCoord decode_tile(const TcConvParams& p, int t, u
 
 // MINB = 2: the same code compiled to <= 102 registers so that two CTAs of a small-footprint launch (<= 112 KB shared memory, <= 256
 // TMEM columns) share an SM: one CTA's prologue / epilogue then overlaps the other's main loop.
-template <int MINB, int PAIR>
+// PROF = 1 (LADIFF_TC_PROF): per-role wait-cycle counters and the LADIFF_TC_DBG ablations; the production instantiation has neither.
+template <int MINB, int PAIR, int PROF>
 __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_constant__ TcConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
@@ -192,7 +193,8 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
   const int total_tiles = tsched_count<PAIR>(p), t_first = tsched_first<PAIR>(), t_step = tsched_step<PAIR>();
   uint32_t rank = 0;
   if (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-  const bool prof = p.prof != nullptr;
+  const bool prof = PROF && p.prof != nullptr;
+  const int dbg = PROF ? dbg : 0;
   const long long t_begin = prof ? clock64() : 0;
 
   if (threadIdx.x == 0) {
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
           const uint32_t tx_bytes = (dummy ? 0u : b_bytes) + (uint32_t)n_a * A_BYTES;
           for (int c = 0; c < nchunk; ++c) {
             mbar_wait_t(&empty_bar[st], ph ^ 1, w_empty, prof);
-            if ((p.dbg & 1) && issued >= S) { mbar_arrive(&full_bar[st]); if (++st == S) { st = 0; ph ^= 1; } continue; }
+            if ((dbg & 1) && issued >= S) { mbar_arrive(&full_bar[st]); if (++st == S) { st = 0; ph ^= 1; } continue; }
             ++issued;
             uint64_t* fb = &full_bar[st];
             mbar_expect_tx(fb, tx_bytes);
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
       const uint32_t idesc = (1u << 4) | (TC_IDESC_AB_FMT << 7) | (TC_IDESC_AB_FMT << 10) | ((uint32_t)(p.NMMA >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       const int S = p.S;
       const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
-      const bool no_mma = (p.dbg & 4) != 0;
+      const bool no_mma = (dbg & 4) != 0;
       int st = 0, tl = 0; uint32_t ph = 0;
       long long w_full = 0, w_tmem = 0;
       constexpr bool pair = PAIR != 0;
@@ -380,7 +382,7 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
         if (b >= p.B) vr = 0;
         float s1 = 0.f, s2 = 0.f;
         for (int r0 = 0; r0 < p.NT; r0 += p.CR, ++cc) {
-          if ((cc & 1) != wg || vr <= r0 || (p.dbg & 2)) continue;    // uniform over the warpgroup
+          if ((cc & 1) != wg || vr <= r0 || (dbg & 2)) continue;    // uniform over the warpgroup
           const int nrows = (p.NT - r0) < p.CR ? (p.NT - r0) : p.CR;
           uint32_t stg = 0;
           const long long te0 = prof ? clock64() : 0;
@@ -391,7 +393,7 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
           }
           const long long te1 = prof ? clock64() : 0;
           const uint32_t tcol = tlane + (uint32_t)(j * p.NT + r0);
-          const bool no_ld = (p.dbg & 8) != 0, no_st = (p.dbg & 16) != 0;   // ablations (LADIFF_TC_DBG)
+          const bool no_ld = (dbg & 8) != 0, no_st = (dbg & 16) != 0;   // ablations (LADIFF_TC_DBG)
           auto consume = [&](const uint32_t (&r)[16], int c0) {
             if (no_st) {
 #pragma unroll
@@ -1199,8 +1201,9 @@ static int tc_conv_launch_minb(const TcConvParams& p, cudaStream_t st) {
   LADIFF_REQUIRE(smem <= limit, LADIFF_ERR_ARG, "tc_conv: smem %zu too large", smem);
   static unsigned long long attr_set = 0;     // opt in to the dynamic shared memory once per device
   if (ladiff_first_on_device(&attr_set)) {
-    LADIFF_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel<MINB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
-    LADIFF_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel<MINB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+    LADIFF_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel<MINB, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+    LADIFF_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel<MINB, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+    LADIFF_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel<MINB, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
   }
   const int tiles = p.pair ? p.MT * ((p.n_ntiles + 1) / 2) : p.MT * p.n_ntiles, slots = p.pair ? tc_num_sms() / 2 : tc_num_sms() * MINB;
   const int grid = (tiles < slots ? tiles : slots) * (p.pair ? 2 : 1);
@@ -1219,11 +1222,11 @@ static int tc_conv_launch_minb(const TcConvParams& p, cudaStream_t st) {
       ++na;
     }
     cfg.attrs = attr; cfg.numAttrs = na;
-    LADIFF_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_conv_kernel<MINB, 1>, p));
+    LADIFF_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_conv_kernel<MINB, 1, 0>, p));
     return 0;
   }
   if (!want_prof) {
-    LADIFF_CUDA_OK(launch_pdl(tc_conv_kernel<MINB, 0>, dim3(grid), dim3(kThreads), smem, st, p));
+    LADIFF_CUDA_OK(launch_pdl(tc_conv_kernel<MINB, 0, 0>, dim3(grid), dim3(kThreads), smem, st, p));
     return 0;
   }
   LADIFF_REQUIRE(!p.pair, LADIFF_ERR_ARG, "LADIFF_TC_PROF does not cover the pair mode");
@@ -1233,7 +1236,7 @@ static int tc_conv_launch_minb(const TcConvParams& p, cudaStream_t st) {
   LADIFF_CUDA_OK(cudaMalloc((void**)&dprof, sizeof(unsigned long long) * 8 * grid));
   LADIFF_CUDA_OK(cudaMemset(dprof, 0, sizeof(unsigned long long) * 8 * grid));
   q.prof = dprof;
-  tc_conv_kernel<MINB, 0><<<grid, kThreads, smem, st>>>(q);
+  tc_conv_kernel<MINB, 0, 1><<<grid, kThreads, smem, st>>>(q);
   LADIFF_CUDA_OK(cudaGetLastError());
   LADIFF_CUDA_OK(cudaStreamSynchronize(st));
   std::vector<unsigned long long> hp((size_t)8 * grid);
