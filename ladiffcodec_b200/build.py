@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_build")
 LIB = os.path.join(HERE, "libladiff_b200.so")
-SOURCES = ["tc_conv.cu", "attn_tc.cu", "unet_ops.cu", "codec_ops.cu", "fold.cu", "api.cu"]
+SOURCES = ["tc_conv.cu", "attn_tc.cu", "unet_ops.cu", "codec_ops.cu", "codec_tc.cu", "fold.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 if os.environ.get("LADIFF_USE_BF16"):          # A/B build: bf16 instead of fp16 operands / activations (csrc/common.cuh)

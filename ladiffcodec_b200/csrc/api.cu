@@ -50,10 +50,10 @@ struct KeySpec {
 };
 
 // ---- folded codec parameters
-struct ConvW { const float* w = nullptr; const float* wt = nullptr; const float* bias = nullptr; int Cout = 0, Cin = 0, K = 0, stride = 1; };
-struct ConvTrW { const float* w2 = nullptr; const float* wt = nullptr; const float* bias = nullptr; int Cin = 0, Cout = 0, s = 1; };
+struct ConvW { const float* w = nullptr; const float* wt = nullptr; const float* bias = nullptr; int Cout = 0, Cin = 0, K = 0, stride = 1; CodecTcWeights tcw; };
+struct ConvTrW { const float* w2 = nullptr; const float* wt = nullptr; const float* bias = nullptr; int Cin = 0, Cout = 0, s = 1; CodecTcWeights tcw; };
 struct ResBlockW { ConvW c1, c2, sc; };
-struct LstmW { int H = 0, layers = 0; const float* wih[4]; const float* wih_t[4]; const float* whh[4]; const float* bias[4]; };
+struct LstmW { int H = 0, layers = 0; const float* wih[4]; const float* wih_t[4]; const float* whh[4]; const float* bias[4]; CodecTcWeights tcw[4]; };
 struct EncoderW { ConvW first, last; std::vector<ResBlockW> rb; std::vector<ConvW> down; LstmW lstm; };
 struct DecoderW { ConvW first, last; std::vector<ConvTrW> up; std::vector<ResBlockW> rb; LstmW lstm; };
 
@@ -317,6 +317,14 @@ template <class T> int dalloc(H* h, T** p, size_t n) {
   return 0;
 }
 
+// hi / lo TF32 planes + tensor map of a K-major weight copy for the tcgen05 codec conv (codec_tc.cu); convs it does not cover keep valid = 0
+int prep_codec_tc(H* h, const float* wt, int CinV, int KT, int CoutV, CodecTcWeights* out) {
+  if (CinV < 32 || CinV % 4 != 0 || KT > 8 || CoutV < 32) return 0;
+  float* planes = nullptr;
+  TRY(dalloc(h, &planes, (size_t)2 * CinV * KT * CoutV));
+  return codec_tc_prepare(wt, CinV, KT, CoutV, planes, out, 0);
+}
+
 int fold_wn_conv(H* h, const std::string& p, int cout, int cin, int k, int stride, ConvW* out) {
   float* w = nullptr;
   TRY(dalloc(h, &w, (size_t)cout * cin * k));
@@ -328,6 +336,7 @@ int fold_wn_conv(H* h, const std::string& p, int cout, int cin, int k, int strid
     TRY(dalloc(h, &wt, (size_t)cout * cin * k));
     TRY(conv_w_transpose_launch(w, wt, cout, cin, k, stride, 0, 0, 0));
     out->wt = wt;
+    TRY(prep_codec_tc(h, wt, cin * stride, k / stride, cout, &out->tcw));
   }
   return 0;
 }
@@ -343,6 +352,7 @@ int fold_wn_convtr(H* h, const std::string& p, int cin, int cout, int s, ConvTrW
     TRY(dalloc(h, &wt, (size_t)cin * cout * 2 * s));
     TRY(conv_w_transpose_launch(w2, wt, s * cout, cin, 2, 1, s, cout, 0));
     out->wt = wt;
+    TRY(prep_codec_tc(h, wt, cin, 2, s * cout, &out->tcw));
   }
   return 0;
 }
@@ -363,6 +373,7 @@ int fold_lstm(H* h, const std::string& p, int dim, int layers, LstmW* lw) {
       TRY(dalloc(h, &wt, (size_t)4 * dim * dim));
       TRY(conv_w_transpose_launch(lw->wih[l], wt, 4 * dim, dim, 1, 1, 0, 0, 0));
       lw->wih_t[l] = wt;
+      TRY(prep_codec_tc(h, wt, dim, 1, 4 * dim, &lw->tcw[l]));
     }
     float* b = nullptr;
     TRY(dalloc(h, &b, (size_t)4 * dim));
@@ -586,6 +597,7 @@ int fold_unet(H* h) {
       TRY(dalloc(h, &wt, (size_t)cc * cc * 2 * s));
       TRY(conv_w_transpose_launch(w2, wt, s * cc, cc, 2, 1, s, cc, 0));
       t.wt = wt;
+      TRY(prep_codec_tc(h, wt, cc, 2, s * cc, &t.tcw));
     }
     u.cond_up.push_back(t);
   }
@@ -633,6 +645,7 @@ int run_conv(H* h, const ConvW& cw, const float* x, int Lin, float* y, int act_i
   a.x = x; a.Cin = cw.Cin; a.Lin = Lin; a.w = cw.w; a.wt = cw.wt; a.bias = cw.bias; a.y = y; a.CoutV = cw.Cout;
   a.LoutV = conv_out_len(Lin, cw.K, cw.stride);
   a.K = cw.K; a.stride = cw.stride; a.padL = (cw.K - 1) - (cw.stride - 1); a.pad_reflect = 1; a.act_in = act_in; a.res = res;
+  a.tcw = cw.tcw.valid ? &cw.tcw : nullptr;
   h->launches++;
   return conv1d_f32_launch(a, B, st);
 }
@@ -646,6 +659,7 @@ int run_convtr(H* h, const ConvTrW& cw, const float* x, int Lin, float* y, int a
   a.il_s = cw.s; a.il_cout = cw.Cout; a.il_lout = Lin * cw.s;
   const int total = cw.s;                    // k - s
   a.il_trim = causal ? 0 : total - total / 2;
+  a.tcw = cw.tcw.valid ? &cw.tcw : nullptr;
   h->launches++;
   return conv1d_f32_launch(a, B, st);
 }
@@ -675,7 +689,7 @@ int run_lstm(H* h, const LstmW& lw, float*& x, int T, Pool& pool, float* hbuf, f
   float* pre = pool.get();
   float* y = nullptr;
   for (int l = 0; l < lw.layers; ++l) {
-    ConvW ip; ip.w = lw.wih[l]; ip.wt = lw.wih_t[l]; ip.bias = lw.bias[l]; ip.Cout = 4 * lw.H; ip.Cin = lw.H; ip.K = 1; ip.stride = 1;
+    ConvW ip; ip.w = lw.wih[l]; ip.wt = lw.wih_t[l]; ip.bias = lw.bias[l]; ip.Cout = 4 * lw.H; ip.Cin = lw.H; ip.K = 1; ip.stride = 1; ip.tcw = lw.tcw[l];
     TRY(run_conv(h, ip, in, T, pre, 0, nullptr, B, st));
     y = pool.get();
     const float* skip = (l == lw.layers - 1) ? x : nullptr;

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) conv1d_f32_kernel(ConvF32Args a, int CI_T
 // every tap, weights come as broadcast LDS.128 -> ~0.05 shared-memory instructions per FMA.  The output tile goes through
 // shared memory so that global stores (and residual loads) are coalesced along time also for the interleaved layout.
 template <int RC, int KT>
-__global__ void __launch_bounds__(256, RC >= 8 ? 2 : 3) conv1d_f32_v2_kernel(ConvF32Args a, int CI_T, int S) {
+__global__ void __launch_bounds__(256, RC >= 8 ? 2 : 3) conv1d_f32_v2_kernel(ConvF32Args a, int CI_T, int S, unsigned magic_span, unsigned magic_s) {
   extern __shared__ __align__(16) float sm2[];
   constexpr int CO_T = 16 * RC, T_T = 128, XW = T_T + KT - 1, XWP = (XW + 3) & ~3, NX = 8 + KT - 1;
   float* xs = sm2;                       // [CI_T][XWP]
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256, RC >= 8 ? 2 : 3) conv1d_f32_v2_kernel(Con
   const long long g_base = (long long)t0 * S - a.padL;
   const int span = XW * S;
   for (int cv0 = 0; cv0 < CinV; cv0 += CI_T) {
-    const int nci = min(CI_T, CinV - cv0), nreal = nci / S;
+    const int nci = min(CI_T, CinV - cv0), nreal = nci / S, cvr0 = cv0 / S;
     __syncthreads();
     // fills: batches of independent loads (all in flight before the first shared-memory store): the layers with long time
     // axes are latency-bound on exactly these loads
@@ -131,12 +131,13 @@ __global__ void __launch_bounds__(256, RC >= 8 ? 2 : 3) conv1d_f32_v2_kernel(Con
         const int i = i0 + qq * 256;
         v[qq] = 0.f; dst[qq] = -1;
         if (i < xtotal) {
-          const int ci = i / span, g = i - ci * span;
+          // (divisions by multiply-high with host-made reciprocals: the generic integer division was 40 % of the kernel's instructions)
+          const int ci = (int)__umulhi((unsigned)i, magic_span), g = i - ci * span;
           long long gi = g_base + g;
           if (gi < 0) gi = a.pad_reflect ? -gi : -1;
           else if (gi >= a.Lin) gi = a.pad_reflect ? 2LL * (a.Lin - 1) - gi : -1;
-          if (gi >= 0 && gi < a.Lin) v[qq] = __ldg(xb + (long long)(cv0 / S + ci) * a.Lin + gi);
-          const int u = S == 1 ? g : g / S, ph = g - u * S;
+          if (gi >= 0 && gi < a.Lin) v[qq] = __ldg(xb + (long long)(cvr0 + ci) * a.Lin + gi);
+          const int u = S == 1 ? g : (int)__umulhi((unsigned)g, magic_s), ph = g - u * S;
           dst[qq] = (ci * S + ph) * XWP + u;
         }
       }
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(256, RC >= 8 ? 2 : 3) conv1d_f32_v2_kernel(Con
           const int e = e0 + qq * 256;
           oo[qq] = -1; rv[qq] = 0.f; bv[qq] = 0.f;
           if (e < etotal) {
-            const int crl = e / ow, pos = e - crl * ow, vch = v0 + crl;
+            const int crl = e >> 7, pos = e & (T_T - 1), vch = v0 + crl;       // ow == T_T == 128 here
             if (vch < a.CoutV && t0 + pos < a.LoutV) {
               oo[qq] = ((long long)b * a.CoutV + vch) * a.LoutV + t0 + pos;
               if (a.res) rv[qq] = __ldg(a.res + oo[qq]);
@@ -249,16 +250,17 @@ __global__ void __launch_bounds__(256, RC >= 8 ? 2 : 3) conv1d_f32_v2_kernel(Con
 #pragma unroll
         for (int qq = 0; qq < EB; ++qq) {
           const int e = e0 + qq * 256;
-          if (oo[qq] >= 0) { const int crl = e / ow, pos = e - crl * ow; a.y[oo[qq]] = es[crl * EPW + pos] + bv[qq] + rv[qq]; }
+          if (oo[qq] >= 0) { const int crl = e >> 7, pos = e & (T_T - 1); a.y[oo[qq]] = es[crl * EPW + pos] + bv[qq] + rv[qq]; }
         }
       }
     } else {
+      const int sh = 31 - __clz(s_il);             // il_s is 2, 4 or 8 on this path (launcher)
       for (int e = tid; e < etotal; e += 256) {
-        const int crl = e / ow, op = e - crl * ow;
-        const int pos = op / s_il, ph = op - pos * s_il;
+        const int crl = e >> (7 + sh), op = e & (ow - 1);
+        const int pos = op >> sh, ph = op & (s_il - 1);
         const int vch = v0 + crl * s_il + ph;
         if (vch >= a.CoutV || t0 + pos >= a.LoutV) continue;
-        const int cr = vch / s_il;
+        const int cr = vch >> sh;
         const long long opos = (long long)(t0 + pos) * s_il + ph - a.il_trim;
         if (opos >= 0 && opos < a.il_lout)
           a.y[((long long)b * a.il_cout + cr) * a.il_lout + opos] = es[(crl * s_il + ph) * EPW + pos] + (a.bias ? __ldg(a.bias + cr) : 0.f);
@@ -996,13 +998,16 @@ static int conv1d_v2_dispatch(const ConvF32Args& a, int KT, int S, int B, cudaSt
   if (epi > smem) smem = epi;
   LADIFF_REQUIRE(smem <= 100 * 1024, LADIFF_ERR_ARG, "conv1d_f32_v2: smem %zu", smem);
   dim3 grid(cdiv(a.LoutV, 128), cdiv(a.CoutV, CO_T), B);
+  // exact for every dividend the fill produces (< 2^16): ceil(2^32 / d) * n >> 32 == n / d  while n * d < 2^32
+  const unsigned span = (unsigned)(128 + KT - 1) * S;
+  const unsigned magic_span = (unsigned)((0x100000000ULL + span - 1) / span), magic_s = (unsigned)((0x100000000ULL + S - 1) / S);
 #define LADIFF_V2_CASE(KTV)                                                                                                   \
   case KTV: {                                                                                                                 \
     static unsigned long long attr = 0;                                                                                       \
     if (ladiff_first_on_device(&attr)) {                                                                                      \
       LADIFF_CUDA_OK(cudaFuncSetAttribute(conv1d_f32_v2_kernel<RC, KTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); \
     }                                                                                                                         \
-    conv1d_f32_v2_kernel<RC, KTV><<<grid, 256, smem, st>>>(a, CI_T, S);                                                       \
+    conv1d_f32_v2_kernel<RC, KTV><<<grid, 256, smem, st>>>(a, CI_T, S, magic_span, magic_s);                                                       \
     break;                                                                                                                    \
   }
   switch (KT) {
@@ -1051,6 +1056,10 @@ int conv1d_f32_launch(const ConvF32Args& a, int B, cudaStream_t st) {
     conv_out1_kernel<32><<<dim3(cdiv(a.Lin, 512), B), 128, smem, st>>>(a.x, a.w, a.bias, a.y, a.Lin, a.act_in);
     LADIFF_CUDA_OK(cudaGetLastError());
     return 0;
+  }
+  if (a.tcw) {                                 // tcgen05 3xTF32 kernel (codec_tc.cu) where the weights were prepared for it
+    const int rc = codec_tc_launch(a, B, st);
+    if (rc <= 0) return rc;
   }
   static const bool no_v2 = getenv("LADIFF_CODEC_V1") != nullptr;
   if (a.wt && !no_v2 && a.K % a.stride == 0) {

@@ -4,6 +4,11 @@
 
 // y[b,co,t] = bias[co] + sum_{ci,k} w[co,ci,k] * act(xpad[b,ci,t*stride + k - padL])  (+ res[b,co,t])
 // xpad: reflect (SConv1d, conv.py:217-232) or zero extension of x outside [0,Lin).
+// Weights of one conv prepared for the tcgen05 3xTF32 kernel (codec_tc.cu): hi / lo planes [2][KT][CoutV][CinV] and their tensor map.
+struct CodecTcWeights {
+  CUtensorMap tm;
+  int CinV = 0, KT = 0, CoutV = 0, valid = 0;
+};
 struct ConvF32Args {
   const float* x; int Cin; int Lin;
   const float* w;          // [CoutV][Cin][K]
@@ -19,7 +24,12 @@ struct ConvF32Args {
   // transposed-conv interleave (SConvTranspose1d, conv.py:252-274): virtual channel v = ph*il_cout + co at
   // virtual position i lands at y[b, co, i*il_s + ph - il_trim] if inside [0, il_lout).  il_s = 0: plain conv.
   int il_s, il_cout, il_trim, il_lout;
+  const CodecTcWeights* tcw;   // optional: prepared tensor-core weights (null: FMA kernels only)
 };
+// planes: device buffer of 2*CinV*KT*CoutV floats (filled here from wt = the K-major copy of conv_w_transpose_launch)
+int codec_tc_prepare(const float* wt, int CinV, int KT, int CoutV, float* planes, CodecTcWeights* out, cudaStream_t st);
+// 0: launched; 1: this conv has no tensor-core form (caller falls back to the FMA kernel); < 0: error
+int codec_tc_launch(const ConvF32Args& a, int B, cudaStream_t st);
 int conv1d_f32_launch(const ConvF32Args& a, int B, cudaStream_t st);
 // Fused SEANet residual block (seanet.py:45-63) for C = 32 / 64: y = shortcut_1x1(x) + conv_k1(ELU(conv_k3(ELU(x)))), causal reflect
 // padding; w1t [C*3][C/2], wsct [C][C], w2t [C/2][C] are the K-major copies (conv_w_transpose_launch).  Returns 0 when launched,

@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
   uint32_t rank = 0;
   if (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   const bool prof = PROF && p.prof != nullptr;
-  const int dbg = PROF ? dbg : 0;
+  const int dbg = PROF ? p.dbg : 0;
   const long long t_begin = prof ? clock64() : 0;
 
   if (threadIdx.x == 0) {
