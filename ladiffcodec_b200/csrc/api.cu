@@ -136,6 +136,7 @@ struct LadiffHandle {
   int profiling = 0;
   Plan* last_plan = nullptr;
   long long launches = 0;
+  int tc_precise = 0;   // set while the cond encoder runs (run_encoder): codec convs then use the extra accumulator chains
   unsigned long long clip_offset = 0;   // global index of this handle's clip 0 (in-kernel noise is keyed by the global clip)
   int enc_hop = 1;
   EncoderW enc; DecoderW dec;
@@ -645,7 +646,7 @@ int run_conv(H* h, const ConvW& cw, const float* x, int Lin, float* y, int act_i
   a.x = x; a.Cin = cw.Cin; a.Lin = Lin; a.w = cw.w; a.wt = cw.wt; a.bias = cw.bias; a.y = y; a.CoutV = cw.Cout;
   a.LoutV = conv_out_len(Lin, cw.K, cw.stride);
   a.K = cw.K; a.stride = cw.stride; a.padL = (cw.K - 1) - (cw.stride - 1); a.pad_reflect = 1; a.act_in = act_in; a.res = res;
-  a.tcw = cw.tcw.valid ? &cw.tcw : nullptr;
+  a.tcw = cw.tcw.valid ? &cw.tcw : nullptr; a.tc_precise = h->tc_precise;
   h->launches++;
   return conv1d_f32_launch(a, B, st);
 }
@@ -731,7 +732,14 @@ int setup_pool(H* h, Bump& bp, int B, int T, Pool& pool, float** hbuf, float** c
   return 0;
 }
 
+int run_encoder_impl(H* h, const float* wav, int B, int T, float* z, Bump bp, cudaStream_t st);
 int run_encoder(H* h, const float* wav, int B, int T, float* z, Bump bp, cudaStream_t st) {
+  h->tc_precise = 1;            // the encoder output is quantised (argmin): its convs use the extra accumulator chains (codec_tc.cu)
+  const int rc = run_encoder_impl(h, wav, B, T, z, bp, st);
+  h->tc_precise = 0;
+  return rc;
+}
+int run_encoder_impl(H* h, const float* wav, int B, int T, float* z, Bump bp, cudaStream_t st) {
   Pool pool; float *hbuf, *cbuf;
   setup_pool(h, bp, B, T, pool, &hbuf, &cbuf);
   float* x = pool.get();

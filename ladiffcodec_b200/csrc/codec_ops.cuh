@@ -25,6 +25,7 @@ struct ConvF32Args {
   // virtual position i lands at y[b, co, i*il_s + ph - il_trim] if inside [0, il_lout).  il_s = 0: plain conv.
   int il_s, il_cout, il_trim, il_lout;
   const CodecTcWeights* tcw;   // optional: prepared tensor-core weights (null: FMA kernels only)
+  int tc_precise;              // 1: this conv feeds the vector quantiser (cond encoder): more accumulator chains (codec_tc.cu)
 };
 // planes: device buffer of 2*CinV*KT*CoutV floats (filled here from wt = the K-major copy of conv_w_transpose_launch)
 int codec_tc_prepare(const float* wt, int CinV, int KT, int CoutV, float* planes, CodecTcWeights* out, cudaStream_t st);

@@ -18,8 +18,8 @@
 //       start + tap*128 B: the swizzle is a function of the absolute shared-memory address)
 // CTA: warp 0 TMA producer (weights), warp 1 TMEM allocation + MMA issue, warps 2-9 fill then epilogue
 //      (tcgen05.ld -> shared [channel][T_T+1] -> coalesced, optionally phase-interleaved global stores with bias / residual).
-// The tensor core adds into its accumulator with truncation (a bias that grows with the chain length): consecutive K blocks
-// rotate over NCH accumulators which the epilogue adds in fp32.
+// The tensor core adds into its accumulator with truncation (a bias that grows with the chain length): the small products have
+// their own accumulator and, for the quantised encoder, the hi*hi products of consecutive K blocks rotate over three (see launcher).
 #include <cudaTypedefs.h>
 #include <stdlib.h>
 #include <string.h>
@@ -93,7 +93,7 @@ __device__ __forceinline__ float c_tf32_rna(float v) {
 struct CodecTcParams {
   ConvF32Args a;
   int S, KT, CinV, nkb;       // phases, taps, virtual input channels, K blocks of 32
-  int XS, WS, NCH;            // activation / weight ring depths, accumulator chains
+  int XS, WS, NHI;            // activation / weight ring depths; hi*hi accumulator chains (the small terms have their own: NHI + 1 in all)
 };
 
 __global__ void __launch_bounds__(CT_THREADS) codec_tc_kernel(const __grid_constant__ CodecTcParams p, const __grid_constant__ CUtensorMap tmW) {
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(CT_THREADS) codec_tc_kernel(const __grid_const
   uint8_t* smem_gen = ct_smem_raw + (smem_base - c_smem_u32(ct_smem_raw));
   const uint32_t x_ring = smem_base, w_ring = smem_base + (uint32_t)p.XS * CT_XSTAGE;
   const int b = blockIdx.z, co0 = blockIdx.y * CT_M, t0 = blockIdx.x * CT_N;
-  const uint32_t tmem_cols = (uint32_t)(CT_N * p.NCH);
+  const uint32_t tmem_cols = p.NHI == 1 ? 256u : 512u;
   const int KT = p.KT, nkb = p.nkb;
 
   if (threadIdx.x == 0) {
@@ -144,12 +144,13 @@ __global__ void __launch_bounds__(CT_THREADS) codec_tc_kernel(const __grid_const
     if (c_elect_one()) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CT_N >> 3) << 17) | ((uint32_t)(CT_M >> 4) << 24);
       int j = 0;
+      uint32_t acc_lo = 0u;
       for (int kb = 0; kb < nkb; ++kb) {
         const int xs = kb % p.XS;
         c_mbar_wait(&x_full[xs], ((uint32_t)(kb / p.XS)) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem = tmem_base + (uint32_t)((kb % p.NCH) * CT_N);
-        uint32_t accumulate = kb >= p.NCH ? 1u : 0u;
+        const uint32_t d_hi = tmem_base + (uint32_t)((kb % p.NHI) * CT_N), d_lo = tmem_base + (uint32_t)(p.NHI * CT_N);
+        uint32_t acc_hi = kb >= p.NHI ? 1u : 0u;
         const uint64_t bh = c_desc(x_ring + (uint32_t)xs * CT_XSTAGE), bl = c_desc(x_ring + (uint32_t)xs * CT_XSTAGE + CT_XPLANE);
         for (int k = 0; k < KT; ++k, ++j) {
           const int ws = j % p.WS;
@@ -159,10 +160,10 @@ __global__ void __launch_bounds__(CT_THREADS) codec_tc_kernel(const __grid_const
           const uint64_t roff = (uint64_t)(k * 8);            // tap = row shift of the activation tile: k * 128 B >> 4
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {                    // 8 tf32 = 32 B per K step
-            c_mma_tf32(d_tmem, al + 2 * kk, bh + roff + 2 * kk, idesc, accumulate);
-            c_mma_tf32(d_tmem, ah + 2 * kk, bl + roff + 2 * kk, idesc, 1u);
-            c_mma_tf32(d_tmem, ah + 2 * kk, bh + roff + 2 * kk, idesc, 1u);
-            accumulate = 1u;
+            c_mma_tf32(d_lo, al + 2 * kk, bh + roff + 2 * kk, idesc, acc_lo);
+            c_mma_tf32(d_lo, ah + 2 * kk, bl + roff + 2 * kk, idesc, 1u);
+            c_mma_tf32(d_hi, ah + 2 * kk, bh + roff + 2 * kk, idesc, acc_hi);
+            acc_lo = 1u; acc_hi = 1u;
           }
           c_commit(&w_empty[ws]);
         }
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(CT_THREADS) codec_tc_kernel(const __grid_const
     float* es = reinterpret_cast<float*>(smem_gen);
     {
       const int q = warp & 3, half = fw >> 2;                 // TMEM lane quadrant of this warp; column half
-      const int nch = nkb < p.NCH ? nkb : p.NCH;
+      const int nhi = nkb < p.NHI ? nkb : p.NHI;
       float* er = es + (q * 32 + lane) * CT_EPW + half * 64;
 #pragma unroll 1
       for (int c16 = 0; c16 < 4; ++c16) {
@@ -256,8 +257,8 @@ __global__ void __launch_bounds__(CT_THREADS) codec_tc_kernel(const __grid_const
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int i = 0; i < 16; ++i) s[i] = __uint_as_float(r[i]);
-        for (int ch = 1; ch < nch; ++ch) {
-          c_ld16(taddr + (uint32_t)(ch * CT_N), r);
+        for (int ch = 1; ch <= nhi; ++ch) {                  // the other hi chains, then the chain of the small terms
+          c_ld16(taddr + (uint32_t)((ch < nhi ? ch : p.NHI) * CT_N), r);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
           for (int i = 0; i < 16; ++i) s[i] += __uint_as_float(r[i]);
@@ -365,13 +366,21 @@ int codec_tc_launch(const ConvF32Args& a, int B, cudaStream_t st) {
   CodecTcParams p;
   memset(&p, 0, sizeof(p));
   p.a = a; p.S = S; p.KT = KT; p.CinV = CinV; p.nkb = cdiv(CinV, CT_KB);
-  static const char* env_nch = getenv("LADIFF_CODEC_TC_NCH");
-  p.NCH = env_nch ? atoi(env_nch) : 4;
-  if (p.NCH != 1 && p.NCH != 2 && p.NCH != 4) p.NCH = 4;
-  // short K loops: a single activation stage and two weight stages fit two CTAs per SM (prologue / epilogue of one overlaps the other)
-  const bool small = p.nkb * KT <= 8;
-  p.XS = small ? 1 : 2; p.WS = small ? 2 : 4;
-  if (small && p.NCH > 2) p.NCH = 2;
+  // Accumulator chains.  The tensor core adds into its fp32 accumulator with truncation: a bias of ~1e-4 abs at the encoder output
+  // with a single chain (measured; the FMA kernel: ~1e-5).  The two small products go to their own accumulator (their truncations
+  // are 2^-11 smaller), which leaves one truncating add per K step on the main chain: bias / 3.  Convs flagged `tc_precise` (the
+  // cond encoder: its output is quantised) with long K loops also rotate the hi*hi products over three accumulators (bias / 9;
+  // 512 TMEM columns, so one CTA per SM).
+  static const char* env_nhi = getenv("LADIFF_CODEC_TC_NHI");
+  p.NHI = (a.tc_precise && p.nkb * KT >= 16) ? 3 : 1;
+  if (env_nhi) p.NHI = atoi(env_nhi) == 3 ? 3 : 1;
+  // NHI = 1: two CTAs per SM (<= 112 KB each, 256 TMEM columns): the fill of one overlaps the MMAs / prologue / epilogue of the other,
+  // which measured better than one CTA with deeper rings on every codec layer (profiles/r2d/codec_tc_stage_sweep.txt); many taps per
+  // K block want the second weight stage, few taps the second activation stage.
+  if (p.NHI == 1) { p.XS = KT >= 3 ? 1 : 2; p.WS = KT >= 3 ? 2 : 1; }
+  else { p.XS = 2; p.WS = 4; }
+  static const char* env_cfg = getenv("LADIFF_CODEC_TC_CFG");      // "XS,WS" for experiments
+  if (env_cfg) sscanf(env_cfg, "%d,%d", &p.XS, &p.WS);
   size_t smem = (size_t)p.XS * CT_XSTAGE + (size_t)p.WS * CT_WSTAGE;
   const size_t epi = (size_t)CT_M * CT_EPW * sizeof(float);
   if (epi > smem) smem = epi;

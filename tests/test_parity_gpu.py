@@ -35,6 +35,8 @@ def test_cond_codec_codes_bit_exact(case):
     with torch.no_grad():
         cond_o, codes_o, z_o = O.get_cond(wav, case["sdc"], case["args"].cond_bandwidth, return_codes=True)
     z = c.encoder(wav.cuda()).cpu()
+    pc.record("cond_encoder_" + case["name"], max_abs_vs_oracle=(z - z_o).abs().max().item(), max_abs_vs_reference=(z - fx["enc_z"]).abs().max().item(),
+              z_absmax=z_o.abs().max().item())
     assert (z - z_o).abs().max().item() <= pc.TOL["codec_abs"]
     assert (z - fx["enc_z"]).abs().max().item() <= pc.TOL["codec_abs"]
     cond, codes = c.get_cond(wav.cuda(), return_codes=True)
