@@ -140,7 +140,7 @@ struct LadiffHandle {
   unsigned long long clip_offset = 0;   // global index of this handle's clip 0 (in-kernel noise is keyed by the global clip)
   int enc_hop = 1;
   EncoderW enc; DecoderW dec;
-  float* embed = nullptr; float* embed_sq = nullptr;
+  float* embed = nullptr; float* embed_sq = nullptr; float* embed_t = nullptr;
   UNetW un;
   std::vector<Plan*> plans;
   // tile shapes the autotuner picked, by conv signature: every plan of this handle (other workspaces, the second slot of a
@@ -428,6 +428,8 @@ int fold_codec(H* h) {
                      p.c_str());
     }
     TRY(rowsq_launch(h->embed, h->embed_sq, c.n_q * kBins, dim, 0));
+    TRY(dalloc(h, &h->embed_t, (size_t)c.n_q * kBins * dim));
+    TRY(rvq_transpose_launch(h->embed, h->embed_t, c.n_q, kBins, dim, 0));
   }
   return 0;
 }
@@ -1414,7 +1416,7 @@ extern "C" int32_t ladiff_rvq_encode(LadiffHandle* h, const float* z, int32_t n_
   LADIFF_REQUIRE(h->cfg.quantization, LADIFF_ERR_STATE, "this model has no quantizer");
   LADIFF_REQUIRE(z && n_q >= 1 && n_q <= h->cfg.n_q && B > 0 && F > 0, LADIFF_ERR_ARG, "ladiff_rvq_encode: n_q=%d", n_q);
   h->launches++;
-  return rvq_encode_launch(z, h->embed, h->embed_sq, n_q, kBins, h->cfg.rep_dims, B, F, quantized, (long long*)codes, st);
+  return rvq_encode_launch(z, h->embed, h->embed_t, h->embed_sq, n_q, kBins, h->cfg.rep_dims, B, F, quantized, (long long*)codes, st);
 }
 
 extern "C" int32_t ladiff_rvq_decode(LadiffHandle* h, const int64_t* codes, int32_t n_q, int32_t B, int32_t F, float* quantized,
@@ -1441,7 +1443,7 @@ extern "C" int32_t ladiff_get_cond(LadiffHandle* h, const float* wav, int32_t B,
     return 0;
   }
   h->launches++;
-  return rvq_encode_launch(z, h->embed, h->embed_sq, h->cfg.n_q_used, kBins, h->cfg.rep_dims, B, F, cond, (long long*)codes, st);
+  return rvq_encode_launch(z, h->embed, h->embed_t, h->embed_sq, h->cfg.n_q_used, kBins, h->cfg.rep_dims, B, F, cond, (long long*)codes, st);
 }
 
 extern "C" int32_t ladiff_upsample_layer(LadiffHandle* h, int32_t i, const float* x, int32_t B, int32_t Lin, float* y, void* stream) {

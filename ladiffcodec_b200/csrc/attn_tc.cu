@@ -437,6 +437,158 @@ __global__ void __launch_bounds__(LT_THREADS) linattn_tail_kernel(ClView qkv, co
   if (warp == 16) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
+// ------------------------------------------------------------------ linear attention, second half, on tcgen05
+// out[n, h*32 + e] = sum_d softmax_d(q[n, h, :])[d] ctx[h][d][e]   (unet.py:214-221) as D[128 positions, 32 e] = P[128, 32 d] C_h^T per head.
+// The SIMT kernel (linattn_out_kernel) spends 1024 FMA + 256 LDS per (position, head); here the thread only does the softmax of its
+// (position, head) row and stores it as the A operand.  Both operands are split  v = hi + lo  in the 16-bit type and the product is
+// three MMAs (lo*hi + hi*lo + hi*hi, fp32 in TMEM): the result keeps the accuracy of the fp32 kernel (ctx and the probabilities are
+// not rounded to 11 bits), at 6 K=16 instructions per head.
+// CTA = 128 positions of one clip; warp w < 16: head w >> 2, rows 32 (w & 3) + lane (= its TMEM lane quadrant); warp 16: TMEM + MMA.
+// Shared memory (SWIZZLE_128B K-major, two 128-byte atoms per row: heads 0-1, heads 2-3): P hi / lo [2][2][128 rows], C^T hi / lo [2][2][32 rows].
+constexpr int LO_THREADS = 544;
+constexpr uint32_t LO_A = 0, LO_B = 65536, LO_SMEM = 65536 + 16384 + 1024;
+
+__global__ void __launch_bounds__(LO_THREADS) linattn_out_tc_kernel(ClView qkv, const float* __restrict__ ctx, ClView out, int L) {
+  extern __shared__ uint8_t lo_raw[];
+  __shared__ __align__(8) uint64_t m_bar;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int b = blockIdx.y, n0 = blockIdx.x * 128;
+  const uint32_t sbase = (a_smem_u32(lo_raw) + 1023u) & ~1023u;
+  if (tid == 0) {
+    a_mbar_init(&m_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 16) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(a_smem_u32(&tmem_base_s)), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  pdl_wait();
+  pdl_trigger();
+  const int h = warp >> 2, r = (warp & 3) * 32 + lane, n = n0 + r;
+  if (warp < 16) {
+    uint4 qraw[4];
+    if (n < L) {
+      const h16* qr = qkv.p + (long long)b * qkv.bstride + (long long)n * qkv.pitch + h * 32;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) qraw[i] = __ldcg(reinterpret_cast<const uint4*>(qr + 8 * i));
+    }
+    {
+      // C_h^T: thread = (head, e, eight d): B operand row e, bytes (head & 1) * 64 + 2 d
+      const int hh = tid >> 7, e = (tid >> 2) & 31, oct = tid & 3;
+      const float* cp = ctx + (long long)b * 4096 + hh * 1024 + (oct * 8) * 32 + e;
+      float c[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) c[j] = __ldcg(cp + j * 32);
+      uint4 hi4, lo4;
+      h162* hp = reinterpret_cast<h162*>(&hi4);
+      h162* lp = reinterpret_cast<h162*>(&lo4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const h162 hv = ff2h2(c[2 * j], c[2 * j + 1]);
+        const float2 hf = h22ff(hv);
+        hp[j] = hv;
+        lp[j] = ff2h2(c[2 * j] - hf.x, c[2 * j + 1] - hf.y);
+      }
+      const uint32_t off = (uint32_t)(hh >> 1) * 4096u + sw128((uint32_t)e, (uint32_t)((hh & 1) * 4 + oct));
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + LO_B + off), "r"(hi4.x), "r"(hi4.y), "r"(hi4.z), "r"(hi4.w) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + LO_B + 8192u + off), "r"(lo4.x), "r"(lo4.y), "r"(lo4.z), "r"(lo4.w) : "memory");
+    }
+    uint4 ph4[4], pl4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { ph4[i] = make_uint4(0u, 0u, 0u, 0u); pl4[i] = make_uint4(0u, 0u, 0u, 0u); }
+    if (n < L) {
+      float q[32];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const h162* hp = reinterpret_cast<const h162*>(&qraw[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 f = h22ff(hp[j]); q[8 * i + 2 * j] = f.x; q[8 * i + 2 * j + 1] = f.y; }
+      }
+      float mx = q[0];
+#pragma unroll
+      for (int i = 1; i < 32; ++i) mx = fmaxf(mx, q[i]);
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { q[i] = __expf(q[i] - mx); sum += q[i]; }
+      const float inv = 1.f / sum;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        h162* hp = reinterpret_cast<h162*>(&ph4[i]);
+        h162* lp = reinterpret_cast<h162*>(&pl4[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float p0 = q[8 * i + 2 * j] * inv, p1 = q[8 * i + 2 * j + 1] * inv;
+          const h162 hv = ff2h2(p0, p1);
+          const float2 hf = h22ff(hv);
+          hp[j] = hv;
+          lp[j] = ff2h2(p0 - hf.x, p1 - hf.y);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t off = (uint32_t)(h >> 1) * 16384u + sw128((uint32_t)r, (uint32_t)((h & 1) * 4 + i));
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + LO_A + off), "r"(ph4[i].x), "r"(ph4[i].y), "r"(ph4[i].z), "r"(ph4[i].w) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + LO_A + 32768u + off), "r"(pl4[i].x), "r"(pl4[i].y), "r"(pl4[i].z), "r"(pl4[i].w) : "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 16) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (a_elect_one()) {
+      const uint32_t idesc = (1u << 4) | (TC_IDESC_AB_FMT << 7) | (TC_IDESC_AB_FMT << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+#pragma unroll
+      for (int hh = 0; hh < 4; ++hh) {
+        const uint32_t ao = sbase + LO_A + (uint32_t)(hh >> 1) * 16384u + (uint32_t)(hh & 1) * 64u;
+        const uint32_t bo = sbase + LO_B + (uint32_t)(hh >> 1) * 4096u + (uint32_t)(hh & 1) * 64u;
+        const uint64_t ah = a_desc(ao), al = a_desc(ao + 32768u), bh = a_desc(bo), bl = a_desc(bo + 8192u);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          a_mma(tmem + (uint32_t)hh * 32u, al + 2 * k, bh + 2 * k, idesc, k ? 1u : 0u);
+          a_mma(tmem + (uint32_t)hh * 32u, ah + 2 * k, bl + 2 * k, idesc, 1u);
+          a_mma(tmem + (uint32_t)hh * 32u, ah + 2 * k, bh + 2 * k, idesc, 1u);
+        }
+      }
+      a_commit(&m_bar);
+    }
+    __syncwarp();
+  }
+  a_mbar_wait(&m_bar, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (warp < 16) {
+    uint32_t r0[16], r1[16];
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)h * 32u;
+    a_ld16(taddr, r0); a_ld16(taddr + 16u, r1);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (n < L) {
+      h16* orow = out.p + (long long)b * out.bstride + (long long)n * out.pitch + h * 32;
+      uint4 o[4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        h162* hp0 = reinterpret_cast<h162*>(&o[i]);
+        h162* hp1 = reinterpret_cast<h162*>(&o[2 + i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          hp0[j] = ff2h2(__uint_as_float(r0[8 * i + 2 * j]), __uint_as_float(r0[8 * i + 2 * j + 1]));
+          hp1[j] = ff2h2(__uint_as_float(r1[8 * i + 2 * j]), __uint_as_float(r1[8 * i + 2 * j + 1]));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(orow + 8 * i) = o[i];
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 16) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
+}
+
 }  // namespace
 
 int fullattn_tc_launch(ClView qkv, ClView out, int B, int L, cudaStream_t st) {
@@ -461,5 +613,16 @@ int linattn_tail_launch(ClView qkv, const float* ctx, const h16* wout, const flo
   }
   LADIFF_CUDA_OK(launch_pdl(linattn_tail_kernel, dim3(cdiv(L, 128), B), dim3(LT_THREADS), (size_t)LT_SMEM, st, qkv, ctx, wout, bias, gain, xres,
                             out, L, C));
+  return 0;
+}
+
+int linattn_out_tc_launch(ClView qkv, const float* ctx, ClView out, int B, int L, cudaStream_t st) {
+  LADIFF_REQUIRE(qkv.pitch % 8 == 0 && out.pitch % 8 == 0, LADIFF_ERR_ARG, "linattn_out_tc: pitch %d %d", qkv.pitch, out.pitch);
+  static unsigned long long attr = 0;
+  if (ladiff_first_on_device(&attr)) {
+    LADIFF_CUDA_OK(cudaFuncSetAttribute(linattn_out_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LO_SMEM));
+    prefer_max_smem_carveout(linattn_out_tc_kernel);
+  }
+  LADIFF_CUDA_OK(launch_pdl(linattn_out_tc_kernel, dim3(cdiv(L, 128), B), dim3(LO_THREADS), (size_t)LO_SMEM, st, qkv, ctx, out, L));
   return 0;
 }

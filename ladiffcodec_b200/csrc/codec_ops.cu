@@ -793,9 +793,13 @@ __global__ void __launch_bounds__(256, 1) lstm_persist_kernel(const float* __res
 // ------------------------------------------------------------------ RVQ
 // 8 frames per CTA, 256 threads; residual kept in smem across the n_q stages
 constexpr int RVQ_FR = 8;
+// embed_t [n_q][D][bins] is the transposed codebook: lanes (consecutive codewords) read consecutive addresses.  (Reading codeword
+// rows from embed [bins][D] made every warp load touch 32 lines: 670 us at config 2; the sums below are the same fma chains in the
+// same order, so the codes are bit-identical.)
 __global__ void __launch_bounds__(256) rvq_encode_kernel(const float* __restrict__ z, const float* __restrict__ embed,
-                                                         const float* __restrict__ embed_sq, int n_q, int bins, int D, int B, int F,
-                                                         float* __restrict__ quantized, long long* __restrict__ codes) {
+                                                         const float* __restrict__ embed_t, const float* __restrict__ embed_sq, int n_q,
+                                                         int bins, int D, int B, int F, float* __restrict__ quantized,
+                                                         long long* __restrict__ codes) {
   extern __shared__ __align__(16) float sm[];
   float* res = sm;                    // [FR][D]
   float* outv = sm + RVQ_FR * D;      // [FR][D]
@@ -827,24 +831,41 @@ __global__ void __launch_bounds__(256) rvq_encode_kernel(const float* __restrict
     float bv[RVQ_FR]; int bi[RVQ_FR];
 #pragma unroll
     for (int f = 0; f < RVQ_FR; ++f) { bv[f] = -INFINITY; bi[f] = 0x7fffffff; }
-    for (int jc = tid; jc < bins; jc += 256) {
-      float dot[RVQ_FR];
+    const float* ET = embed_t + (long long)q * bins * D;
+    for (int jc0 = tid; jc0 < bins; jc0 += 1024) {           // four codewords per thread per sweep over d: jc0 + 256 c
+      float dot[4][RVQ_FR];
 #pragma unroll
-      for (int f = 0; f < RVQ_FR; ++f) dot[f] = 0.f;
-      const float4* e4 = reinterpret_cast<const float4*>(E + (long long)jc * D);
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int f = 0; f < RVQ_FR; ++f) dot[c][f] = 0.f;
       for (int d4 = 0; d4 < D / 4; ++d4) {
-        const float4 e = e4[d4];
+        float4 r[RVQ_FR];
 #pragma unroll
-        for (int f = 0; f < RVQ_FR; ++f) {
-          const float4 r = *reinterpret_cast<const float4*>(res + f * D + 4 * d4);
-          dot[f] += r.x * e.x; dot[f] += r.y * e.y; dot[f] += r.z * e.z; dot[f] += r.w * e.w;
-        }
+        for (int f = 0; f < RVQ_FR; ++f) r[f] = *reinterpret_cast<const float4*>(res + f * D + 4 * d4);
+        float e[4][4];
+#pragma unroll
+        for (int dd = 0; dd < 4; ++dd)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) e[dd][c] = (jc0 + 256 * c < bins) ? __ldg(ET + (long long)(4 * d4 + dd) * bins + jc0 + 256 * c) : 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int f = 0; f < RVQ_FR; ++f) {
+            dot[c][f] = fmaf(r[f].x, e[0][c], dot[c][f]); dot[c][f] = fmaf(r[f].y, e[1][c], dot[c][f]);
+            dot[c][f] = fmaf(r[f].z, e[2][c], dot[c][f]); dot[c][f] = fmaf(r[f].w, e[3][c], dot[c][f]);
+          }
       }
-      const float ee = ES[jc];
 #pragma unroll
-      for (int f = 0; f < RVQ_FR; ++f) {
-        const float dist = -((xx[f] - 2.f * dot[f]) + ee);      // core_vq.py:176-180
-        if (dist > bv[f]) { bv[f] = dist; bi[f] = jc; }          // ascending jc per thread: first max kept
+      for (int c = 0; c < 4; ++c) {
+        const int jc = jc0 + 256 * c;
+        if (jc < bins) {
+          const float ee = ES[jc];
+#pragma unroll
+          for (int f = 0; f < RVQ_FR; ++f) {
+            const float dist = -((xx[f] - 2.f * dot[c][f]) + ee);      // core_vq.py:176-180
+            if (dist > bv[f]) { bv[f] = dist; bi[f] = jc; }            // ascending jc per thread: first max kept
+          }
+        }
       }
     }
 #pragma unroll
@@ -1165,12 +1186,27 @@ int lstm_steps_launch(const float* pre, const float* whh, const float* skip, flo
   return 0;
 }
 
-int rvq_encode_launch(const float* z, const float* embed, const float* embed_sq, int n_q, int bins, int D, int B, int F,
+__global__ void rvq_transpose_kernel(const float* __restrict__ e, float* __restrict__ et, int n_q, int bins, int D) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n_q * bins * D) return;
+  const int j = (int)(i % bins);
+  const long long r = i / bins;
+  const int d = (int)(r % D), q = (int)(r / D);
+  et[i] = e[((long long)q * bins + j) * D + d];
+}
+int rvq_transpose_launch(const float* embed, float* embed_t, int n_q, int bins, int D, cudaStream_t st) {
+  const long long total = (long long)n_q * bins * D;
+  rvq_transpose_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(embed, embed_t, n_q, bins, D);
+  LADIFF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int rvq_encode_launch(const float* z, const float* embed, const float* embed_t, const float* embed_sq, int n_q, int bins, int D, int B, int F,
                       float* quantized, long long* codes, cudaStream_t st) {
   LADIFF_REQUIRE(D % 4 == 0 && D <= 512, LADIFF_ERR_ARG, "rvq: D=%d", D);
   const long long NF = (long long)B * F;
   const size_t smem = (size_t)2 * RVQ_FR * D * sizeof(float);
-  rvq_encode_kernel<<<(unsigned)((NF + RVQ_FR - 1) / RVQ_FR), 256, smem, st>>>(z, embed, embed_sq, n_q, bins, D, B, F, quantized, codes);
+  rvq_encode_kernel<<<(unsigned)((NF + RVQ_FR - 1) / RVQ_FR), 256, smem, st>>>(z, embed, embed_t, embed_sq, n_q, bins, D, B, F, quantized, codes);
   LADIFF_CUDA_OK(cudaGetLastError());
   return 0;
 }

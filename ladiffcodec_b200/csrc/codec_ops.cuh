@@ -56,8 +56,10 @@ size_t lstm_persist_scratch_floats(int B, int H);
 
 // Residual VQ (core_vq.py:174-189, 324-362).  z [B][D][F] -> quantized [B][D][F] (nullable), codes [n_q][B][F] int64 (nullable)
 // embed [n_q][bins][D], embed_sq [n_q][bins] = sum_d e^2
-int rvq_encode_launch(const float* z, const float* embed, const float* embed_sq, int n_q, int bins, int D, int B, int F,
+// embed_t [n_q][D][bins]: transposed copy (rvq_transpose_launch) for coalesced codeword sweeps
+int rvq_encode_launch(const float* z, const float* embed, const float* embed_t, const float* embed_sq, int n_q, int bins, int D, int B, int F,
                       float* quantized, long long* codes, cudaStream_t st);
+int rvq_transpose_launch(const float* embed, float* embed_t, int n_q, int bins, int D, cudaStream_t st);
 int rvq_decode_launch(const long long* codes, const float* embed, int n_q, int bins, int D, int B, int F, float* quantized,
                       cudaStream_t st);
 int rowsq_launch(const float* e, float* sq, int rows, int D, cudaStream_t st);

@@ -996,6 +996,8 @@ int linattn_launch(ClView qkv, float* ctx, float* part, int* counters, ClView ou
   LADIFF_CARVEOUT_ONCE(linattn_ctx_kernel);
   LADIFF_CARVEOUT_ONCE(linattn_out_kernel);
   LADIFF_CUDA_OK(launch_pdl(linattn_ctx_kernel, dim3(ns, 4, B), dim3(256), 0, st, qkv, ctx, part, counters, L, S, ns));
+  static const bool out_simt = getenv("LADIFF_LINATTN_OUT_SIMT") != nullptr;       // ablation: the fp32 FMA kernel
+  if (!out_simt && qkv.pitch % 8 == 0 && out.pitch % 8 == 0) return linattn_out_tc_launch(qkv, ctx, out, B, L, st);
   LADIFF_CUDA_OK(launch_pdl(linattn_out_kernel, dim3(cdiv(L, 64), B), dim3(256), 0, st, qkv, (const float*)ctx, out, L));
   return 0;
 }

@@ -41,6 +41,8 @@ size_t linattn_part_floats(int B, int L);
 // the two halves separately: context only, and (csrc/attn_tc.cu) everything after it in one kernel — ctx^T softmax(q), the to_out 1x1
 // conv on tcgen05, channel LayerNorm and the residual:  out = LN(W_out (ctx^T q~) + b) g + xres
 int linattn_ctx_launch(ClView qkv, float* ctx, float* part, int* counters, int B, int L, cudaStream_t st);
+// second half of the linear attention on tcgen05 (attn_tc.cu): out = softmax_d(q) ctx, split operands, fp32-kernel accuracy
+int linattn_out_tc_launch(ClView qkv, const float* ctx, ClView out, int B, int L, cudaStream_t st);
 int linattn_tail_launch(ClView qkv, const float* ctx, const h16* wout, const float* bias, const float* gain, ClView xres, ClView out, int B,
                         int L, int C, cudaStream_t st);
 // Attention core (mid block)                                    unet.py:234-245

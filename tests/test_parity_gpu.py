@@ -68,6 +68,7 @@ def test_cond_upsamplers(case):
         img = layer(img)
     with torch.no_grad():
         img_o = O.cond_upsample(fx["cond"], case["sdm"], args.upsampling_ratios)
+    pc.record("cond_upsample_" + case["name"], max_abs_vs_oracle=(img.cpu() - img_o).abs().max().item(), absmax=img_o.abs().max().item())
     assert (img.cpu() - img_o).abs().max().item() <= pc.TOL["upsample_abs"]
     assert (img.cpu()[:, ::4, ::4] - fx["img_raw_sub"]).abs().max().item() <= pc.TOL["upsample_abs"]
 
@@ -164,6 +165,7 @@ def test_decoder(case):
     with torch.no_grad():
         d_o = O.seanet_decoder(img, case["sdm"], list(args.enc_ratios))
     d = m.decoder(img.cuda()).cpu()
+    pc.record("decoder_" + case["name"], max_abs_vs_oracle=(d - d_o).abs().max().item(), absmax=d_o.abs().max().item())
     assert (d - d_o).abs().max().item() <= pc.TOL["codec_abs"]
 
 
@@ -520,3 +522,39 @@ def test_fused_linear_attention_tail_operator_level():
     assert r.returncode == 0, r.stderr[-2000:]
     rel = float([l for l in r.stdout.splitlines() if l.startswith("REL")][0].split()[1])
     assert rel <= pc.TOL["unet_rel_l2"], rel
+
+
+@pytest.mark.gpu
+def test_codec_fma_kernels_against_tensor_core_path(case):
+    """The codec's two conv implementations against each other and the oracle: the default tcgen05 3xTF32 kernel (codec_tc.cu) in this
+    process, the fp32 FMA kernels (LADIFF_CODEC_SIMT=1, read once per process) in a subprocess.  Both must give the reference's RVQ
+    codes; the encoder / decoder outputs of the two must agree within the codec tolerance."""
+    import os, subprocess, sys, tempfile
+    if case["name"] != "B_3kbps":
+        pytest.skip("one layout is enough for the A/B of the two implementations")
+    c, m, wav = case["c"], case["m"], case["wav"]
+    img, _ = _unet_inputs(case)
+    z_tc = c.encoder(wav.cuda()).cpu()
+    _, codes_tc = c.get_cond(wav.cuda(), return_codes=True)
+    d_tc = m.decoder(img.cuda()).cpu()
+    with tempfile.TemporaryDirectory() as td:
+        out = os.path.join(td, "fma.pt")
+        code = (
+            "import sys, torch; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import parity_common as pc\n"
+            "fx, args, sdm, sdc, wav, noise = pc.case_setup('B_3kbps')\n"
+            "m, c = pc.cuda_models(args, sdm, sdc)\n"
+            "img = pc.normalized_img(fx['cond'], sdm, args)\n"
+            "z = c.encoder(wav.cuda()).cpu()\n"
+            "_, codes = c.get_cond(wav.cuda(), return_codes=True)\n"
+            "d = m.decoder(img.cuda()).cpu()\n"
+            "torch.save(dict(z=z, codes=codes.cpu(), d=d), %r)\n"
+        ) % (pc.ROOT, os.path.join(pc.ROOT, "tests"), out)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=dict(os.environ, LADIFF_CODEC_SIMT="1"))
+        assert r.returncode == 0, r.stderr[-2000:]
+        fma = torch.load(out)
+    pc.record("codec_tensor_core_vs_fma", encoder_max_abs=(z_tc - fma["z"]).abs().max().item(), decoder_max_abs=(d_tc - fma["d"]).abs().max().item())
+    assert torch.equal(codes_tc.cpu(), fma["codes"])
+    assert torch.equal(codes_tc.cpu().to(torch.int16), case["fx"]["codes"])
+    assert (z_tc - fma["z"]).abs().max().item() <= pc.TOL["codec_abs"]
+    assert (d_tc - fma["d"]).abs().max().item() <= pc.TOL["codec_abs"]
