@@ -42,7 +42,7 @@ CONFIGS = {
     5: dict(name="config5: B=128, 3 kbps, README layout (L=4800), DDPM step sweep",
             flags=dict(LAYOUT_A, cond_bandwidth=3.0), batch=128, n_steps=50, scaling="weak", sweep=[10, 50, 200, 1000]),
 }
-PARITY_REPORT = os.path.join(ROOT, "profiles", "r2a", "parity_report_f16.json")
+PARITY_REPORT = os.path.join(ROOT, "profiles", "r2d", "parity_report_f16.json")
 
 
 def peaks():
@@ -181,10 +181,12 @@ def parity_block(dtype):
     if dtype == "f16" and os.path.exists(PARITY_REPORT):
         r = json.load(open(PARITY_REPORT))
         g = lambda k, f: r.get(k, {}).get(f)
-        blk.update(source="profiles/r2a/parity_report_f16.json (tests/test_parity_long_gpu.py on one B200, CUDA path vs the fp32 oracle and "
+        blk.update(source="profiles/r2d/parity_report_f16.json (tests/test_parity_gpu.py + test_parity_long_gpu.py on one B200, final build, CUDA path vs the fp32 oracle and "
                           "vs vectors of the real reference, same pre-drawn noise)",
                    unet_eval_rel_l2_config2_full_size=g("config2_full_size", "unet_rel_l2_2_of_32_clips"),
                    rvq_code_mismatches_config2_full_size=g("config2_full_size", "code_mismatches"),
+                   codec_max_abs=dict(cond_encoder=g("cond_encoder_B_3kbps", "max_abs_vs_reference"), cond_upsample=g("cond_upsample_B_3kbps", "max_abs_vs_oracle"),
+                                      decoder=g("decoder_B_3kbps", "max_abs_vs_oracle")),
                    n50_layout_b=dict(latent_rel_l2=g("halfway_B_N50", "latent_rel_l2_vs_reference"), wav_snr_db=g("halfway_B_N50", "wav_snr_db_vs_reference")),
                    n200_layout_a=dict(latent_rel_l2=g("halfway_A_N200", "latent_rel_l2_vs_reference"), wav_snr_db=g("halfway_A_N200", "wav_snr_db_vs_reference")),
                    n1000_from_noise=dict(latent_rel_l2=g("sample_full1000", "latent_rel_l2_vs_reference"), wav_snr_db=g("sample_full1000", "wav_snr_db_vs_reference")),
