@@ -381,6 +381,9 @@ int codec_tc_launch(const ConvF32Args& a, int B, cudaStream_t st) {
   else { p.XS = 2; p.WS = 4; }
   static const char* env_cfg = getenv("LADIFF_CODEC_TC_CFG");      // "XS,WS" for experiments
   if (env_cfg) sscanf(env_cfg, "%d,%d", &p.XS, &p.WS);
+  p.XS = p.XS < 1 ? 1 : (p.XS > CT_MAXS ? CT_MAXS : p.XS);
+  p.WS = p.WS < 1 ? 1 : (p.WS > CT_MAXS ? CT_MAXS : p.WS);
+  while ((size_t)p.XS * CT_XSTAGE + (size_t)p.WS * CT_WSTAGE > 216 * 1024) { if (p.WS > 1) --p.WS; else --p.XS; }
   size_t smem = (size_t)p.XS * CT_XSTAGE + (size_t)p.WS * CT_WSTAGE;
   const size_t epi = (size_t)CT_M * CT_EPW * sizeof(float);
   if (epi > smem) smem = epi;
