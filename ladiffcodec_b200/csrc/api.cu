@@ -50,10 +50,10 @@ struct KeySpec {
 };
 
 // ---- folded codec parameters
-struct ConvW { const float* w = nullptr; const float* wt = nullptr; const float* bias = nullptr; int Cout = 0, Cin = 0, K = 0, stride = 1; CodecTcWeights tcw; };
+struct ConvW { const float* w = nullptr; const float* wt = nullptr; const float* bias = nullptr; int Cout = 0, Cin = 0, K = 0, stride = 1; CodecTcWeights tcw; int precise = 0; };
 struct ConvTrW { const float* w2 = nullptr; const float* wt = nullptr; const float* bias = nullptr; int Cin = 0, Cout = 0, s = 1; CodecTcWeights tcw; };
 struct ResBlockW { ConvW c1, c2, sc; };
-struct LstmW { int H = 0, layers = 0; const float* wih[4]; const float* wih_t[4]; const float* whh[4]; const float* bias[4]; CodecTcWeights tcw[4]; };
+struct LstmW { int H = 0, layers = 0; const float* wih[4]; const float* wih_t[4]; const float* whh[4]; const float* bias[4]; CodecTcWeights tcw[4]; int precise = 0; };
 struct EncoderW { ConvW first, last; std::vector<ResBlockW> rb; std::vector<ConvW> down; LstmW lstm; };
 struct DecoderW { ConvW first, last; std::vector<ConvTrW> up; std::vector<ResBlockW> rb; LstmW lstm; };
 
@@ -136,7 +136,6 @@ struct LadiffHandle {
   int profiling = 0;
   Plan* last_plan = nullptr;
   long long launches = 0;
-  int tc_precise = 0;   // set while the cond encoder runs (run_encoder): codec convs then use the extra accumulator chains
   unsigned long long clip_offset = 0;   // global index of this handle's clip 0 (in-kernel noise is keyed by the global clip)
   int enc_hop = 1;
   EncoderW enc; DecoderW dec;
@@ -400,6 +399,10 @@ int fold_codec(H* h) {
     if (c.lstm_layers) TRY(fold_lstm(h, M("encoder", i++), mult * nf, c.lstm_layers, &h->enc.lstm));
     i++;
     TRY(fold_wn_conv(h, M("encoder", i), dim, mult * nf, 7, 1, &h->enc.last));
+    // the encoder output is quantised (argmin over codewords): its tensor-core convs use the extra accumulator chains (codec_tc.cu)
+    h->enc.first.precise = h->enc.last.precise = h->enc.lstm.precise = 1;
+    for (auto& d : h->enc.down) d.precise = 1;
+    for (auto& rb : h->enc.rb) rb.c1.precise = rb.c2.precise = rb.sc.precise = 1;
   }
   {
     int i = 0, mult = 1 << nr;
@@ -648,7 +651,7 @@ int run_conv(H* h, const ConvW& cw, const float* x, int Lin, float* y, int act_i
   a.x = x; a.Cin = cw.Cin; a.Lin = Lin; a.w = cw.w; a.wt = cw.wt; a.bias = cw.bias; a.y = y; a.CoutV = cw.Cout;
   a.LoutV = conv_out_len(Lin, cw.K, cw.stride);
   a.K = cw.K; a.stride = cw.stride; a.padL = (cw.K - 1) - (cw.stride - 1); a.pad_reflect = 1; a.act_in = act_in; a.res = res;
-  a.tcw = cw.tcw.valid ? &cw.tcw : nullptr; a.tc_precise = h->tc_precise;
+  a.tcw = cw.tcw.valid ? &cw.tcw : nullptr; a.tc_precise = cw.precise;
   h->launches++;
   return conv1d_f32_launch(a, B, st);
 }
@@ -692,7 +695,7 @@ int run_lstm(H* h, const LstmW& lw, float*& x, int T, Pool& pool, float* hbuf, f
   float* pre = pool.get();
   float* y = nullptr;
   for (int l = 0; l < lw.layers; ++l) {
-    ConvW ip; ip.w = lw.wih[l]; ip.wt = lw.wih_t[l]; ip.bias = lw.bias[l]; ip.Cout = 4 * lw.H; ip.Cin = lw.H; ip.K = 1; ip.stride = 1; ip.tcw = lw.tcw[l];
+    ConvW ip; ip.w = lw.wih[l]; ip.wt = lw.wih_t[l]; ip.bias = lw.bias[l]; ip.Cout = 4 * lw.H; ip.Cin = lw.H; ip.K = 1; ip.stride = 1; ip.tcw = lw.tcw[l]; ip.precise = lw.precise;
     TRY(run_conv(h, ip, in, T, pre, 0, nullptr, B, st));
     y = pool.get();
     const float* skip = (l == lw.layers - 1) ? x : nullptr;
@@ -734,14 +737,7 @@ int setup_pool(H* h, Bump& bp, int B, int T, Pool& pool, float** hbuf, float** c
   return 0;
 }
 
-int run_encoder_impl(H* h, const float* wav, int B, int T, float* z, Bump bp, cudaStream_t st);
 int run_encoder(H* h, const float* wav, int B, int T, float* z, Bump bp, cudaStream_t st) {
-  h->tc_precise = 1;            // the encoder output is quantised (argmin): its convs use the extra accumulator chains (codec_tc.cu)
-  const int rc = run_encoder_impl(h, wav, B, T, z, bp, st);
-  h->tc_precise = 0;
-  return rc;
-}
-int run_encoder_impl(H* h, const float* wav, int B, int T, float* z, Bump bp, cudaStream_t st) {
   Pool pool; float *hbuf, *cbuf;
   setup_pool(h, bp, B, T, pool, &hbuf, &cbuf);
   float* x = pool.get();
