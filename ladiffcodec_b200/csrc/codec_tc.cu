@@ -5,8 +5,10 @@
 // The codec feeds a vector quantiser (argmin over 1024 codewords, quantization/core_vq.py), so 10-bit operands are not an option;
 // every fp32 value is split  v = hi + lo  (hi = rna_tf32(v), lo = rna_tf32(v - hi)) and  x*w ~= lo*hi + hi*lo + hi*hi  is three
 // kind::tf32 MMAs into the same fp32 TMEM accumulator (dropped lo*lo term and the rounding of lo: <= 2^-22 relative, unbiased).
-// (mma.sync TF32 was measured first: HMMA.1688.F32.TF32 sustains only ~55-60 TFLOP/s on B200, so 3xTF32 through it is no faster
-//  than the FMA kernel; tcgen05 kind::tf32 is the only fast path.)
+// (A first version on mma.sync (HMMA.1688.F32.TF32, operands fetched from shared memory with LDS) reached 55-60 TFLOP/s of TF32,
+//  i.e. the speed of the FMA kernel once divided by three.  The instruction itself peaks at 278 TFLOP/s with register operands
+//  (profiles/ubench/mma_sync_rate.cu), a quarter of tcgen05 kind::tf32's nominal rate - and tcgen05 reads both operands from
+//  shared memory with no register traffic at all, which is what a conv whose operands must be transposed and split needs.)
 //
 // Formulation (as conv1d_f32_v2_kernel): a conv of stride S with K = KT*S taps is a stride-1 conv with KT taps over the S "phase
 // channels" of every input channel: cv = ci*S + p,  xv[cv][u] = xpad[ci][u*S + p - padL];  transposed convs arrive here as
